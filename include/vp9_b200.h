@@ -1,0 +1,217 @@
+/*
+ * vp9_b200.h -- C ABI of the B200-native VP9 decode-reconstruction engine.
+ *
+ * This is the drop-in boundary that takes the role of the reference's
+ *     extern "C" wrap_cuda_inter_prediction / wrap_cuda_intra_prediction
+ *     (vpx-master/cuda_extern_wrap.cpp:5-17, declared vp9_decodeframe.c:2299-2302,
+ *      called vp9_decodeframe.c:2546,2564)
+ * but with plain pointers and sizes only -- no libvpx types cross it.  Three layers:
+ *
+ *   1. vp9gpu_*   reconstruction context: device frame pool + "one packed buffer per frame"
+ *                 (SURVEY.md section 8(b)).  A libvpx host calls this once per frame from
+ *                 decode_tiles() after parsing all tiles (INTEGRATION.md shows the stub).
+ *   2. vp9b_parser_*   host bitstream parser that produces the packed buffer (role of
+ *                 vp9_read_mode_info / vp9_decode_block_tokens / vp9_build_mask,
+ *                 vp9_decodemv.c:811, vp9_detokenize.c:274, vp9_loopfilter.c:1528).
+ *   3. vp9b_decoder_*  whole decoder = parser + gpu ctx; mirrors vpx_codec_decode /
+ *                 vpx_codec_get_frame (vpx/src/vpx_decoder.c:104,  vp9_dx_iface.c:331,399).
+ *
+ * All functions return 0 on success and a negative VP9B_ERR_* otherwise; nothing aborts.
+ */
+#ifndef VP9_B200_H_
+#define VP9_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VP9B_MAGIC 0x39425056u /* "VPB9" */
+#define VP9B_NUM_SLOTS 12      /* device frame pool: 8 refs + current + held output + spare */
+
+enum {
+  VP9B_OK = 0,
+  VP9B_ERR_INVALID = -1,     /* bad argument / corrupt packed buffer            */
+  VP9B_ERR_UNSUP = -2,       /* unsupported bitstream feature (e.g. 4:2:2 LPF)  */
+  VP9B_ERR_CORRUPT = -3,     /* corrupt bitstream                                */
+  VP9B_ERR_CUDA = -4,        /* CUDA runtime error (see *_last_error)           */
+  VP9B_ERR_MEM = -5,
+  VP9B_ERR_NOGPU = -6        /* library built without / run without a CUDA device */
+};
+
+/* ------------------------------------------------------------------ packed frame buffer --- */
+/* Section ids of the packed per-frame buffer ("one packed SoA buffer", BASELINE north_star). */
+enum {
+  VP9B_SEC_BLOCKS = 0,   /* vp9b_block[]      every prediction block in decode order          */
+  VP9B_SEC_SUBMV = 1,    /* vp9b_submv[]      MVs of sub-8x8 inter blocks                     */
+  VP9B_SEC_TXB_INTER = 2,/* vp9b_txb[]        inter residual transform blocks, eob > 0 only   */
+  VP9B_SEC_TXB_INTRA_Y = 3, /* vp9b_txb[]     intra transform blocks per plane, decode order  */
+  VP9B_SEC_TXB_INTRA_U = 4,
+  VP9B_SEC_TXB_INTRA_V = 5,
+  VP9B_SEC_SB_INTRA = 6, /* vp9b_sbrange[3][sb_rows*sb_cols]  per-plane range into TXB_INTRA_* */
+  VP9B_SEC_COEF = 7,     /* int16 (8-bit) or int32 (HBD) dequantised coefs, scan order, eob each */
+  VP9B_SEC_LFM = 8,      /* vp9b_lfm[sb_rows*sb_cols]  final (adjusted) loop-filter masks     */
+  VP9B_SEC_COUNT = 12
+};
+
+typedef struct vp9b_section {
+  uint32_t offset; /* bytes from start of the packed buffer, 16-byte aligned */
+  uint32_t count;  /* number of records (COEF: number of coefficients)       */
+} vp9b_section;
+
+typedef struct vp9b_ref_desc { /* role of struct scale_factors + RefBuffer (vp9_scale.h:25-38) */
+  int32_t slot;                /* device frame slot, -1 if unused               */
+  uint32_t width, height;      /* reference frame crop size (luma)              */
+  int32_t x_scale_fp, y_scale_fp; /* 14-bit fixed point (vp9_scale.c:37-43)     */
+  int32_t x_step_q4, y_step_q4;   /* 16 == unscaled                              */
+} vp9b_ref_desc;
+
+typedef struct vp9b_frame_hdr {
+  uint32_t magic;
+  uint32_t total_bytes;
+  uint32_t width, height;        /* frame crop size in luma samples */
+  uint32_t mi_cols, mi_rows;     /* 8x8 units; aligned size = 8*mi   */
+  uint32_t sb_cols, sb_rows;     /* 64x64 units                      */
+  uint8_t bit_depth;             /* 8, 10, 12                        */
+  uint8_t ss_x, ss_y;
+  uint8_t lossless;              /* all transforms are 4x4 WHT       */
+  uint8_t intra_only;            /* key frame or intra-only frame: no inter blocks */
+  uint8_t show_frame;
+  uint8_t lf_level;              /* 0 => loop filter skipped          */
+  uint8_t lf_sharpness;
+  uint8_t coef_bytes;            /* 2 or 4                            */
+  uint8_t reserved[3];
+  int32_t dst_slot;              /* device frame slot reconstructed into */
+  vp9b_ref_desc ref[3];          /* LAST, GOLDEN, ALTREF              */
+  vp9b_section sec[VP9B_SEC_COUNT];
+  uint8_t lf_lim[64];            /* per level: inside limit  (vp9_loopfilter.c:212-231) */
+  uint8_t lf_mblim[64];          /* per level: edge limit; hev_thr = level >> 4 (:249)  */
+  uint32_t frame_index;          /* decode-order counter, informational */
+  uint32_t n_inter_px[3];        /* predicted samples per plane (roofline accounting)   */
+  uint32_t n_compound_px[3];
+  uint32_t reserved2[8];
+} vp9b_frame_hdr;
+
+typedef struct vp9b_block { /* 16 bytes. role of MODE_INFO fields in vp9_blockd.h:74-97 */
+  uint16_t mi_col, mi_row;
+  uint8_t bsize;      /* BLOCK_4X4..BLOCK_64X64 (0..12) */
+  uint8_t ref0;       /* 0 intra, 1 LAST, 2 GOLDEN, 3 ALTREF */
+  uint8_t ref1;       /* 0 none, else second reference (compound) */
+  uint8_t filter;     /* 0 regular, 1 smooth, 2 sharp, 3 bilinear (vp9_filter.c:79-82) */
+  int16_t mv[2][2];   /* [ref][row,col] in 1/8 pel; for bsize < 8X8 inter blocks
+                         mv[0] holds the uint32 index into VP9B_SEC_SUBMV instead */
+} vp9b_block;
+
+typedef struct vp9b_submv { /* 40 bytes */
+  int16_t luma[4][2][2];   /* [block 0..3][ref][row,col]  (bmi[], vp9_decodemv.c:761-768) */
+  int16_t chroma[2][2];    /* [ref][row,col]: 4:2:0 average, vp9_reconinter.c:61-87,112-124 */
+} vp9b_submv;
+
+typedef struct vp9b_txb { /* 12 bytes */
+  uint32_t coef_off;  /* index of first coefficient in VP9B_SEC_COEF            */
+  uint16_t x4, y4;    /* position inside the plane in units of 4 samples        */
+  uint16_t eob;       /* number of coefficients stored (scan order); 0 = none   */
+  uint8_t tx;         /* tx_size (bits 0-1) | tx_type (2-3) | plane (4-5)       */
+  uint8_t aux;        /* intra: mode (0-3) | have_top (4) | have_left (5) | have_right (6) */
+} vp9b_txb;
+
+typedef struct vp9b_sbrange {
+  uint32_t start, count;
+} vp9b_sbrange;
+
+typedef struct vp9b_lfm { /* 160 bytes. role of LOOP_FILTER_MASK, vp9_loopfilter.h:60-68 */
+  uint64_t left_y[4];
+  uint64_t above_y[4];
+  uint64_t int_4x4_y;
+  uint16_t left_uv[4];
+  uint16_t above_uv[4];
+  uint16_t int_4x4_uv;
+  uint16_t pad[3];
+  uint8_t lfl_y[64];
+} vp9b_lfm;
+
+/* ------------------------------------------------------------------ 1. reconstruction ctx --- */
+typedef struct vp9gpu_ctx vp9gpu_ctx;
+
+/* device < 0: current device.  Returns NULL on failure (no CUDA device). */
+vp9gpu_ctx *vp9gpu_create(int device);
+void vp9gpu_destroy(vp9gpu_ctx *ctx);
+const char *vp9gpu_last_error(vp9gpu_ctx *ctx);
+
+/* Reconstruct one frame from a packed buffer in HOST memory (copied H2D asynchronously from an
+ * internal pinned ring) -- enqueues upload + all kernels on the ctx stream and returns. */
+int vp9gpu_frame_submit(vp9gpu_ctx *ctx, const void *packed, size_t bytes);
+/* Same, but the packed buffer already lives in DEVICE memory (recon-only replay, bench). */
+int vp9gpu_frame_submit_device(vp9gpu_ctx *ctx, const void *d_packed, const vp9b_frame_hdr *hdr);
+/* Upload a packed buffer to a ctx-owned device allocation for later submit_device calls. */
+int vp9gpu_upload_packed(vp9gpu_ctx *ctx, const void *packed, size_t bytes, void **d_packed);
+int vp9gpu_free_packed(vp9gpu_ctx *ctx, void *d_packed);
+/* Wait for everything enqueued on the ctx stream. */
+int vp9gpu_sync(vp9gpu_ctx *ctx);
+/* D2H copy of the cropped planes of a slot (8-bit: 1 byte/sample, HBD: 2, little endian).
+ * Strides in bytes.  Synchronous.  (role of vp9_get_raw_frame, vp9_decoder.c:494) */
+int vp9gpu_get_frame(vp9gpu_ctx *ctx, int slot, uint8_t *y, uint8_t *u, uint8_t *v,
+                     int y_stride, int uv_stride);
+/* H2D copy into a slot (VP8_SET_REFERENCE, vp9_decoder.c:258-331, and tests). */
+int vp9gpu_set_frame(vp9gpu_ctx *ctx, int slot, uint32_t width, uint32_t height, int bit_depth,
+                     int ss_x, int ss_y, const uint8_t *y, const uint8_t *u, const uint8_t *v,
+                     int y_stride, int uv_stride);
+/* Debug/test hook: stop after a stage (0 = all; 1 inter pred; 2 + inter residual; 3 + intra;
+ * 4 + loop filter). */
+int vp9gpu_set_stop_stage(vp9gpu_ctx *ctx, int stage);
+/* CUDA stream handle (cudaStream_t) used by the ctx, for event timing by the caller. */
+void *vp9gpu_stream(vp9gpu_ctx *ctx);
+/* Number of kernel launches issued since creation. */
+uint64_t vp9gpu_launch_count(vp9gpu_ctx *ctx);
+/* Accumulated device milliseconds per stage since last reset (needs profiling enabled):
+ * 0 upload/expand, 1 inter pred, 2 inter residual, 3 intra, 4 loop filter. */
+int vp9gpu_set_profiling(vp9gpu_ctx *ctx, int enable);
+int vp9gpu_get_stage_ms(vp9gpu_ctx *ctx, float ms[8], int reset);
+
+/* ------------------------------------------------------------------ 2. host parser --------- */
+typedef struct vp9b_parser vp9b_parser;
+
+vp9b_parser *vp9b_parser_create(void);
+void vp9b_parser_destroy(vp9b_parser *p);
+const char *vp9b_parser_last_error(vp9b_parser *p);
+/* Parse ONE frame (not a superframe) of compressed data.  On success *packed points to a
+ * parser-owned buffer (valid until the next call) holding vp9b_frame_hdr + sections, or NULL
+ * with *bytes == 0 for a show_existing_frame.  *show_slot is the frame slot to output
+ * (-1: nothing to show).  (role of vp9_receive_compressed_data, vp9_decoder.c:407) */
+int vp9b_parser_parse(vp9b_parser *p, const uint8_t *data, size_t size, const void **packed,
+                      size_t *bytes, int *show_slot);
+/* Geometry of a slot as the parser last set it up. */
+int vp9b_parser_slot_info(vp9b_parser *p, int slot, uint32_t *width, uint32_t *height,
+                          int *bit_depth, int *ss_x, int *ss_y);
+/* Split a superframe (vp9_parse_superframe_index, vp9_dx_iface.c:354): fills up to 8 sizes,
+ * returns the number of frames (>=1) or a negative error. */
+int vp9b_parse_superframe(const uint8_t *data, size_t size, uint32_t sizes[8]);
+
+/* ------------------------------------------------------------------ 3. whole decoder ------- */
+typedef struct vp9b_decoder vp9b_decoder;
+
+typedef struct vp9b_image {
+  uint32_t width, height;
+  int bit_depth, ss_x, ss_y;
+  int slot;
+} vp9b_image;
+
+vp9b_decoder *vp9b_decoder_create(int device);
+void vp9b_decoder_destroy(vp9b_decoder *d);
+const char *vp9b_decoder_last_error(vp9b_decoder *d);
+/* Decode one chunk (IVF frame payload; superframes handled).  (vpx_codec_decode) */
+int vp9b_decoder_decode(vp9b_decoder *d, const uint8_t *data, size_t size);
+/* After decode: 1 if a frame is ready to show (fills *img), 0 if none.  (vpx_codec_get_frame) */
+int vp9b_decoder_get_frame(vp9b_decoder *d, vp9b_image *img);
+/* Copy the cropped planes of the shown frame to host memory (strides in bytes). */
+int vp9b_decoder_read_frame(vp9b_decoder *d, const vp9b_image *img, uint8_t *y, uint8_t *u,
+                            uint8_t *v, int y_stride, int uv_stride);
+vp9gpu_ctx *vp9b_decoder_gpu(vp9b_decoder *d);
+vp9b_parser *vp9b_decoder_parser(vp9b_decoder *d);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VP9_B200_H_ */

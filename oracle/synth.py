@@ -1,0 +1,76 @@
+"""TEST INFRASTRUCTURE ONLY -- seeded synthetic video content + clip encoding through the libvpx
+1.15.2 encoder API (clips C4/C5).  Content: box-blurred noise texture that
+translates (3,2) px per frame over a slowly changing gradient, plus a few independently moving
+patches and per-frame fresh noise in one corner, so that inter (single + compound), intra, skip
+and all transform sizes occur.
+"""
+import numpy as np
+
+from . import vpx_oracle as vo
+
+
+def _blur(a, k):
+    if k <= 1:
+        return a
+    c = np.cumsum(np.pad(a, ((k, 0), (k, 0)), mode="wrap").astype(np.float64), axis=0)
+    a = (c[k:] - c[:-k]) / k
+    c = np.cumsum(a, axis=1)
+    a = (c[:, k:] - c[:, :-k]) / k
+    return a
+
+
+def make_frames(w, h, n, seed=1234, bit_depth=8, motion=(3, 2), detail=0.04, noise_corner=True):
+    """Returns list of (Y,U,V) arrays, 4:2:0."""
+    rng = np.random.default_rng(seed)
+    maxv = (1 << bit_depth) - 1
+    W, H = w + 256, h + 256
+    tex = _blur(rng.integers(0, 256, size=(H, W)).astype(np.float64), 9)
+    tex = (tex - tex.mean()) * 6.0 + 128
+    fine = rng.integers(0, 256, size=(H, W)).astype(np.float64)
+    tex = (1.0 - detail) * tex + detail * fine
+    texu = _blur(rng.integers(0, 256, size=(H // 2, W // 2)).astype(np.float64), 7)
+    texv = _blur(rng.integers(0, 256, size=(H // 2, W // 2)).astype(np.float64), 9)
+    texu = (texu - texu.mean()) * 4 + 128
+    texv = (texv - texv.mean()) * 4 + 128
+    yy, xx = np.mgrid[0:h, 0:w]
+    frames = []
+    scale = (maxv + 1) / 256.0
+    for t in range(n):
+        dx, dy = (motion[0] * t) % 128, (motion[1] * t) % 128
+        y = tex[dy:dy + h, dx:dx + w].copy()
+        grad = 20.0 * np.sin((xx + 5 * t) / 97.0) + 15.0 * np.cos((yy - 3 * t) / 61.0)
+        y += grad
+        # an independently moving patch (creates occlusion => intra / compound)
+        ps = max(16, min(w, h) // 5) & ~1
+        px = int((w - ps) * (0.5 + 0.45 * np.sin(t / 7.0))) & ~1
+        py = int((h - ps) * (0.5 + 0.45 * np.cos(t / 5.0))) & ~1
+        y[py:py + ps, px:px + ps] = tex[H - ps - 8:H - 8, 8:8 + ps] * 0.7 + 60
+        # fresh noise corner (forces intra in inter frames)
+        cs = max(16, min(w, h) // 8) & ~1
+        if noise_corner:
+            y[:cs, w - cs:] = rng.integers(0, 256, size=(cs, cs))
+        u = texu[dy // 2:dy // 2 + (h + 1) // 2, dx // 2:dx // 2 + (w + 1) // 2].copy()
+        v = texv[dy // 2:dy // 2 + (h + 1) // 2, dx // 2:dx // 2 + (w + 1) // 2].copy()
+        u[py // 2:(py + ps) // 2, px // 2:(px + ps) // 2] += 30
+        dt = np.uint16 if bit_depth > 8 else np.uint8
+        f = [np.clip(np.rint(p * scale), 0, maxv).astype(dt) for p in (y, u, v)]
+        frames.append(f)
+    return frames
+
+
+def encode_clip(path, w, h, n, seed=1234, bit_depth=8, scale_at=None, detail=0.04, noise_corner=True,
+                deadline=1000000, **enc_kw):
+    """Encode n synthetic frames to an IVF.  scale_at: {frame_index: (hmode, vmode)} issues
+    VP8E_SET_SCALEMODE mid-stream (scaled reference frames, test/resize_test.cc:283)."""
+    frames = make_frames(w, h, n, seed=seed, bit_depth=bit_depth, detail=detail,
+                         noise_corner=noise_corner)
+    enc = vo.Encoder(w, h, bit_depth=bit_depth, **enc_kw)
+    chunks = []
+    for i, f in enumerate(frames):
+        if scale_at and i in scale_at:
+            enc.set_scalemode(*scale_at[i])
+        chunks += enc.encode(f, deadline=deadline)
+    chunks += enc.flush()
+    enc.close()
+    vo.ivf_write(path, chunks, w, h)
+    return chunks
