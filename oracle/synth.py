@@ -19,7 +19,8 @@ def _blur(a, k):
     return a
 
 
-def make_frames(w, h, n, seed=1234, bit_depth=8, motion=(3, 2), detail=0.04, noise_corner=True):
+def make_frames(w, h, n, seed=1234, bit_depth=8, motion=(3, 2), detail=0.04, noise_corner=True,
+                temporal_noise=0.0):
     """Returns list of (Y,U,V) arrays, 4:2:0."""
     rng = np.random.default_rng(seed)
     maxv = (1 << bit_depth) - 1
@@ -49,6 +50,8 @@ def make_frames(w, h, n, seed=1234, bit_depth=8, motion=(3, 2), detail=0.04, noi
         cs = max(16, min(w, h) // 8) & ~1
         if noise_corner:
             y[:cs, w - cs:] = rng.integers(0, 256, size=(cs, cs))
+        if temporal_noise > 0:
+            y += rng.normal(0.0, temporal_noise, size=y.shape)
         u = texu[dy // 2:dy // 2 + (h + 1) // 2, dx // 2:dx // 2 + (w + 1) // 2].copy()
         v = texv[dy // 2:dy // 2 + (h + 1) // 2, dx // 2:dx // 2 + (w + 1) // 2].copy()
         u[py // 2:(py + ps) // 2, px // 2:(px + ps) // 2] += 30
@@ -59,12 +62,22 @@ def make_frames(w, h, n, seed=1234, bit_depth=8, motion=(3, 2), detail=0.04, noi
 
 
 def encode_clip(path, w, h, n, seed=1234, bit_depth=8, scale_at=None, detail=0.04, noise_corner=True,
-                deadline=1000000, **enc_kw):
+                deadline=1000000, temporal_noise=0.0, **enc_kw):
     """Encode n synthetic frames to an IVF.  scale_at: {frame_index: (hmode, vmode)} issues
     VP8E_SET_SCALEMODE mid-stream (scaled reference frames, test/resize_test.cc:283)."""
+    two_pass = enc_kw.pop("two_pass", False)
     frames = make_frames(w, h, n, seed=seed, bit_depth=bit_depth, detail=detail,
-                         noise_corner=noise_corner)
-    enc = vo.Encoder(w, h, bit_depth=bit_depth, **enc_kw)
+                         noise_corner=noise_corner, temporal_noise=temporal_noise)
+    if two_pass:  # first pass collects stats (vpxenc.c two-pass loop)
+        e1 = vo.Encoder(w, h, bit_depth=bit_depth, g_pass=1, **enc_kw)
+        for f in frames:
+            e1.encode(f, deadline=deadline)
+        e1.flush()
+        stats = b"".join(e1.stats_out)
+        e1.close()
+        enc = vo.Encoder(w, h, bit_depth=bit_depth, g_pass=2, stats=stats, **enc_kw)
+    else:
+        enc = vo.Encoder(w, h, bit_depth=bit_depth, **enc_kw)
     chunks = []
     for i, f in enumerate(frames):
         if scale_at and i in scale_at:

@@ -240,7 +240,8 @@ class Encoder:
     def __init__(self, w, h, bit_depth=8, cpu_used=4, lag=0, auto_alt_ref=0, tile_cols_log2=0,
                  tile_rows_log2=0, lossless=0, cq_level=None, bitrate=None, min_q=0, max_q=63,
                  kf_max_dist=9999, error_resilient=0, frame_parallel=0, threads=4, aq_mode=0,
-                 end_usage=None, resize_allowed=0, sharpness=None):
+                 end_usage=None, resize_allowed=0, sharpness=None, g_pass=0, stats=None,
+                 arnr_maxframes=None, arnr_strength=None):
         L = lib()
         self.L, self.w, self.h, self.bd = L, w, h, bit_depth
         iface = C.c_void_p(L.vpx_codec_vp9_cx())
@@ -265,6 +266,12 @@ class Encoder:
             cfg.rc_end_usage = 3  # VPX_Q
         if bitrate is not None:
             cfg.rc_target_bitrate = bitrate
+        cfg.g_pass = g_pass  # 0 one pass, 1 first pass, 2 last pass (vpx_encoder.h vpx_enc_pass)
+        self._stats = None
+        if stats is not None:
+            self._stats = C.create_string_buffer(stats, len(stats))
+            cfg.stats_buf = C.cast(self._stats, C.c_void_p)
+            cfg.stats_sz = len(stats)
         self.cfg = cfg
         self.ctx = C.create_string_buffer(256)
         flags = 0x40000 if bit_depth > 8 else 0  # VPX_CODEC_USE_HIGHBITDEPTH
@@ -287,6 +294,11 @@ class Encoder:
             self.ctrl(VP8E_SET_CQ_LEVEL, cq_level)
         if sharpness is not None:
             self.ctrl(VP8E_SET_SHARPNESS, sharpness)
+        if arnr_maxframes is not None:
+            self.ctrl(VP8E_SET_ARNR_MAXFRAMES, arnr_maxframes)
+        if arnr_strength is not None:
+            self.ctrl(VP8E_SET_ARNR_STRENGTH, arnr_strength)
+        self.stats_out = []
         fmt = VPX_IMG_FMT_I42016 if bit_depth > 8 else VPX_IMG_FMT_I420
         self.img_p = L.vpx_img_alloc(None, fmt, w, h, 32)
         self.img = VpxImage.from_address(self.img_p)
@@ -323,6 +335,11 @@ class Encoder:
             if not p:
                 break
             kind = C.c_int.from_address(p).value
+            if kind == 1:  # VPX_CODEC_STATS_PKT
+                buf = C.c_void_p.from_address(p + 8).value
+                sz = C.c_size_t.from_address(p + 16).value
+                self.stats_out.append(C.string_at(buf, sz))
+                continue
             if kind != 0:
                 continue
             buf = C.c_void_p.from_address(p + 8).value
