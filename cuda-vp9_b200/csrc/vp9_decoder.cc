@@ -1,0 +1,97 @@
+// Whole decoder = host parser + GPU reconstruction context (include/vp9_b200.h section 3).
+// Mirrors decoder_decode / decode_one / decoder_get_frame (vp9_dx_iface.c:294-423): a chunk may
+// be a superframe; each frame is parsed on the host, its packed buffer is submitted to the GPU
+// stream, and the last frame flagged show_frame becomes the output of the chunk.
+#include <string.h>
+
+#include <new>
+#include <string>
+
+#include "vp9_b200.h"
+
+struct vp9b_decoder {
+  vp9b_parser *parser = nullptr;
+  vp9gpu_ctx *gpu = nullptr;
+  std::string err;
+  int show_slot = -1;
+};
+
+extern "C" {
+
+vp9b_decoder *vp9b_decoder_create(int device) {
+  vp9b_decoder *d = new (std::nothrow) vp9b_decoder();
+  if (!d) return nullptr;
+  d->parser = vp9b_parser_create();
+  d->gpu = vp9gpu_create(device);
+  if (!d->parser || !d->gpu) {  // no CPU fallback: without a CUDA device there is no decoder
+    vp9b_parser_destroy(d->parser);
+    vp9gpu_destroy(d->gpu);
+    delete d;
+    return nullptr;
+  }
+  return d;
+}
+
+void vp9b_decoder_destroy(vp9b_decoder *d) {
+  if (!d) return;
+  vp9gpu_destroy(d->gpu);
+  vp9b_parser_destroy(d->parser);
+  delete d;
+}
+
+const char *vp9b_decoder_last_error(vp9b_decoder *d) { return d ? d->err.c_str() : "null decoder"; }
+vp9gpu_ctx *vp9b_decoder_gpu(vp9b_decoder *d) { return d ? d->gpu : nullptr; }
+vp9b_parser *vp9b_decoder_parser(vp9b_decoder *d) { return d ? d->parser : nullptr; }
+
+int vp9b_decoder_decode(vp9b_decoder *d, const uint8_t *data, size_t size) {
+  if (!d || !data || !size) return VP9B_ERR_INVALID;
+  d->show_slot = -1;
+  uint32_t sizes[8];
+  const int n = vp9b_parse_superframe(data, size, sizes);
+  if (n < 0) {
+    d->err = "corrupt superframe index";
+    return n;
+  }
+  size_t off = 0;
+  for (int i = 0; i < n; i++) {
+    const void *packed = nullptr;
+    size_t bytes = 0;
+    int show = -1;
+    // a frame of size 1 with only the marker is a skipped frame in libvpx superframes
+    int e = vp9b_parser_parse(d->parser, data + off, sizes[i], &packed, &bytes, &show);
+    if (e) {
+      d->err = vp9b_parser_last_error(d->parser);
+      return e;
+    }
+    if (packed) {
+      e = vp9gpu_frame_submit(d->gpu, packed, bytes);
+      if (e) {
+        d->err = vp9gpu_last_error(d->gpu);
+        return e;
+      }
+    }
+    if (show >= 0) d->show_slot = show;
+    off += sizes[i];
+  }
+  return VP9B_OK;
+}
+
+int vp9b_decoder_get_frame(vp9b_decoder *d, vp9b_image *img) {
+  if (!d || !img) return VP9B_ERR_INVALID;
+  if (d->show_slot < 0) return 0;
+  img->slot = d->show_slot;
+  int e = vp9b_parser_slot_info(d->parser, d->show_slot, &img->width, &img->height, &img->bit_depth, &img->ss_x,
+                                &img->ss_y);
+  if (e) return e;
+  return 1;
+}
+
+int vp9b_decoder_read_frame(vp9b_decoder *d, const vp9b_image *img, uint8_t *y, uint8_t *u, uint8_t *v, int y_stride,
+                            int uv_stride) {
+  if (!d || !img) return VP9B_ERR_INVALID;
+  const int e = vp9gpu_get_frame(d->gpu, img->slot, y, u, v, y_stride, uv_stride);
+  if (e) d->err = vp9gpu_last_error(d->gpu);
+  return e;
+}
+
+}  // extern "C"

@@ -1,0 +1,85 @@
+#!/usr/bin/env python3
+"""Generate the synthetic test clips under tests/golden/clips/ and their per-frame MD5 lists
+(tests/golden/md5/<clip>.md5, same format as the reference's Sony.md5 / netflix.md5) with the
+libvpx v1.15.2 encoder + decoder that ships in this image.
+
+The clips stand in for the reference's Bravia.1440.ivf / FoodMarket2.ivf, which are absent from
+the reference checkout (.MISSING_LARGE_BLOBS:1-2).  Usage:
+    python tools/make_clips.py            # all small parity clips
+    python tools/make_clips.py bench      # larger bench clips (1440p / 4K)
+"""
+import os
+import sys
+import time
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+from oracle import synth, vpx_oracle as vo  # noqa: E402
+
+ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tests", "golden")
+
+# name -> encode parameters.  Each clip targets features of the hot path.
+PARITY = {
+    # odd frame sizes (edge emulation in MC, intra edge extension, lpf mask trimming), real-time
+    # mode so that the loop filter level is non-zero on key frames too
+    "odd_rt": dict(w=200, h=136, n=8, deadline=1, cpu_used=6, bitrate=200),
+    "odd2": dict(w=130, h=98, n=6, cpu_used=2, cq_level=35),
+    # 4 tile columns x 2 tile rows (intra have_left is tile relative)
+    "tiles_rt": dict(w=1280, h=384, n=4, deadline=1, cpu_used=7, tile_cols_log2=2, tile_rows_log2=1, bitrate=700),
+    # two-pass, hidden alt-ref frame (superframe), compound prediction
+    "comp": dict(w=352, h=288, n=40, cpu_used=1, lag=16, auto_alt_ref=1, two_pass=True, bitrate=400, end_usage=0,
+                 arnr_maxframes=7, arnr_strength=5, detail=0.02, temporal_noise=4.0, noise_corner=False),
+    # sub-8x8 partitions (4x4/4x8/8x4 inter + intra)
+    "sub8": dict(w=352, h=288, n=6, cpu_used=0, bitrate=2000, end_usage=0, min_q=4, max_q=40),
+    # profile 2, 10 and 12 bit (highbd convolve / idct / lpf)
+    "hbd10": dict(w=320, h=240, n=6, bit_depth=10, cpu_used=3, cq_level=30),
+    "hbd12": dict(w=208, h=160, n=5, bit_depth=12, cpu_used=4, cq_level=40, deadline=1),
+    # lossless: 4x4 WHT path
+    "lossless": dict(w=176, h=144, n=3, lossless=1, cpu_used=4),
+    # segmentation (per-segment q and lf level)
+    "aq": dict(w=352, h=288, n=8, aq_mode=3, cpu_used=5, deadline=1, bitrate=300),
+    "errres": dict(w=352, h=288, n=6, error_resilient=1, cpu_used=5, deadline=1, bitrate=300),
+    "fpar": dict(w=352, h=288, n=6, frame_parallel=1, cpu_used=3, cq_level=30),
+    # reference scaling: the coded size changes mid-stream (VP8E_SET_SCALEMODE), so inter
+    # prediction reads references of a different size (x_step_q4 != 16)
+    "scaled": dict(w=352, h=288, n=12, cpu_used=3, cq_level=30, scale_at={3: (3, 3), 6: (1, 2), 9: (0, 0)}),
+    "scaled_rt": dict(w=416, h=240, n=10, cpu_used=6, deadline=1, bitrate=300,
+                      scale_at={2: (3, 1), 5: (2, 3), 8: (0, 0)}, temporal_noise=2.0),
+}
+
+# Bench clips: stand-ins for BASELINE.json configs[1] (1440p) and configs[2]/[3] (4K, 4 tile
+# columns, compound).  Real-time two-pass is not available, so good quality / cpu_used 5.
+BENCH = {
+    "bench_1440p": dict(w=2560, h=1440, n=20, cpu_used=5, lag=8, auto_alt_ref=1, two_pass=True, bitrate=12000,
+                        end_usage=0, tile_cols_log2=2, detail=0.02, temporal_noise=2.5, noise_corner=False, threads=8),
+    "bench_4k": dict(w=3840, h=2160, n=12, cpu_used=5, lag=8, auto_alt_ref=1, two_pass=True, bitrate=25000,
+                     end_usage=0, tile_cols_log2=2, detail=0.02, temporal_noise=2.5, noise_corner=False, threads=8),
+}
+
+
+def make(name, params, outdir):
+    kw = dict(params)
+    w, h, n = kw.pop("w"), kw.pop("h"), kw.pop("n")
+    path = os.path.join(outdir, "clips", name + ".ivf")
+    t = time.time()
+    synth.encode_clip(path, w, h, n, **kw)
+    md5 = vo.decode_ivf_md5(path)
+    with open(os.path.join(outdir, "md5", name + ".md5"), "w") as f:
+        for i, m in enumerate(md5):
+            f.write("%s  img-%dx%d-%04d.i420\n" % (m, w, h, i + 1))
+    print("%-12s %4dx%-4d %3d frames %8d bytes  %.1fs" % (name, w, h, len(md5), os.path.getsize(path), time.time() - t))
+
+
+def main():
+    os.makedirs(os.path.join(ROOT, "clips"), exist_ok=True)
+    os.makedirs(os.path.join(ROOT, "md5"), exist_ok=True)
+    args = sys.argv[1:]
+    table = dict(PARITY)
+    if args and args[0] == "bench":
+        table = dict(BENCH)
+        args = args[1:]
+    for name in (args or list(table)):
+        make(name, table[name], ROOT)
+
+
+if __name__ == "__main__":
+    main()
