@@ -27,6 +27,8 @@ def lib():
         L.vp9ref_destroy.argtypes = [vp]
         L.vp9ref_recon_frame.argtypes = [vp, C.c_char_p, C.c_size_t, C.c_int]
         L.vp9ref_get_frame.argtypes = [vp, C.c_int, vp, vp, vp, C.c_int, C.c_int]
+        L.vp9ref_set_frame.argtypes = [vp, C.c_int, C.c_uint32, C.c_uint32, C.c_int, C.c_int, C.c_int, vp, vp, vp,
+                                       C.c_int, C.c_int]
         L.vp9ref_intra_predictor.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp, C.c_int, C.c_int]
         L.vp9ref_inverse_transform_add.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, C.c_int, C.c_int]
         L.vp9ref_lpf_edge8.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
@@ -55,6 +57,13 @@ class RefRecon:
         if e:
             raise RuntimeError("vp9ref_get_frame: %d" % e)
         return pl
+
+    def set_frame(self, slot, planes, bd, sx, sy):
+        y, u, v = [np.ascontiguousarray(p) for p in planes]
+        e = self.L.vp9ref_set_frame(self.c, slot, y.shape[1], y.shape[0], bd, sx, sy, y.ctypes.data, u.ctypes.data,
+                                    v.ctypes.data, y.strides[0], u.strides[0])
+        if e:
+            raise RuntimeError("vp9ref_set_frame: %d" % e)
 
     def close(self):
         if self.c:

@@ -62,7 +62,7 @@ def make_frames(w, h, n, seed=1234, bit_depth=8, motion=(3, 2), detail=0.04, noi
 
 
 def encode_clip(path, w, h, n, seed=1234, bit_depth=8, scale_at=None, detail=0.04, noise_corner=True,
-                deadline=1000000, temporal_noise=0.0, **enc_kw):
+                deadline=1000000, temporal_noise=0.0, force_lf=False, **enc_kw):
     """Encode n synthetic frames to an IVF.  scale_at: {frame_index: (hmode, vmode)} issues
     VP8E_SET_SCALEMODE mid-stream (scaled reference frames, test/resize_test.cc:283)."""
     two_pass = enc_kw.pop("two_pass", False)
@@ -85,5 +85,127 @@ def encode_clip(path, w, h, n, seed=1234, bit_depth=8, scale_at=None, detail=0.0
         chunks += enc.encode(f, deadline=deadline)
     chunks += enc.flush()
     enc.close()
+    if force_lf:
+        chunks = force_loop_filter(chunks)
     vo.ivf_write(path, chunks, w, h)
     return chunks
+
+
+# ----------------------------------------------------------------------------------------------
+# Bitstream editing: libvpx's good-quality encoder searches the loop-filter level against the
+# source and settles on 0 for this synthetic content, which would leave the loop filter (half of
+# the hot path) idle in clips that also have alt-ref/compound prediction.  Rewriting the 6-bit
+# filter_level field of the uncompressed header (vp9_decodeframe.c:1610-1612) yields a perfectly
+# valid VP9 stream whose reference output is simply whatever libvpx decodes it to.
+class _Bits:
+    def __init__(self, data):
+        self.d, self.pos = data, 0
+
+    def bit(self):
+        b = (self.d[self.pos >> 3] >> (7 - (self.pos & 7))) & 1
+        self.pos += 1
+        return b
+
+    def lit(self, n):
+        v = 0
+        for _ in range(n):
+            v = (v << 1) | self.bit()
+        return v
+
+
+def _lf_field(frame, state):
+    """Returns (bit position of filter_level, current level, base_qindex) or None."""
+    r = _Bits(frame)
+    if r.lit(2) != 2:
+        return None
+    profile = r.bit() | (r.bit() << 1)
+    if profile == 3:
+        r.bit()
+    if r.bit():  # show_existing_frame
+        return None
+    frame_type, show_frame, error_res = r.bit(), r.bit(), r.bit()
+
+    def colorspace():
+        if profile >= 2:
+            r.bit()
+        cs = r.lit(3)
+        if cs != 7:
+            r.bit()
+            if profile in (1, 3):
+                r.lit(3)
+        elif profile in (1, 3):
+            r.bit()
+
+    if frame_type == 0:
+        r.lit(24)
+        colorspace()
+        r.lit(32)
+        if r.bit():
+            r.lit(32)
+    else:
+        intra_only = 0 if show_frame else r.bit()
+        if not error_res:
+            r.lit(2)
+        if intra_only:
+            r.lit(24)
+            if profile > 0:
+                colorspace()
+            r.lit(8)
+            r.lit(32)
+            if r.bit():
+                r.lit(32)
+        else:
+            r.lit(8)
+            for _ in range(3):
+                r.lit(4)
+            found = 0
+            for _ in range(3):
+                if r.bit():
+                    found = 1
+                    break
+            if not found:
+                r.lit(32)
+            if r.bit():
+                r.lit(32)
+            r.bit()
+            if not r.bit():
+                r.lit(2)
+    if not error_res:
+        r.lit(2)
+    r.lit(2)
+    pos = r.pos
+    level = r.lit(6)
+    r.lit(3)
+    if r.bit():
+        if r.bit():
+            for _ in range(6):
+                if r.bit():
+                    r.lit(7)
+    q = r.lit(8)
+    return pos, level, q
+
+
+def force_loop_filter(chunks, level_fn=None):
+    """Set a non-zero loop-filter level in every frame whose level is 0 (lossless frames kept)."""
+    import cuda_vp9_b200 as vb
+    if level_fn is None:
+        level_fn = lambda q: max(1, min(63, (q + 6) // 5))  # noqa: E731
+    out = []
+    for ch in chunks:
+        frames = vb.parse_superframe(ch)
+        buf = bytearray(ch)
+        off = 0
+        for fr in frames:
+            f = _lf_field(fr, None)
+            if f is not None:
+                pos, level, q = f
+                if level == 0 and q > 0:
+                    nl = level_fn(q)
+                    for k in range(6):
+                        bitpos = off * 8 + pos + k
+                        bit = (nl >> (5 - k)) & 1
+                        byte, sh = bitpos >> 3, 7 - (bitpos & 7)
+                        buf[byte] = (buf[byte] & ~(1 << sh)) | (bit << sh)
+            off += len(fr)
+        out.append(bytes(buf))
+    return out

@@ -1046,6 +1046,26 @@ int vp9ref_slot_info(vp9ref_ctx *c, int slot, uint32_t *w, uint32_t *h, int *bd,
   return 0;
 }
 
+/* Test hook: (re)initialise a slot with given samples (8-bit: 1 byte/sample, else 2 LE). */
+int vp9ref_set_frame(vp9ref_ctx *c, int slot, uint32_t w, uint32_t h, int bd, int ss_x, int ss_y, const uint8_t *y,
+                     const uint8_t *u, const uint8_t *v, int y_stride, int uv_stride) {
+  if (!c || slot < 0 || slot >= VP9B_NUM_SLOTS) return VP9B_ERR_INVALID;
+  vp9ref_frame *f = &c->slot[slot];
+  int e = setup_slot(f, w, h, ss_x, ss_y, bd);
+  if (e) return e;
+  const uint8_t *in[3] = { y, u, v };
+  for (int p = 0; p < 3; p++) {
+    const int pw = p ? (int)((w + ss_x) >> ss_x) : (int)w, ph = p ? (int)((h + ss_y) >> ss_y) : (int)h;
+    const int istride = p ? uv_stride : y_stride;
+    memset(f->plane[p], 0, (size_t)f->stride[p] * f->alloc_h[p] * sizeof(uint16_t));
+    for (int r = 0; r < ph; r++)
+      for (int x = 0; x < pw; x++)
+        f->plane[p][(size_t)r * f->stride[p] + x] =
+            bd == 8 ? in[p][(size_t)r * istride + x] : ((const uint16_t *)(in[p] + (size_t)r * istride))[x];
+  }
+  return 0;
+}
+
 /* Unit-test hooks: one loop-filter edge of 8 positions, and a w x h convolution. */
 void vp9ref_lpf_edge8(uint16_t *s, int pitch, int vertical, int size, int blimit, int limit, int thresh, int bd) {
   for (int i = 0; i < 8; i++) {

@@ -36,6 +36,12 @@ def _stage_frames(name, stage):
                 continue
             h = vb.FrameHdr.from_buffer_copy(packed[: C.sizeof(vb.FrameHdr)])
             geom = (h.width, h.height, h.bit_depth, h.ss_x, h.ss_y)
+            # same starting content on both sides (partial stages leave some samples untouched)
+            dt = np.uint16 if h.bit_depth > 8 else np.uint8
+            shapes = [(h.height, h.width)] + [((h.height + h.ss_y) >> h.ss_y, (h.width + h.ss_x) >> h.ss_x)] * 2
+            blank = [np.full(s, 7, dtype=dt) for s in shapes]
+            gpu.set_frame(h.dst_slot, blank, h.bit_depth, h.ss_x, h.ss_y)
+            ref_stage.set_frame(h.dst_slot, blank, h.bit_depth, h.ss_x, h.ss_y)
             gpu.set_stop_stage(stage)
             gpu.submit(packed)
             g = gpu.get_frame(h.dst_slot, *geom)

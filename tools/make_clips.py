@@ -28,6 +28,10 @@ PARITY = {
     # two-pass, hidden alt-ref frame (superframe), compound prediction
     "comp": dict(w=352, h=288, n=40, cpu_used=1, lag=16, auto_alt_ref=1, two_pass=True, bitrate=400, end_usage=0,
                  arnr_maxframes=7, arnr_strength=5, detail=0.02, temporal_noise=4.0, noise_corner=False),
+    # same kind of stream with the loop-filter level forced on (bitstream edit, oracle/synth.py)
+    "comp_lf": dict(w=352, h=288, n=40, cpu_used=1, lag=16, auto_alt_ref=1, two_pass=True, bitrate=400, end_usage=0,
+                    arnr_maxframes=7, arnr_strength=5, detail=0.02, temporal_noise=4.0, noise_corner=False,
+                    force_lf=True),
     # sub-8x8 partitions (4x4/4x8/8x4 inter + intra)
     "sub8": dict(w=352, h=288, n=6, cpu_used=0, bitrate=2000, end_usage=0, min_q=4, max_q=40),
     # profile 2, 10 and 12 bit (highbd convolve / idct / lpf)
@@ -49,10 +53,12 @@ PARITY = {
 # Bench clips: stand-ins for BASELINE.json configs[1] (1440p) and configs[2]/[3] (4K, 4 tile
 # columns, compound).  Real-time two-pass is not available, so good quality / cpu_used 5.
 BENCH = {
-    "bench_1440p": dict(w=2560, h=1440, n=20, cpu_used=5, lag=8, auto_alt_ref=1, two_pass=True, bitrate=12000,
-                        end_usage=0, tile_cols_log2=2, detail=0.02, temporal_noise=2.5, noise_corner=False, threads=8),
-    "bench_4k": dict(w=3840, h=2160, n=12, cpu_used=5, lag=8, auto_alt_ref=1, two_pass=True, bitrate=25000,
-                     end_usage=0, tile_cols_log2=2, detail=0.02, temporal_noise=2.5, noise_corner=False, threads=8),
+    "bench_1440p": dict(w=2560, h=1440, n=24, cpu_used=2, lag=16, auto_alt_ref=1, two_pass=True, bitrate=6000,
+                        end_usage=0, tile_cols_log2=2, arnr_maxframes=7, arnr_strength=5, detail=0.02,
+                        temporal_noise=3.5, noise_corner=False, threads=8, force_lf=True),
+    "bench_4k": dict(w=3840, h=2160, n=20, cpu_used=2, lag=16, auto_alt_ref=1, two_pass=True, bitrate=12000,
+                     end_usage=0, tile_cols_log2=2, arnr_maxframes=7, arnr_strength=5, detail=0.02,
+                     temporal_noise=3.5, noise_corner=False, threads=8, force_lf=True),
 }
 
 
