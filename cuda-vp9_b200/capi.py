@@ -99,6 +99,12 @@ def lib_gpu():
         L.vp9gpu_free_packed.argtypes = [vp, vp]
         L.vp9gpu_sync.argtypes = [vp]
         L.vp9gpu_get_frame.argtypes = [vp, C.c_int, vp, vp, vp, C.c_int, C.c_int]
+        L.vp9gpu_get_frame_async.argtypes = [vp, C.c_int, vp, vp, vp, C.c_int, C.c_int]
+        L.vp9gpu_alloc_host.restype = vp
+        L.vp9gpu_alloc_host.argtypes = [C.c_size_t]
+        L.vp9gpu_free_host.argtypes = [vp]
+        L.vp9b_decoder_read_frame_async.argtypes = [vp, C.POINTER(Image), vp, vp, vp, C.c_int, C.c_int]
+        L.vp9b_decoder_sync.argtypes = [vp]
         L.vp9gpu_set_frame.argtypes = [vp, C.c_int, C.c_uint32, C.c_uint32, C.c_int, C.c_int, C.c_int, vp, vp, vp,
                                        C.c_int, C.c_int]
         L.vp9gpu_set_stop_stage.argtypes = [vp, C.c_int]
@@ -258,6 +264,32 @@ class GpuRecon:
             pass
 
 
+class PinnedFrame:
+    """Page-locked (Y,U,V) output planes allocated through the C ABI (vp9gpu_alloc_host)."""
+
+    def __init__(self, w, h, bd=8, sx=1, sy=1):
+        self.L = lib_gpu()
+        bps = 2 if bd > 8 else 1
+        shapes = plane_shapes(w, h, sx, sy)
+        sizes = [s[0] * s[1] * bps for s in shapes]
+        self.nbytes = sum(sizes)
+        self.ptr = self.L.vp9gpu_alloc_host(self.nbytes)
+        if not self.ptr:
+            raise MemoryError("vp9gpu_alloc_host")
+        dt = np.uint16 if bd > 8 else np.uint8
+        self.planes, off = [], 0
+        for s, n in zip(shapes, sizes):
+            buf = (C.c_uint8 * n).from_address(self.ptr + off)
+            self.planes.append(np.frombuffer(buf, dtype=dt).reshape(s))
+            off += n
+
+    def close(self):
+        if self.ptr:
+            self.planes = []
+            self.L.vp9gpu_free_host(self.ptr)
+            self.ptr = None
+
+
 class Decoder:
     """Whole decoder on one GPU: vpx_codec_decode / vpx_codec_get_frame equivalents."""
 
@@ -287,6 +319,21 @@ class Decoder:
         self._chk(self.L.vp9b_decoder_read_frame(self.d, C.byref(img), pl[0].ctypes.data, pl[1].ctypes.data,
                                                  pl[2].ctypes.data, pl[0].strides[0], pl[1].strides[0]))
         return pl
+
+    def get_frame_into(self, pinned, sync=False):
+        """Asynchronous output into a PinnedFrame; returns False when there is no frame to show."""
+        img = Image()
+        r = self._chk(self.L.vp9b_decoder_get_frame(self.d, C.byref(img)))
+        if r == 0:
+            return False
+        pl = pinned.planes
+        fn = self.L.vp9b_decoder_read_frame if sync else self.L.vp9b_decoder_read_frame_async
+        self._chk(fn(self.d, C.byref(img), pl[0].ctypes.data, pl[1].ctypes.data, pl[2].ctypes.data,
+                     pl[0].strides[0], pl[1].strides[0]))
+        return True
+
+    def sync(self):
+        self._chk(self.L.vp9b_decoder_sync(self.d))
 
     def gpu_launch_count(self):
         return int(self.L.vp9gpu_launch_count(self.L.vp9b_decoder_gpu(self.d)))

@@ -94,4 +94,19 @@ int vp9b_decoder_read_frame(vp9b_decoder *d, const vp9b_image *img, uint8_t *y, 
   return e;
 }
 
+int vp9b_decoder_read_frame_async(vp9b_decoder *d, const vp9b_image *img, uint8_t *y, uint8_t *u, uint8_t *v,
+                                  int y_stride, int uv_stride) {
+  if (!d || !img) return VP9B_ERR_INVALID;
+  const int e = vp9gpu_get_frame_async(d->gpu, img->slot, y, u, v, y_stride, uv_stride);
+  if (e) d->err = vp9gpu_last_error(d->gpu);
+  return e;
+}
+
+int vp9b_decoder_sync(vp9b_decoder *d) {
+  if (!d) return VP9B_ERR_INVALID;
+  const int e = vp9gpu_sync(d->gpu);
+  if (e) d->err = vp9gpu_last_error(d->gpu);
+  return e;
+}
+
 }  // extern "C"

@@ -73,12 +73,9 @@ struct FrameParams {
   const void *coef;
   const vp9b_lfm *lfm;
   MiEntry *mi;
-  const uint32_t *order_intra;  // ticket -> sb index (anti-diagonal order r+c)
-  const uint32_t *order_lf;     // ticket -> sb index (order 2r+c)
-  uint32_t *flags_intra;        // [3][nsb] epoch when done
-  uint32_t *flags_lf;           // [3][nsb]
-  uint32_t *tickets;            // [2]
-  uint32_t epoch;
+  uint32_t *prog_intra;         // [3][sb_rows] progress counters: prog_base + superblocks done in the row
+  uint32_t *prog_lf;            // [sb_rows]
+  uint32_t prog_base;           // per-frame epoch offset: counters never need clearing between frames
   uint8_t lf_lim[64], lf_mblim[64];
 };
 
@@ -225,6 +222,207 @@ __global__ void k_inter_pred_generic(const __grid_constant__ FrameParams P, int 
     val = r ? ((val + v + 1) >> 1) : v;
   }
   ((Px *)P.dst[plane].ptr)[(size_t)y * P.dst[plane].stride + x] = (Px)val;
+}
+
+// ------------------------------------------------------------------------------------------
+// stage 1 fast path: 8-bit, unscaled references.  One thread predicts a 4-wide x 8-tall strip
+// (two 4x4 units when the two halves belong to different prediction units).  Reference rows
+// are fetched as aligned 32-bit words through L1 (neighbouring threads overlap heavily), the
+// 8-tap filters run as two DP4A (u8 samples x s8 taps) per output with byte windows built by
+// funnel shifts, the horizontally filtered rows are clipped and kept packed, transposed 4x4 by
+// PRMT so that the vertical pass is DP4A too, and results are packed with cvt.pack.sat.  The
+// compound average is a packed rounding byte average.  Units that touch the frame edge (need
+// clamped fetches) and scaled references fall back to predict_sample().
+__device__ __constant__ uint32_t d_taps4[4 * 16 * 2];  // [filter][phase][lo,hi] packed s8 taps
+
+VP9B_DEV int dp4a_us(uint32_t a, uint32_t b, int c) {
+  int d;
+  asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+  return d;
+}
+VP9B_DEV uint32_t pack_sat_u8x4(int a, int b, int c, int d) {  // bytes (a,b,c,d), a lowest, each >>7 done by caller
+  uint32_t lo, r;
+  asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, 0;" : "=r"(lo) : "r"(d), "r"(c));
+  asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(b), "r"(a), "r"(lo));
+  return r;
+}
+VP9B_DEV uint32_t avg_u8x4(uint32_t a, uint32_t b) {  // per byte (a + b + 1) >> 1
+  return (a | b) - (((a ^ b) >> 1) & 0x7f7f7f7fu);
+}
+
+// Predict a 4 x H unit (H = 4 or 8) from one reference; returns H packed rows in out[].
+// One code path for all sub-pel classes: lanes whose phase is 0 in a direction simply sit out
+// that direction's filter, so a warp pays for the most expensive class it contains, not the sum.
+template <int H>
+VP9B_DEV void mc_unit_fast(const uint8_t *__restrict__ ref, int rstride, int x0, int y0, int sx, int sy, int filter,
+                           uint32_t *out) {
+  constexpr int R = H + 7;  // rows y0-3 .. y0+H+3
+  const uint32_t txl = d_taps4[(filter * 16 + sx) * 2], txh = d_taps4[(filter * 16 + sx) * 2 + 1];
+  const uint32_t tyl = d_taps4[(filter * 16 + sy) * 2], tyh = d_taps4[(filter * 16 + sy) * 2 + 1];
+  const int xs = x0 - 3, o = (xs & 3) * 8;
+  const uint32_t *p = (const uint32_t *)(ref + (ptrdiff_t)(y0 - 3) * rstride + (xs & ~3));
+  uint32_t im[R + 1];
+#pragma unroll
+  for (int r = 0; r < R; r++) {
+    uint32_t v = 0;
+    if (sy || (r >= 3 && r < 3 + H)) {
+      const uint32_t a0 = __ldg(p), a1 = __ldg(p + 1), a2 = __ldg(p + 2), a3 = __ldg(p + 3);
+      const uint32_t v0 = __funnelshift_r(a0, a1, o), v1 = __funnelshift_r(a1, a2, o), v2 = __funnelshift_r(a2, a3, o);
+      if (sx) {
+        int s[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          const uint32_t w0 = __funnelshift_r(v0, v1, 8 * j), w1 = __funnelshift_r(v1, v2, 8 * j);
+          s[j] = dp4a_us(w1, txh, dp4a_us(w0, txl, 64)) >> 7;
+        }
+        v = pack_sat_u8x4(s[0], s[1], s[2], s[3]);
+      } else {
+        v = __funnelshift_r(v0, v1, 24);  // samples x0 .. x0+3
+      }
+    }
+    im[r] = v;
+    p = (const uint32_t *)((const uint8_t *)p + rstride);
+  }
+  im[R] = 0;
+  if (sy) {
+    // transpose 4x4 byte blocks: col[c][g] = samples of column c, rows 4g..4g+3
+    constexpr int G = (R + 3) / 4;
+    uint32_t col[4][G];
+#pragma unroll
+    for (int g = 0; g < G; g++) {
+      const uint32_t r0 = im[4 * g], r1 = im[4 * g + 1], r2 = (4 * g + 2 <= R) ? im[4 * g + 2] : 0,
+                     r3 = (4 * g + 3 <= R) ? im[4 * g + 3] : 0;
+      const uint32_t t0 = __byte_perm(r0, r1, 0x5140), t1 = __byte_perm(r2, r3, 0x5140);
+      const uint32_t t2 = __byte_perm(r0, r1, 0x7362), t3 = __byte_perm(r2, r3, 0x7362);
+      col[0][g] = __byte_perm(t0, t1, 0x5410);
+      col[1][g] = __byte_perm(t0, t1, 0x7632);
+      col[2][g] = __byte_perm(t2, t3, 0x5410);
+      col[3][g] = __byte_perm(t2, t3, 0x7632);
+    }
+#pragma unroll
+    for (int y = 0; y < H; y++) {
+      int s[4];
+#pragma unroll
+      for (int c = 0; c < 4; c++) {
+        const int g = y >> 2, sh = (y & 3) * 8;
+        const uint32_t w0 = __funnelshift_r(col[c][g], col[c][g + 1], sh);
+        const uint32_t w1 = __funnelshift_r(col[c][g + 1], (g + 2 < G) ? col[c][g + 2] : 0u, sh);
+        s[c] = dp4a_us(w1, tyh, dp4a_us(w0, tyl, 64)) >> 7;
+      }
+      out[y] = pack_sat_u8x4(s[0], s[1], s[2], s[3]);
+    }
+  } else {
+#pragma unroll
+    for (int y = 0; y < H; y++) out[y] = im[y + 3];
+  }
+}
+
+// is the whole fetch footprint of a 4xH unit (incl. the aligned word reads) inside the plane?
+VP9B_DEV bool mc_inside(int x0, int y0, int H, int rw, int rh) {
+  return x0 - 3 >= 0 && y0 - 3 >= 0 && x0 + 8 <= rw && y0 + H + 4 <= rh;
+}
+
+// one 4xH unit: all references of the prediction unit, compound average
+template <int H>
+VP9B_DEV void mc_unit(const FrameParams &P, int plane, const MiEntry &e, int mi_row, int mi_col, int x, int y,
+                      uint32_t *out) {
+  const int ss_x = plane ? P.ss_x : 0, ss_y = plane ? P.ss_y : 0;
+  const bool sub8 = e.bsize < 3;
+#pragma unroll 1
+  for (int r = 0; r < (e.ref1 ? 2 : 1); r++) {
+    const RefGeom &R = P.ref[(r ? e.ref1 : e.ref0) - 1];
+    int mvr, mvc;
+    if (sub8) {
+      const vp9b_submv &s = P.submv[e.aux];
+      if (ss_x && ss_y) { mvr = s.chroma[r][0]; mvc = s.chroma[r][1]; }
+      else {
+        const int k = (((y << ss_y) & 7) >> 2) * 2 + (((x << ss_x) & 7) >> 2);
+        mvr = s.luma[k][r][0]; mvc = s.luma[k][r][1];
+      }
+    } else {
+      mvr = e.mv[r][0];
+      mvc = e.mv[r][1];
+    }
+    uint32_t pr[H];
+    bool fast = false;
+    if (R.x_step_q4 == 16 && R.y_step_q4 == 16) {
+      const int smvr = mvr * (1 << (1 - ss_y)), smvc = mvc * (1 << (1 - ss_x));
+      const int x0 = x + (smvc >> 4), y0 = y + (smvr >> 4);
+      if (mc_inside(x0, y0, H, R.w[plane], R.h[plane])) {
+        mc_unit_fast<H>((const uint8_t *)R.pl[plane].ptr, R.pl[plane].stride, x0, y0, smvc & 15, smvr & 15, e.filter, pr);
+        fast = true;
+      }
+    }
+    if (!fast) {  // frame edge (clamped fetches) or scaled reference: exact per-sample path
+      const int bw8 = d_bw8[e.bsize], bh8 = d_bh8[e.bsize];
+      const int mi_col0 = mi_col & ~(bw8 - 1), mi_row0 = mi_row & ~(bh8 - 1);
+      const int bx = x - ((mi_col0 * 8) >> ss_x), by = y - ((mi_row0 * 8) >> ss_y);
+      const int xoff = sub8 ? (bx & ~3) : 0, yoff = sub8 ? (by & ~3) : 0;
+      const PredPos pp = pred_position(P, R, plane, mi_row0, mi_col0, bw8, bh8, xoff, yoff, mvr, mvc);
+#pragma unroll
+      for (int yy = 0; yy < H; yy++) {
+        uint32_t w = 0;
+#pragma unroll 1
+        for (int xx = 0; xx < 4; xx++)
+          w |= (uint32_t)predict_sample<uint8_t>(P, R, plane, pp, bx - xoff + xx, by - yoff + yy, e.filter) << (8 * xx);
+        pr[yy] = w;
+      }
+    }
+    if (r == 0) {
+#pragma unroll
+      for (int i = 0; i < H; i++) out[i] = pr[i];
+    } else {
+#pragma unroll
+      for (int i = 0; i < H; i++) out[i] = avg_u8x4(out[i], pr[i]);
+    }
+  }
+}
+
+// Thread = one 4 x H unit; warp = 8 x 4 units (32 x 4H samples) so that a warp mostly stays
+// inside one prediction block.  Luma runs with H = 8 (sub-8x8 blocks split into two 4x4
+// units), 4:2:0 chroma with H = 4 (one unit per 8x8 luma block).
+template <int H>
+VP9B_DEV void inter_pred_u8_body(const FrameParams &P, int plane, int bx_, int by_) {
+  const int ss_x = plane ? P.ss_x : 0, ss_y = plane ? P.ss_y : 0;
+  const int pw = (P.mi_cols * 8) >> ss_x, ph = (P.mi_rows * 8) >> ss_y;
+  const int x = (bx_ * 8 + (threadIdx.x & 7)) * 4;
+  const int y = (by_ * 16 + (threadIdx.x >> 3)) * H;
+  if (x >= pw || y >= ph) return;
+  uint8_t *dst = (uint8_t *)P.dst[plane].ptr + (size_t)y * P.dst[plane].stride + x;
+  const int dstride = P.dst[plane].stride;
+  const int mi_col = (x << ss_x) >> 3, mi_row = (y << ss_y) >> 3;
+  const MiEntry e = P.mi[(size_t)mi_row * P.mi_cols + mi_col];
+  if (!e.ref0) return;
+  if (H == 8 && e.bsize < 3) {  // sub-8x8 block in an unsubsampled plane: two 4x4 units
+    uint32_t o[4];
+    mc_unit<4>(P, plane, e, mi_row, mi_col, x, y, o);
+#pragma unroll
+    for (int i = 0; i < 4; i++) *(uint32_t *)(dst + (size_t)i * dstride) = o[i];
+    mc_unit<4>(P, plane, e, mi_row, mi_col, x, y + 4, o);
+#pragma unroll
+    for (int i = 0; i < 4; i++) *(uint32_t *)(dst + (size_t)(i + 4) * dstride) = o[i];
+    return;
+  }
+  uint32_t o[H];
+  mc_unit<H>(P, plane, e, mi_row, mi_col, x, y, o);
+#pragma unroll
+  for (int i = 0; i < H; i++) *(uint32_t *)(dst + (size_t)i * dstride) = o[i];
+}
+
+// All three planes in one launch: a flat grid of CTAs, luma tiles (32x128 samples) first, then
+// the two chroma planes (4:2:0: 32x64-sample tiles of 4x4 units; 4:4:4: same as luma).
+__global__ void __launch_bounds__(128) k_inter_pred_u8(const __grid_constant__ FrameParams P, int ncta_y, int ncta_c,
+                                                       int gx_y, int gx_c) {
+  int b = blockIdx.x;
+  if (b < ncta_y) {
+    inter_pred_u8_body<8>(P, 0, b % gx_y, b / gx_y);
+    return;
+  }
+  b -= ncta_y;
+  const int plane = 1 + b / ncta_c;
+  b %= ncta_c;
+  if (P.ss_x) inter_pred_u8_body<4>(P, plane, b % gx_c, b / gx_c);
+  else inter_pred_u8_body<8>(P, plane, b % gx_c, b / gx_c);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -462,36 +660,35 @@ VP9B_DEV void warp_intra_predict(const FrameParams &P, IntraEdge &E, const vp9b_
 
 constexpr int kWaveWarps = 4;
 
-// Persistent wavefront over superblocks.  Work units are handed out by an atomic ticket in an
-// order in which every dependency has a smaller ticket, so a waiting warp always waits on a
-// unit that is already running or done (forward progress without co-residency assumptions).
+// progress counters hold prog_base + count; stale values of earlier frames compare as negative
+VP9B_DEV void wait_progress(const uint32_t *p, uint32_t base, int need) {
+  while ((int)(ld_acquire(p) - base) < need) __nanosleep(20);
+}
+
+// One persistent warp per (superblock row, plane) walks its row left to right.  Intra edges
+// only reach into the left, above-left and above superblocks (above-right samples are taken
+// inside the prediction block only, vp9_reconintra.c:356-386,412), so row r may process
+// superblock c once row r-1 has finished superblock c: a wavefront with lag 1, tracked by one
+// progress counter per (plane, row).  Rows without intra blocks just publish their progress.
 template <typename Px, typename PT>
 __global__ void __launch_bounds__(kWaveWarps * 32) k_intra(const __grid_constant__ FrameParams P) {
   __shared__ int tbuf[kWaveWarps][32 * 33];
   __shared__ IntraEdge edges[kWaveWarps];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int unit = blockIdx.x * kWaveWarps + warp;
+  if (unit >= 3 * P.sb_rows) return;
+  // units are ordered row-major so that a row's dependency (row-1, same plane) has a lower index
+  const int sbr = unit / 3, plane = unit % 3;
   const int nsb = P.sb_cols * P.sb_rows;
-  const uint32_t total = 3u * nsb;
-  while (true) {
-    uint32_t tk = 0;
-    if (lane == 0) tk = atomicAdd(&P.tickets[0], 1u);
-    tk = __shfl_sync(0xffffffffu, tk, 0);
-    if (tk >= total) break;
-    const int plane = tk % 3, sb = P.order_intra[tk / 3];
-    const int sbr = sb / P.sb_cols, sbc = sb % P.sb_cols;
-    const vp9b_sbrange rg = P.sb_intra[plane * nsb + sb];
-    uint32_t *flags = P.flags_intra + plane * nsb;
+  uint32_t *prog = P.prog_intra + plane * P.sb_rows;
+  const vp9b_sbrange *rgs = P.sb_intra + plane * nsb + sbr * P.sb_cols;
+  for (int sbc = 0; sbc < P.sb_cols; sbc++) {
+    const vp9b_sbrange rg = rgs[sbc];
     if (rg.count) {
-      // wait for left, above-left, above (same plane)
-      if (lane < 3) {
-        const int dr = lane == 0 ? 0 : -1, dc = lane == 2 ? 0 : -1;
-        const int r = sbr + dr, c = sbc + dc;
-        if (r >= 0 && c >= 0) {
-          const uint32_t *f = flags + r * P.sb_cols + c;
-          while (ld_acquire(f) != P.epoch) __nanosleep(40);
-        }
+      if (sbr > 0) {
+        if (lane == 0) wait_progress(prog + sbr - 1, P.prog_base, min(sbc + 1, P.sb_cols));
+        __syncwarp();
       }
-      __syncwarp();
       const vp9b_txb *list = P.txb_intra[plane] + rg.start;
       for (uint32_t i = 0; i < rg.count; i++) {
         const vp9b_txb t = list[i];
@@ -499,197 +696,234 @@ __global__ void __launch_bounds__(kWaveWarps * 32) k_intra(const __grid_constant
         warp_residual<Px, PT>(P, tbuf[warp], t, lane);
       }
       __syncwarp();
-      __threadfence();
+      if (lane == 0) {
+        __threadfence();
+        st_release(prog + sbr, P.prog_base + (uint32_t)(sbc + 1));
+      }
+    } else if (lane == 0) {
+      // no intra block here: these samples were final after the inter stages, and everything to
+      // the left in this row is done (program order), so just publish
+      st_release(prog + sbr, P.prog_base + (uint32_t)(sbc + 1));
     }
-    if (lane == 0) st_release(flags + sb, P.epoch);
   }
 }
 
 // ------------------------------------------------------------------------------------------
-// stage 4: loop filter.  Per (superblock, plane) unit, wavefront order 2*row+col (a unit
-// depends on its left and above-right neighbours: the lag libvpx's own row-MT filter uses,
-// vp9_thread_common.c:38-87).  The unit stages its 64x64 (+8 halo left/top) tile in shared
-// memory, filters all vertical edges (lane = sample row) then all horizontal edges
-// (lane = sample column) exactly in vp9_filter_block_plane_ss00/ss11 order
-// (vp9_loopfilter.c:1241-1422) and writes the tile back.  Filter arithmetic:
-// vpx_dsp/loopfilter.c:360-743.
-struct LfTile {
-  uint16_t px[72 * 73];  // stride 73 to spread banks for column walks
-};
-
+// stage 4: loop filter.  One CTA per superblock (all planes), wavefront order 2*row+col: a
+// superblock depends on its left and above-right neighbours -- the lag libvpx's own row-MT
+// filter uses (vp9_thread_common.c:38-87) -- because libvpx filters superblock by superblock,
+// vertical edges then horizontal edges (vp9_loopfilter.c:1440-1467).  The CTA stages the
+// 64x64 luma tile and the chroma tiles (+8 samples halo left/top) in shared memory, filters
+// all vertical edges (thread = sample row) then all horizontal edges (thread = sample column)
+// in vp9_filter_block_plane_ss00/ss11 order (vp9_loopfilter.c:1241-1422) and writes the tiles
+// back with 8/16-byte vectors.  The tile interior is prefetched before the dependency wait.
+// Filter arithmetic: vpx_dsp/loopfilter.c:18-357 (8-bit) == :360-743 evaluated at bd.
 VP9B_DEV int sc_clamp(int t, int bd) {
   const int lim = 128 << (bd - 8);
   return clampi(t, -lim, lim - 1);
 }
 
 // s: pointer to q0 in the tile; step: distance between taps
-VP9B_DEV void lf_px(uint16_t *s, int step, int size, int blimit, int limit, int thresh, int bd) {
+template <typename Px>
+VP9B_DEV void lf_px(Px *s, int step, int size, int blimit, int limit, int thresh, int bd) {
   const int sh = bd - 8;
   const int p3 = s[-4 * step], p2 = s[-3 * step], p1 = s[-2 * step], p0 = s[-step];
   const int q0 = s[0], q1 = s[step], q2 = s[2 * step], q3 = s[3 * step];
   const int lim16 = limit << sh, blim16 = blimit << sh, one = 1 << sh;
   const bool fm = !(abs(p3 - p2) > lim16 || abs(p2 - p1) > lim16 || abs(p1 - p0) > lim16 || abs(q1 - q0) > lim16 ||
                     abs(q2 - q1) > lim16 || abs(q3 - q2) > lim16 || abs(p0 - q0) * 2 + abs(p1 - q1) / 2 > blim16);
+  if (!fm) return;  // filter_mask == 0: every variant leaves the samples untouched
   bool flat = false;
   if (size >= 8)
     flat = !(abs(p1 - p0) > one || abs(q1 - q0) > one || abs(p2 - p0) > one || abs(q2 - q0) > one ||
              abs(p3 - p0) > one || abs(q3 - q0) > one);
-  if (size == 16 && flat && fm) {
+  if (size == 16 && flat) {
     const int p7 = s[-8 * step], p6 = s[-7 * step], p5 = s[-6 * step], p4 = s[-5 * step];
     const int q4 = s[4 * step], q5 = s[5 * step], q6 = s[6 * step], q7 = s[7 * step];
     const bool flat2 = !(abs(p4 - p0) > one || abs(q4 - q0) > one || abs(p5 - p0) > one || abs(q5 - q0) > one ||
                          abs(p6 - p0) > one || abs(q6 - q0) > one || abs(p7 - p0) > one || abs(q7 - q0) > one);
     if (flat2) {
-      s[-7 * step] = (uint16_t)((p7 * 7 + p6 * 2 + p5 + p4 + p3 + p2 + p1 + p0 + q0 + 8) >> 4);
-      s[-6 * step] = (uint16_t)((p7 * 6 + p6 + p5 * 2 + p4 + p3 + p2 + p1 + p0 + q0 + q1 + 8) >> 4);
-      s[-5 * step] = (uint16_t)((p7 * 5 + p6 + p5 + p4 * 2 + p3 + p2 + p1 + p0 + q0 + q1 + q2 + 8) >> 4);
-      s[-4 * step] = (uint16_t)((p7 * 4 + p6 + p5 + p4 + p3 * 2 + p2 + p1 + p0 + q0 + q1 + q2 + q3 + 8) >> 4);
-      s[-3 * step] = (uint16_t)((p7 * 3 + p6 + p5 + p4 + p3 + p2 * 2 + p1 + p0 + q0 + q1 + q2 + q3 + q4 + 8) >> 4);
-      s[-2 * step] = (uint16_t)((p7 * 2 + p6 + p5 + p4 + p3 + p2 + p1 * 2 + p0 + q0 + q1 + q2 + q3 + q4 + q5 + 8) >> 4);
-      s[-1 * step] = (uint16_t)((p7 + p6 + p5 + p4 + p3 + p2 + p1 + p0 * 2 + q0 + q1 + q2 + q3 + q4 + q5 + q6 + 8) >> 4);
-      s[0] = (uint16_t)((p6 + p5 + p4 + p3 + p2 + p1 + p0 + q0 * 2 + q1 + q2 + q3 + q4 + q5 + q6 + q7 + 8) >> 4);
-      s[1 * step] = (uint16_t)((p5 + p4 + p3 + p2 + p1 + p0 + q0 + q1 * 2 + q2 + q3 + q4 + q5 + q6 + q7 * 2 + 8) >> 4);
-      s[2 * step] = (uint16_t)((p4 + p3 + p2 + p1 + p0 + q0 + q1 + q2 * 2 + q3 + q4 + q5 + q6 + q7 * 3 + 8) >> 4);
-      s[3 * step] = (uint16_t)((p3 + p2 + p1 + p0 + q0 + q1 + q2 + q3 * 2 + q4 + q5 + q6 + q7 * 4 + 8) >> 4);
-      s[4 * step] = (uint16_t)((p2 + p1 + p0 + q0 + q1 + q2 + q3 + q4 * 2 + q5 + q6 + q7 * 5 + 8) >> 4);
-      s[5 * step] = (uint16_t)((p1 + p0 + q0 + q1 + q2 + q3 + q4 + q5 * 2 + q6 + q7 * 6 + 8) >> 4);
-      s[6 * step] = (uint16_t)((p0 + q0 + q1 + q2 + q3 + q4 + q5 + q6 * 2 + q7 * 7 + 8) >> 4);
+      // 15-tap: running sums
+      const int sp = p6 + p5 + p4 + p3 + p2 + p1 + p0, sq = q0 + q1 + q2 + q3 + q4 + q5 + q6;
+      int a = p7 * 7 + p6 + sp + q0 + 8;  // op6 numerator: p7*7 + p6*2 + p5..p0 + q0
+      s[-7 * step] = (Px)(a >> 4);
+      a += p5 - p7 + q1 - p6;  s[-6 * step] = (Px)(a >> 4);  // p7*6 + p6 + p5*2 + p4..p0 + q0 + q1
+      a += p4 - p7 + q2 - p5;  s[-5 * step] = (Px)(a >> 4);
+      a += p3 - p7 + q3 - p4;  s[-4 * step] = (Px)(a >> 4);
+      a += p2 - p7 + q4 - p3;  s[-3 * step] = (Px)(a >> 4);
+      a += p1 - p7 + q5 - p2;  s[-2 * step] = (Px)(a >> 4);
+      a += p0 - p7 + q6 - p1;  s[-1 * step] = (Px)(a >> 4);
+      a += q0 - p7 + q7 - p0;  s[0] = (Px)(a >> 4);
+      a += q1 - p6 + q7 - q0;  s[1 * step] = (Px)(a >> 4);
+      a += q2 - p5 + q7 - q1;  s[2 * step] = (Px)(a >> 4);
+      a += q3 - p4 + q7 - q2;  s[3 * step] = (Px)(a >> 4);
+      a += q4 - p3 + q7 - q3;  s[4 * step] = (Px)(a >> 4);
+      a += q5 - p2 + q7 - q4;  s[5 * step] = (Px)(a >> 4);
+      a += q6 - p1 + q7 - q5;  s[6 * step] = (Px)(a >> 4);
+      (void)sq;
       return;
     }
   }
-  if (flat && fm) {
-    s[-3 * step] = (uint16_t)((p3 + p3 + p3 + 2 * p2 + p1 + p0 + q0 + 4) >> 3);
-    s[-2 * step] = (uint16_t)((p3 + p3 + p2 + 2 * p1 + p0 + q0 + q1 + 4) >> 3);
-    s[-1 * step] = (uint16_t)((p3 + p2 + p1 + 2 * p0 + q0 + q1 + q2 + 4) >> 3);
-    s[0] = (uint16_t)((p2 + p1 + p0 + 2 * q0 + q1 + q2 + q3 + 4) >> 3);
-    s[1 * step] = (uint16_t)((p1 + p0 + q0 + 2 * q1 + q2 + q3 + q3 + 4) >> 3);
-    s[2 * step] = (uint16_t)((p0 + q0 + q1 + 2 * q2 + q3 + q3 + q3 + 4) >> 3);
+  if (flat) {
+    s[-3 * step] = (Px)((p3 + p3 + p3 + 2 * p2 + p1 + p0 + q0 + 4) >> 3);
+    s[-2 * step] = (Px)((p3 + p3 + p2 + 2 * p1 + p0 + q0 + q1 + 4) >> 3);
+    s[-1 * step] = (Px)((p3 + p2 + p1 + 2 * p0 + q0 + q1 + q2 + 4) >> 3);
+    s[0] = (Px)((p2 + p1 + p0 + 2 * q0 + q1 + q2 + q3 + 4) >> 3);
+    s[1 * step] = (Px)((p1 + p0 + q0 + 2 * q1 + q2 + q3 + q3 + 4) >> 3);
+    s[2 * step] = (Px)((p0 + q0 + q1 + 2 * q2 + q3 + q3 + q3 + 4) >> 3);
     return;
   }
-  // filter4
+  // filter4 (mask is all ones here)
   const int off = 0x80 << sh;
   const int ps1 = p1 - off, ps0 = p0 - off, qs0 = q0 - off, qs1 = q1 - off;
   const int t16 = thresh << sh;
   const int hev = (abs(p1 - p0) > t16 || abs(q1 - q0) > t16) ? -1 : 0;
-  const int mask = fm ? -1 : 0;
   int f = sc_clamp(ps1 - qs1, bd) & hev;
-  f = sc_clamp(f + 3 * (qs0 - ps0), bd) & mask;
+  f = sc_clamp(f + 3 * (qs0 - ps0), bd);
   const int f1 = sc_clamp(f + 4, bd) >> 3, f2 = sc_clamp(f + 3, bd) >> 3;
-  s[0] = (uint16_t)(sc_clamp(qs0 - f1, bd) + off);
-  s[-step] = (uint16_t)(sc_clamp(ps0 + f2, bd) + off);
+  s[0] = (Px)(sc_clamp(qs0 - f1, bd) + off);
+  s[-step] = (Px)(sc_clamp(ps0 + f2, bd) + off);
   f = ((f1 + 1) >> 1) & ~hev;
-  s[step] = (uint16_t)(sc_clamp(qs1 - f, bd) + off);
-  s[-2 * step] = (uint16_t)(sc_clamp(ps1 + f, bd) + off);
+  s[step] = (Px)(sc_clamp(qs1 - f, bd) + off);
+  s[-2 * step] = (Px)(sc_clamp(ps1 + f, bd) + off);
 }
 
+template <typename Px> struct LfVec;       // vector type moving 8 samples
+template <> struct LfVec<uint8_t> { typedef uint2 T; };
+template <> struct LfVec<uint16_t> { typedef uint4 T; };
+// shared-memory rows are only 4-byte aligned (odd word stride): move vectors as 32-bit words
+VP9B_DEV void smem_put(void *d, uint2 v) { uint32_t *w = (uint32_t *)d; w[0] = v.x; w[1] = v.y; }
+VP9B_DEV void smem_put(void *d, uint4 v) { uint32_t *w = (uint32_t *)d; w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w; }
+VP9B_DEV void smem_get(const void *s, uint2 &v) { const uint32_t *w = (const uint32_t *)s; v.x = w[0]; v.y = w[1]; }
+VP9B_DEV void smem_get(const void *s, uint4 &v) { const uint32_t *w = (const uint32_t *)s; v.x = w[0]; v.y = w[1]; v.z = w[2]; v.w = w[3]; }
+
+// geometry of one plane's tile in shared memory
+struct LfPlane {
+  int n;        // tile size in samples (64 or 32)
+  int ts;       // row stride in samples
+  int off;      // offset (samples) of the tile in the shared array
+};
+
 template <typename Px>
-__global__ void __launch_bounds__(kWaveWarps * 32) k_loopfilter(const __grid_constant__ FrameParams P) {
-  __shared__ LfTile tiles[kWaveWarps];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int nsb = P.sb_cols * P.sb_rows;
-  const uint32_t total = 3u * nsb;
-  constexpr int TS = 73;
-  while (true) {
-    uint32_t tk = 0;
-    if (lane == 0) tk = atomicAdd(&P.tickets[1], 1u);
-    tk = __shfl_sync(0xffffffffu, tk, 0);
-    if (tk >= total) break;
-    const int plane = tk % 3, sb = P.order_lf[tk / 3];
-    const int sbr = sb / P.sb_cols, sbc = sb % P.sb_cols;
-    uint32_t *flags = P.flags_lf + plane * nsb;
-    // dependencies: left (r,c-1) and above-right (r-1,c+1) [or (r-1,c) in the last column]
-    if (lane < 2) {
-      int r = sbr, c = sbc - 1;
-      if (lane == 1) { r = sbr - 1; c = min(sbc + 1, P.sb_cols - 1); }
-      if (r >= 0 && c >= 0) {
-        const uint32_t *f = flags + r * P.sb_cols + c;
-        while (ld_acquire(f) != P.epoch) __nanosleep(40);
+__global__ void __launch_bounds__(192) k_loopfilter(const __grid_constant__ FrameParams P) {
+  // One persistent CTA per superblock ROW walks its row left to right.  The left neighbour is
+  // the previous iteration of the same CTA (its right-most 8 columns stay in shared memory);
+  // the above-right neighbour is tracked by a per-row progress counter of the row above.
+  extern __shared__ __align__(16) unsigned char lf_smem[];
+  Px *tile = (Px *)lf_smem;
+  typedef typename LfVec<Px>::T Vec;
+  const int tid = threadIdx.x, nthreads = blockDim.x;
+  const bool sub = P.ss_x != 0;  // 4:2:0 (else 4:4:4)
+  // stride in samples: (stride bytes / 4) odd -> conflict-free row-per-thread walks
+  const int tsY = sizeof(Px) == 1 ? 76 : 74, tsC = sub ? (sizeof(Px) == 1 ? 44 : 42) : tsY;
+  const int nC = sub ? 32 : 64;
+  const int pl_n[3] = { 64, nC, nC };
+  const int pl_ts[3] = { tsY, tsC, tsC };
+  const int pl_off[3] = { 0, 72 * tsY, 72 * tsY + (nC + 8) * tsC };
+  int my_plane, my_idx;
+  if (tid < 64) { my_plane = 0; my_idx = tid; }
+  else if (tid < 64 + nC) { my_plane = 1; my_idx = tid - 64; }
+  else { my_plane = 2; my_idx = tid - 64 - nC; }
+  const bool uvsub = my_plane && sub;
+  const int n = my_plane ? nC : 64, ts = my_plane ? tsC : tsY, nb = n >> 3;
+  Px *T = tile + (my_plane == 0 ? 0 : (my_plane == 1 ? 72 * tsY : 72 * tsY + (nC + 8) * tsC)) + 8 * ts + 8;
+  const int sbr = blockIdx.x;
+  const int mi_row = sbr * 8;
+  const int hy = sbr > 0 ? 8 : 0;
+  uint32_t *prog = P.prog_lf;  // [sb_rows] prog_base + superblocks done in the row
+  const uint32_t base = P.prog_base;
+  bool left_in_smem = false;
+  for (int sbc = 0; sbc < P.sb_cols; sbc++) {
+    const vp9b_lfm &M = P.lfm[sbr * P.sb_cols + sbc];
+    const uint64_t anyY = M.left_y[0] | M.left_y[1] | M.left_y[2] | M.above_y[0] | M.above_y[1] | M.above_y[2] | M.int_4x4_y;
+    const uint32_t anyUV = M.left_uv[0] | M.left_uv[1] | M.left_uv[2] | M.above_uv[0] | M.above_uv[1] | M.above_uv[2] | M.int_4x4_uv;
+    const bool work = (anyY | anyUV) != 0;
+    const int hx = sbc > 0 ? 8 : 0;
+    if (work) {
+      // ---- (A) tile interior (no other superblock has touched it yet) + left halo if not carried
+#pragma unroll
+      for (int p = 0; p < 3; p++) {
+        const int pn = pl_n[p], vpr = (pn >> 3) + ((hx && !left_in_smem) ? 1 : 0), voff = vpr - (pn >> 3);
+        const int stride = P.dst[p].stride;
+        const Px *g = (const Px *)P.dst[p].ptr + (size_t)(sbr * pn) * stride + sbc * pn;
+        Px *Tp = tile + pl_off[p] + 8 * pl_ts[p] + 8;
+        for (int i = tid; i < pn * vpr; i += nthreads) {
+          const int r = i / vpr, v = i % vpr - voff;
+          smem_put(Tp + r * pl_ts[p] + v * 8, __ldcg((const Vec *)(g + (size_t)r * stride + v * 8)));
+        }
       }
     }
-    __syncwarp();
-    const vp9b_lfm &M = P.lfm[sb];
-    const bool sub = plane && P.ss_x;  // 4:2:0 chroma
-    const int n = sub ? 32 : 64;       // tile size in samples
-    const int nb = n >> 3;             // 8-sample columns/rows per tile
-    const int stride = P.dst[plane].stride;
-    const int x0 = sbc * n, y0 = sbr * n;
-    Px *g = (Px *)P.dst[plane].ptr;
-    uint16_t *T = tiles[warp].px;
-    const int mi_row = sbr * 8;
-    // any edge in this unit?
-    uint64_t anym;
-    if (!sub) {
-      if (plane == 0 || !P.ss_x)
-        anym = M.left_y[0] | M.left_y[1] | M.left_y[2] | M.above_y[0] | M.above_y[1] | M.above_y[2] | M.int_4x4_y;
-      else anym = 0;
-    } else {
-      anym = (uint64_t)(M.left_uv[0] | M.left_uv[1] | M.left_uv[2] | M.above_uv[0] | M.above_uv[1] | M.above_uv[2] |
-                        M.int_4x4_uv);
+    // ---- (B) the row above must have finished superblock sbc+1 (above-right)
+    if (hy) {
+      if (tid == 0) wait_progress(prog + sbr - 1, base, min(sbc + 2, P.sb_cols));
+      __syncthreads();
     }
-    if (anym) {
-      const int hx = x0 >= 8 ? 8 : 0, hy = y0 >= 8 ? 8 : 0;  // halo present?
-      // ---- load tile: rows y0-hy .. y0+n-1, cols x0-hx .. x0+n-1 ; tile origin (8,8) = (x0,y0)
-      for (int ry = 8 - hy; ry < 8 + n; ry++) {
-        const Px *src = g + (size_t)(y0 + ry - 8) * stride + x0 - 8;
-        for (int cx = 8 - hx + lane; cx < 8 + n; cx += 32) T[ry * TS + cx] = (uint16_t)__ldcg(src + cx);
-      }
-      __syncwarp();
-      // ---- vertical edges: lane = sample row
-      for (int rb = 0; rb < n; rb += 32) {
-        const int y = rb + lane;          // row inside the tile
-        const int r8 = y >> 3;            // 8-sample row index inside the unit
-        const int pr = r8 & ~1;           // first row of the row pair (filter_selectively_vert_row2)
-        const int mrow = sub ? 2 * pr : pr;  // mi row of the pair start, for the frame-height test
-        const bool active = (mi_row + mrow < P.mi_rows);
-        if (active) {
-          uint16_t *row = T + (8 + y) * TS + 8;
-          for (int c = 0; c < nb; c++) {
-            int b0, b1;  // bit positions of this column in rows pr and pr+1
-            uint32_t m16, m8, m4, m4i;
-            int lvl_own, lvl_first;
-            if (!sub) {
-              b0 = pr * 8 + c; b1 = b0 + 8;
-              const int bo = r8 * 8 + c;
-              m16 = (uint32_t)((M.left_y[2] >> bo) & 1) | ((uint32_t)((M.left_y[2] >> b0) & (M.left_y[2] >> b1) & 1) << 1);
-              m8 = (uint32_t)((M.left_y[1] >> bo) & 1);
-              m4 = (uint32_t)((M.left_y[0] >> bo) & 1);
-              m4i = (uint32_t)((M.int_4x4_y >> bo) & 1);
-              lvl_own = M.lfl_y[bo];
-              lvl_first = M.lfl_y[b0];
-            } else {
-              b0 = pr * 4 + c; b1 = b0 + 4;
-              const int bo = r8 * 4 + c;
-              m16 = (uint32_t)((M.left_uv[2] >> bo) & 1) | ((uint32_t)((M.left_uv[2] >> b0) & (M.left_uv[2] >> b1) & 1) << 1);
-              m8 = (uint32_t)((M.left_uv[1] >> bo) & 1);
-              m4 = (uint32_t)((M.left_uv[0] >> bo) & 1);
-              m4i = (uint32_t)((M.int_4x4_uv >> bo) & 1);
-              lvl_own = M.lfl_y[(2 * r8) * 8 + 2 * c];
-              lvl_first = M.lfl_y[(2 * pr) * 8 + 2 * c];
-            }
-            uint16_t *s = row + c * 8;
-            if (m16 & 1) {
-              const int lv = (m16 & 2) ? lvl_first : lvl_own;  // dual 16: both bands use the first band's level
-              lf_px(s, 1, 16, P.lf_mblim[lv], P.lf_lim[lv], lv >> 4, P.bd);
-            }
-            if (m8) lf_px(s, 1, 8, P.lf_mblim[lvl_own], P.lf_lim[lvl_own], lvl_own >> 4, P.bd);
-            if (m4) lf_px(s, 1, 4, P.lf_mblim[lvl_own], P.lf_lim[lvl_own], lvl_own >> 4, P.bd);
-            if (m4i) lf_px(s + 4, 1, 4, P.lf_mblim[lvl_own], P.lf_lim[lvl_own], lvl_own >> 4, P.bd);
+    if (work) {
+      // ---- (C) top halo rows
+      if (hy) {
+#pragma unroll
+        for (int p = 0; p < 3; p++) {
+          const int pn = pl_n[p], vpr = pn >> 3, stride = P.dst[p].stride;
+          const Px *g = (const Px *)P.dst[p].ptr + (size_t)(sbr * pn) * stride + sbc * pn;
+          Px *Tp = tile + pl_off[p] + 8 * pl_ts[p] + 8;
+          for (int i = tid; i < 8 * vpr; i += nthreads) {
+            const int r = i / vpr - 8, v = i % vpr;
+            smem_put(Tp + r * pl_ts[p] + v * 8, __ldcg((const Vec *)(g + (ptrdiff_t)r * stride + v * 8)));
           }
         }
       }
-      __syncwarp();
-      // ---- horizontal edges: lane = sample column
-      for (int cb = 0; cb < n; cb += 32) {
-        const int x = cb + lane;
-        const int c = x >> 3;
-        uint16_t *col = T + 8 * TS + 8 + x;
+      __syncthreads();
+      // ---- (D) vertical edges: thread = sample row
+      {
+        const int y = my_idx, r8 = y >> 3, pr = r8 & ~1;
+        const int mrow = uvsub ? 2 * pr : pr;
+        if (mi_row + mrow < P.mi_rows) {
+          uint32_t m16, m16n, m8, m4, m4i;
+          if (!uvsub) {
+            m16 = (uint32_t)(M.left_y[2] >> (r8 * 8)) & 0xff;
+            m16n = (uint32_t)(M.left_y[2] >> (pr * 8)) & (uint32_t)(M.left_y[2] >> (pr * 8 + 8)) & 0xff;
+            m8 = (uint32_t)(M.left_y[1] >> (r8 * 8)) & 0xff;
+            m4 = (uint32_t)(M.left_y[0] >> (r8 * 8)) & 0xff;
+            m4i = (uint32_t)(M.int_4x4_y >> (r8 * 8)) & 0xff;
+          } else {
+            m16 = (uint32_t)(M.left_uv[2] >> (r8 * 4)) & 0xf;
+            m16n = (uint32_t)(M.left_uv[2] >> (pr * 4)) & (uint32_t)(M.left_uv[2] >> (pr * 4 + 4)) & 0xf;
+            m8 = (uint32_t)(M.left_uv[1] >> (r8 * 4)) & 0xf;
+            m4 = (uint32_t)(M.left_uv[0] >> (r8 * 4)) & 0xf;
+            m4i = (uint32_t)(M.int_4x4_uv >> (r8 * 4)) & 0xf;
+          }
+          uint32_t all = m16 | m8 | m4 | m4i;
+          Px *row = T + y * ts;
+          while (all) {
+            const int c = __ffs(all) - 1;
+            all &= all - 1;
+            const int lo = uvsub ? M.lfl_y[(2 * r8) * 8 + 2 * c] : M.lfl_y[r8 * 8 + c];
+            Px *s = row + c * 8;
+            if ((m16 >> c) & 1) {
+              // dual 16 (both rows of the pair set): both bands use the first band's level
+              const int lv = ((m16n >> c) & 1) ? (uvsub ? M.lfl_y[(2 * pr) * 8 + 2 * c] : M.lfl_y[pr * 8 + c]) : lo;
+              lf_px<Px>(s, 1, 16, P.lf_mblim[lv], P.lf_lim[lv], lv >> 4, P.bd);
+            } else if ((m8 >> c) & 1) {
+              lf_px<Px>(s, 1, 8, P.lf_mblim[lo], P.lf_lim[lo], lo >> 4, P.bd);
+            } else if ((m4 >> c) & 1) {
+              lf_px<Px>(s, 1, 4, P.lf_mblim[lo], P.lf_lim[lo], lo >> 4, P.bd);
+            }
+            if ((m4i >> c) & 1) lf_px<Px>(s + 4, 1, 4, P.lf_mblim[lo], P.lf_lim[lo], lo >> 4, P.bd);
+          }
+        }
+      }
+      __syncthreads();
+      // ---- (E) horizontal edges: thread = sample column
+      {
+        const int x = my_idx, c = x >> 3;
+        Px *col = T + x;
         for (int r = 0; r < nb; r++) {
-          const int mrow = sub ? 2 * r : r;
+          const int mrow = uvsub ? 2 * r : r;
           if (mi_row + mrow >= P.mi_rows) break;
           uint32_t row16, row8, row4, row4i;
           const uint8_t *lfl;
           int lstep;
-          if (!sub) {
+          if (!uvsub) {
             row16 = (uint32_t)(M.above_y[2] >> (r * 8)) & 0xff;
             row8 = (uint32_t)(M.above_y[1] >> (r * 8)) & 0xff;
             row4 = (uint32_t)(M.above_y[0] >> (r * 8)) & 0xff;
@@ -706,36 +940,68 @@ __global__ void __launch_bounds__(kWaveWarps * 32) k_loopfilter(const __grid_con
             lstep = 2;
           }
           if (mi_row + mrow == 0) row16 = row8 = row4 = 0;
-          uint16_t *s = col + r * 8 * TS;
+          if (!(((row16 | row8 | row4 | row4i) >> c) & 1)) continue;
+          Px *s = col + r * 8 * ts;
           const int lvl = lfl[c * lstep];
           if ((row16 >> c) & 1) {
-            // greedy pairing from the left: the second block of a pair uses the first one's level
+            // greedy pairing from the left (vpx_lpf_horizontal_16_dual): the second block of a
+            // pair is filtered with the first block's thresholds
             int start = c;
             while (start > 0 && ((row16 >> (start - 1)) & 1)) start--;
             const int lv = ((c - start) & 1) ? lfl[(c - 1) * lstep] : lvl;
-            lf_px(s, TS, 16, P.lf_mblim[lv], P.lf_lim[lv], lv >> 4, P.bd);
+            lf_px<Px>(s, ts, 16, P.lf_mblim[lv], P.lf_lim[lv], lv >> 4, P.bd);
           } else if ((row8 >> c) & 1) {
-            lf_px(s, TS, 8, P.lf_mblim[lvl], P.lf_lim[lvl], lvl >> 4, P.bd);
-            if ((row4i >> c) & 1) lf_px(s + 4 * TS, TS, 4, P.lf_mblim[lvl], P.lf_lim[lvl], lvl >> 4, P.bd);
+            lf_px<Px>(s, ts, 8, P.lf_mblim[lvl], P.lf_lim[lvl], lvl >> 4, P.bd);
           } else if ((row4 >> c) & 1) {
-            lf_px(s, TS, 4, P.lf_mblim[lvl], P.lf_lim[lvl], lvl >> 4, P.bd);
-            if ((row4i >> c) & 1) lf_px(s + 4 * TS, TS, 4, P.lf_mblim[lvl], P.lf_lim[lvl], lvl >> 4, P.bd);
-          } else if ((row4i >> c) & 1) {
-            lf_px(s + 4 * TS, TS, 4, P.lf_mblim[lvl], P.lf_lim[lvl], lvl >> 4, P.bd);
+            lf_px<Px>(s, ts, 4, P.lf_mblim[lvl], P.lf_lim[lvl], lvl >> 4, P.bd);
           }
+          if (!((row16 >> c) & 1) && ((row4i >> c) & 1))
+            lf_px<Px>(s + 4 * ts, ts, 4, P.lf_mblim[lvl], P.lf_lim[lvl], lvl >> 4, P.bd);
         }
       }
-      __syncwarp();
-      // ---- store: top halo rows (cols x0..), then body rows (cols x0-hx..)
-      for (int ry = 8 - hy; ry < 8 + n; ry++) {
-        Px *dstp = g + (size_t)(y0 + ry - 8) * stride + x0 - 8;
-        const int c_lo = (ry < 8) ? 8 : 8 - hx;
-        for (int cx = c_lo + lane; cx < 8 + n; cx += 32) __stcg(dstp + cx, (Px)T[ry * TS + cx]);
+      __syncthreads();
+      // ---- (F) store: top halo rows (columns of this superblock only), body rows incl. left halo
+#pragma unroll
+      for (int p = 0; p < 3; p++) {
+        const int pn = pl_n[p], pts = pl_ts[p], stride = P.dst[p].stride;
+        Px *g = (Px *)P.dst[p].ptr + (size_t)(sbr * pn) * stride + sbc * pn;
+        Px *Tp = tile + pl_off[p] + 8 * pts + 8;
+        const int vtop = pn >> 3, vbody = (pn >> 3) + (hx ? 1 : 0);
+        if (hy)
+          for (int i = tid; i < 8 * vtop; i += nthreads) {
+            const int r = i / vtop - 8, v = i % vtop;
+            Vec vv;
+            smem_get(Tp + r * pts + v * 8, vv);
+            __stcg((Vec *)(g + (ptrdiff_t)r * stride + v * 8), vv);
+          }
+        for (int i = tid; i < pn * vbody; i += nthreads) {
+          const int r = i / vbody, v = i % vbody - (hx ? 1 : 0);
+          Vec vv;
+          smem_get(Tp + r * pts + v * 8, vv);
+          __stcg((Vec *)(g + (size_t)r * stride + v * 8), vv);
+        }
       }
-      __syncwarp();
-      __threadfence();
+      __syncthreads();
+      // ---- (G) carry the right-most 8 columns over as the next superblock's left halo
+#pragma unroll
+      for (int p = 0; p < 3; p++) {
+        const int pn = pl_n[p], pts = pl_ts[p];
+        Px *Tp = tile + pl_off[p] + 8 * pts + 8;
+        for (int r = tid; r < pn; r += nthreads) {
+          Vec vv;
+          smem_get(Tp + r * pts + pn - 8, vv);
+          smem_put(Tp + r * pts - 8, vv);
+        }
+      }
+      left_in_smem = true;
+    } else {
+      left_in_smem = false;
     }
-    if (lane == 0) st_release(flags + sb, P.epoch);
+    __syncthreads();
+    if (tid == 0) {
+      __threadfence();
+      st_release(prog + sbr, base + (uint32_t)(sbc + 1));
+    }
   }
 }
 
@@ -769,7 +1035,7 @@ struct vp9gpu_ctx {
   // per-geometry workspace
   int ws_sb_cols = 0, ws_sb_rows = 0, ws_mi_cols = 0, ws_mi_rows = 0;
   MiEntry *d_mi = nullptr;
-  uint32_t *d_order_intra = nullptr, *d_order_lf = nullptr, *d_flags = nullptr, *d_tickets = nullptr;
+  uint32_t *d_tickets = nullptr;  // wavefront progress counters
   uint32_t epoch = 0;
   int stop_stage = 0;
   uint64_t launches = 0;
@@ -801,6 +1067,14 @@ static int init_tables(vp9gpu_ctx *ctx) {
   int8_t f8[4 * 16 * 8];
   for (int i = 0; i < 4 * 16 * 8; i++) f8[i] = (int8_t)(kSubpelFilters[i] > 127 ? 127 : kSubpelFilters[i]);
   CK(cudaMemcpyToSymbol(d_filters, f8, sizeof(f8)));
+  uint32_t t4[4 * 16 * 2];
+  for (int i = 0; i < 4 * 16; i++)
+    for (int hhalf = 0; hhalf < 2; hhalf++) {
+      uint32_t w = 0;
+      for (int k = 0; k < 4; k++) w |= (uint32_t)(uint8_t)(int8_t)f8[i * 8 + hhalf * 4 + k] << (8 * k);
+      t4[i * 2 + hhalf] = w;
+    }
+  CK(cudaMemcpyToSymbol(d_taps4, t4, sizeof(t4)));
   ctx->tables_ready = true;
   return 0;
 }
@@ -832,7 +1106,7 @@ extern "C" void vp9gpu_destroy(vp9gpu_ctx *ctx) {
     cudaEventDestroy(ctx->ring_ev[i]);
   }
   for (int i = 0; i < 6; i++) cudaEventDestroy(ctx->prof_ev[i]);
-  cudaFree(ctx->d_mi); cudaFree(ctx->d_order_intra); cudaFree(ctx->d_order_lf); cudaFree(ctx->d_flags);
+  cudaFree(ctx->d_mi);
   cudaFree(ctx->d_tickets);
   cudaStreamDestroy(ctx->stream);
   delete ctx;
@@ -900,35 +1174,17 @@ static int setup_slot(vp9gpu_ctx *ctx, int s, uint32_t w, uint32_t h, int bd, in
 static int setup_workspace(vp9gpu_ctx *ctx, const vp9b_frame_hdr *h) {
   if ((int)h->mi_cols != ctx->ws_mi_cols || (int)h->mi_rows != ctx->ws_mi_rows) {
     CK(cudaStreamSynchronize(ctx->stream));
-    cudaFree(ctx->d_mi); cudaFree(ctx->d_order_intra); cudaFree(ctx->d_order_lf); cudaFree(ctx->d_flags);
-    ctx->d_mi = nullptr; ctx->d_order_intra = ctx->d_order_lf = ctx->d_flags = nullptr;
-    const int nsb = h->sb_cols * h->sb_rows;
+    cudaFree(ctx->d_mi);
+    ctx->d_mi = nullptr;
     CK(cudaMalloc(&ctx->d_mi, sizeof(MiEntry) * (size_t)h->mi_cols * h->mi_rows));
     CK(cudaMemsetAsync(ctx->d_mi, 0, sizeof(MiEntry) * (size_t)h->mi_cols * h->mi_rows, ctx->stream));
-    CK(cudaMalloc(&ctx->d_order_intra, sizeof(uint32_t) * nsb));
-    CK(cudaMalloc(&ctx->d_order_lf, sizeof(uint32_t) * nsb));
-    CK(cudaMalloc(&ctx->d_flags, sizeof(uint32_t) * nsb * 6));
-    CK(cudaMemsetAsync(ctx->d_flags, 0, sizeof(uint32_t) * nsb * 6, ctx->stream));
-    if (!ctx->d_tickets) CK(cudaMalloc(&ctx->d_tickets, sizeof(uint32_t) * 4));
-    // ticket orders: every dependency of a unit has a smaller ticket
-    std::vector<uint32_t> oi, ol;
-    const int R = h->sb_rows, Cc = h->sb_cols;
-    for (int d = 0; d < R + Cc - 1; d++)
-      for (int r = 0; r < R; r++) {
-        const int c = d - r;
-        if (c >= 0 && c < Cc) oi.push_back(r * Cc + c);
-      }
-    for (int d = 0; d < 2 * R + Cc; d++)
-      for (int r = 0; r < R; r++) {
-        const int c = d - 2 * r;
-        if (c >= 0 && c < Cc) ol.push_back(r * Cc + c);
-      }
-    CK(cudaMemcpyAsync(ctx->d_order_intra, oi.data(), sizeof(uint32_t) * nsb, cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaMemcpyAsync(ctx->d_order_lf, ol.data(), sizeof(uint32_t) * nsb, cudaMemcpyHostToDevice, ctx->stream));
+    if (!ctx->d_tickets) {
+      CK(cudaMalloc(&ctx->d_tickets, sizeof(uint32_t) * 4096));
+      CK(cudaMemsetAsync(ctx->d_tickets, 0, sizeof(uint32_t) * 4096, ctx->stream));
+    }
     CK(cudaStreamSynchronize(ctx->stream));
     ctx->ws_mi_cols = h->mi_cols; ctx->ws_mi_rows = h->mi_rows;
     ctx->ws_sb_cols = h->sb_cols; ctx->ws_sb_rows = h->sb_rows;
-    ctx->epoch = 0;
   }
   return 0;
 }
@@ -945,12 +1201,22 @@ static int launch_stages(vp9gpu_ctx *ctx, const FrameParams &P, const vp9b_frame
       ctx->launches++;
     }
     if (prof) cudaEventRecord(ctx->prof_ev[1], st);
-    for (int p = 0; p < 3; p++) {
-      const int sx = p ? P.ss_x : 0, sy = p ? P.ss_y : 0;
-      const int pw = (P.mi_cols * 8) >> sx, ph = (P.mi_rows * 8) >> sy;
-      dim3 blk(32, 8), grd((pw + 31) / 32, (ph + 7) / 8);
-      k_inter_pred_generic<Px><<<grd, blk, 0, st>>>(P, p);
+    if (sizeof(Px) == 1) {
+      const int pwy = P.mi_cols * 8, phy = P.mi_rows * 8;
+      const int pwc = pwy >> P.ss_x, phc = phy >> P.ss_y;
+      const int gx_y = (pwy + 31) / 32, gy_y = (phy + 127) / 128;
+      const int gx_c = (pwc + 31) / 32, gy_c = P.ss_x ? (phc + 63) / 64 : (phc + 127) / 128;
+      const int ncta_y = gx_y * gy_y, ncta_c = gx_c * gy_c;
+      k_inter_pred_u8<<<ncta_y + 2 * ncta_c, 128, 0, st>>>(P, ncta_y, ncta_c, gx_y, gx_c);
       ctx->launches++;
+    } else {
+      for (int p = 0; p < 3; p++) {
+        const int sx = p ? P.ss_x : 0, sy = p ? P.ss_y : 0;
+        const int pw = (P.mi_cols * 8) >> sx, ph = (P.mi_rows * 8) >> sy;
+        dim3 blk(32, 8), grd((pw + 31) / 32, (ph + 7) / 8);
+        k_inter_pred_generic<Px><<<grd, blk, 0, st>>>(P, p);
+        ctx->launches++;
+      }
     }
     if (prof) cudaEventRecord(ctx->prof_ev[2], st);
     if (stop != 1 && P.n_txb_inter) {
@@ -964,8 +1230,7 @@ static int launch_stages(vp9gpu_ctx *ctx, const FrameParams &P, const vp9b_frame
   }
   if (prof) cudaEventRecord(ctx->prof_ev[3], st);
   if (stop == 1 || stop == 2) return 0;
-  const int nsb = P.sb_cols * P.sb_rows;
-  const int wave_blocks = std::min((3 * nsb + kWaveWarps - 1) / kWaveWarps, ctx->num_sms * 4);
+  const int wave_blocks = (3 * P.sb_rows + kWaveWarps - 1) / kWaveWarps;
   {
     const uint32_t n_intra = h->sec[VP9B_SEC_TXB_INTRA_Y].count + h->sec[VP9B_SEC_TXB_INTRA_U].count +
                              h->sec[VP9B_SEC_TXB_INTRA_V].count;
@@ -977,7 +1242,11 @@ static int launch_stages(vp9gpu_ctx *ctx, const FrameParams &P, const vp9b_frame
   if (prof) cudaEventRecord(ctx->prof_ev[4], st);
   if (stop == 3) return 0;
   if (h->lf_level) {
-    k_loopfilter<Px><<<wave_blocks, kWaveWarps * 32, 0, st>>>(P);
+    const bool sub = P.ss_x != 0;
+    const int threads = sub ? 128 : 192;
+    const int tsY = sizeof(Px) == 1 ? 76 : 74, tsC = sub ? (sizeof(Px) == 1 ? 44 : 42) : tsY, nC = sub ? 32 : 64;
+    const size_t smem = sizeof(Px) * (size_t)(72 * tsY + 2 * (nC + 8) * tsC) + 32;
+    k_loopfilter<Px><<<P.sb_rows, threads, smem, st>>>(P);
     ctx->launches++;
   }
   if (prof) {
@@ -1000,7 +1269,17 @@ static int submit_device(vp9gpu_ctx *ctx, const uint8_t *d_packed, const vp9b_fr
     return VP9B_ERR_UNSUP;
   }
   CK(cudaSetDevice(ctx->device));
-  int e = setup_slot(ctx, h->dst_slot, h->width, h->height, h->bit_depth, h->ss_x, h->ss_y);
+  int e = 0;
+  if (!ctx->slot[h->dst_slot].base) {
+    // first use: size the whole pool now so that no allocation happens in the steady state
+    for (int s2 = 0; s2 < VP9B_NUM_SLOTS && !e; s2++)
+      if (!ctx->slot[s2].base) {
+        e = setup_slot(ctx, s2, h->width, h->height, h->bit_depth, h->ss_x, h->ss_y);
+        ctx->slot[s2].valid = false;
+      }
+    if (e) return e;
+  }
+  e = setup_slot(ctx, h->dst_slot, h->width, h->height, h->bit_depth, h->ss_x, h->ss_y);
   if (e) return e;
   e = setup_workspace(ctx, h);
   if (e) return e;
@@ -1041,16 +1320,17 @@ static int submit_device(vp9gpu_ctx *ctx, const uint8_t *d_packed, const vp9b_fr
   P.coef = d_packed + h->sec[VP9B_SEC_COEF].offset;
   P.lfm = (const vp9b_lfm *)(d_packed + h->sec[VP9B_SEC_LFM].offset);
   P.mi = ctx->d_mi;
-  P.order_intra = ctx->d_order_intra;
-  P.order_lf = ctx->d_order_lf;
   const int nsb = h->sb_cols * h->sb_rows;
-  P.flags_intra = ctx->d_flags;
-  P.flags_lf = ctx->d_flags + 3 * nsb;
-  P.tickets = ctx->d_tickets;
-  P.epoch = ++ctx->epoch;
+  // progress counters: [0, 3*1024) intra (plane, row), [3072, 4096) loop filter.  Values are
+  // prog_base + count with prog_base advancing by 2048 per frame; cleared only when it wraps.
+  if (h->sb_rows > 1024 || h->sb_cols >= 2048) { ctx->err = "frame too large"; return VP9B_ERR_UNSUP; }
+  ctx->epoch++;
+  if ((ctx->epoch & 0xfffff) == 0) CK(cudaMemsetAsync(ctx->d_tickets, 0, sizeof(uint32_t) * 4096, ctx->stream));
+  P.prog_intra = ctx->d_tickets;
+  P.prog_lf = ctx->d_tickets + 3072;
+  P.prog_base = (ctx->epoch & 0xfffff) << 11;
   memcpy(P.lf_lim, h->lf_lim, 64);
   memcpy(P.lf_mblim, h->lf_mblim, 64);
-  CK(cudaMemsetAsync(ctx->d_tickets, 0, sizeof(uint32_t) * 4, ctx->stream));
   if (h->bit_depth == 8) e = launch_stages<uint8_t, int>(ctx, P, h);
   else e = launch_stages<uint16_t, long long>(ctx, P, h);
   if (e) return e;
@@ -1072,14 +1352,18 @@ extern "C" int vp9gpu_frame_submit(vp9gpu_ctx *ctx, const void *packed, size_t b
   ctx->ring_pos = (k + 1) % vp9gpu_ctx::kRing;
   CK(cudaEventSynchronize(ctx->ring_ev[k]));  // previous user of this ring entry is done
   if (ctx->ring_bytes[k] < bytes) {
-    const size_t nb = (bytes * 3 / 2 + (1 << 20)) & ~(size_t)4095;
-    cudaFreeHost(ctx->h_pinned[k]);
-    cudaFree(ctx->d_packed[k]);
-    ctx->h_pinned[k] = ctx->d_packed[k] = nullptr;
-    ctx->ring_bytes[k] = 0;
-    CK(cudaMallocHost(&ctx->h_pinned[k], nb));
-    CK(cudaMalloc(&ctx->d_packed[k], nb));
-    ctx->ring_bytes[k] = nb;
+    // grow every ring entry together (allocation synchronises the device: do it rarely)
+    const size_t nb = std::max((bytes * 3 / 2 + (1 << 20)) & ~(size_t)4095, (size_t)4 << 20);
+    CK(cudaStreamSynchronize(ctx->stream));
+    for (int i = 0; i < vp9gpu_ctx::kRing; i++) {
+      cudaFreeHost(ctx->h_pinned[i]);
+      cudaFree(ctx->d_packed[i]);
+      ctx->h_pinned[i] = ctx->d_packed[i] = nullptr;
+      ctx->ring_bytes[i] = 0;
+      CK(cudaMallocHost(&ctx->h_pinned[i], nb));
+      CK(cudaMalloc(&ctx->d_packed[i], nb));
+      ctx->ring_bytes[i] = nb;
+    }
   }
   memcpy(ctx->h_pinned[k], packed, h->total_bytes);
   CK(cudaMemcpyAsync(ctx->d_packed[k], ctx->h_pinned[k], h->total_bytes, cudaMemcpyHostToDevice, ctx->stream));
@@ -1104,8 +1388,15 @@ extern "C" int vp9gpu_free_packed(vp9gpu_ctx *ctx, void *d_packed) {
   return 0;
 }
 
-extern "C" int vp9gpu_get_frame(vp9gpu_ctx *ctx, int slot, uint8_t *y, uint8_t *u, uint8_t *v, int y_stride,
-                                int uv_stride) {
+extern "C" void *vp9gpu_alloc_host(size_t bytes) {
+  void *p = nullptr;
+  if (cudaMallocHost(&p, bytes) != cudaSuccess) return nullptr;
+  return p;
+}
+extern "C" void vp9gpu_free_host(void *p) { cudaFreeHost(p); }
+
+static int get_frame_impl(vp9gpu_ctx *ctx, int slot, uint8_t *y, uint8_t *u, uint8_t *v, int y_stride, int uv_stride,
+                          bool sync) {
   if (!ctx || slot < 0 || slot >= VP9B_NUM_SLOTS || !ctx->slot[slot].valid) return VP9B_ERR_INVALID;
   CK(cudaSetDevice(ctx->device));
   const DevFrame &f = ctx->slot[slot];
@@ -1116,8 +1407,17 @@ extern "C" int vp9gpu_get_frame(vp9gpu_ctx *ctx, int slot, uint8_t *y, uint8_t *
     CK(cudaMemcpy2DAsync(out[p], p ? uv_stride : y_stride, f.pl[p].ptr, (size_t)f.pl[p].stride * f.bps,
                          (size_t)w * f.bps, hh, cudaMemcpyDeviceToHost, ctx->stream));
   }
-  CK(cudaStreamSynchronize(ctx->stream));
+  if (sync) CK(cudaStreamSynchronize(ctx->stream));
   return 0;
+}
+
+extern "C" int vp9gpu_get_frame(vp9gpu_ctx *ctx, int slot, uint8_t *y, uint8_t *u, uint8_t *v, int y_stride,
+                                int uv_stride) {
+  return get_frame_impl(ctx, slot, y, u, v, y_stride, uv_stride, true);
+}
+extern "C" int vp9gpu_get_frame_async(vp9gpu_ctx *ctx, int slot, uint8_t *y, uint8_t *u, uint8_t *v, int y_stride,
+                                      int uv_stride) {
+  return get_frame_impl(ctx, slot, y, u, v, y_stride, uv_stride, false);
 }
 
 extern "C" int vp9gpu_set_frame(vp9gpu_ctx *ctx, int slot, uint32_t width, uint32_t height, int bit_depth, int ss_x,

@@ -154,6 +154,14 @@ int vp9gpu_sync(vp9gpu_ctx *ctx);
  * Strides in bytes.  Synchronous.  (role of vp9_get_raw_frame, vp9_decoder.c:494) */
 int vp9gpu_get_frame(vp9gpu_ctx *ctx, int slot, uint8_t *y, uint8_t *u, uint8_t *v,
                      int y_stride, int uv_stride);
+/* Same without the final synchronisation: the copy is ordered after the reconstruction of the
+ * slot on the ctx stream; call vp9gpu_sync() (or reuse the ctx) before reading the buffers.
+ * Use pinned destination buffers (vp9gpu_alloc_host) so that the copy overlaps later frames. */
+int vp9gpu_get_frame_async(vp9gpu_ctx *ctx, int slot, uint8_t *y, uint8_t *u, uint8_t *v, int y_stride,
+                           int uv_stride);
+/* Page-locked host memory for output frames / packed buffers. */
+void *vp9gpu_alloc_host(size_t bytes);
+void vp9gpu_free_host(void *p);
 /* H2D copy into a slot (VP8_SET_REFERENCE, vp9_decoder.c:258-331, and tests). */
 int vp9gpu_set_frame(vp9gpu_ctx *ctx, int slot, uint32_t width, uint32_t height, int bit_depth,
                      int ss_x, int ss_y, const uint8_t *y, const uint8_t *u, const uint8_t *v,
@@ -208,6 +216,10 @@ int vp9b_decoder_get_frame(vp9b_decoder *d, vp9b_image *img);
 /* Copy the cropped planes of the shown frame to host memory (strides in bytes). */
 int vp9b_decoder_read_frame(vp9b_decoder *d, const vp9b_image *img, uint8_t *y, uint8_t *u,
                             uint8_t *v, int y_stride, int uv_stride);
+/* Asynchronous variant (see vp9gpu_get_frame_async) and the matching wait. */
+int vp9b_decoder_read_frame_async(vp9b_decoder *d, const vp9b_image *img, uint8_t *y, uint8_t *u, uint8_t *v,
+                                  int y_stride, int uv_stride);
+int vp9b_decoder_sync(vp9b_decoder *d);
 vp9gpu_ctx *vp9b_decoder_gpu(vp9b_decoder *d);
 vp9b_parser *vp9b_decoder_parser(vp9b_decoder *d);
 
