@@ -661,8 +661,15 @@ VP9B_DEV void warp_intra_predict(const FrameParams &P, IntraEdge &E, const vp9b_
 constexpr int kWaveWarps = 4;
 
 // progress counters hold prog_base + count; stale values of earlier frames compare as negative
+VP9B_DEV uint32_t ld_relaxed(const uint32_t *p) {
+  uint32_t v;
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
 VP9B_DEV void wait_progress(const uint32_t *p, uint32_t base, int need) {
-  while ((int)(ld_acquire(p) - base) < need) __nanosleep(20);
+  // poll with relaxed loads (no L1 invalidation per poll), then one acquire to order the data reads
+  while ((int)(ld_relaxed(p) - base) < need) __nanosleep(20);
+  (void)ld_acquire(p);
 }
 
 // One persistent warp per (superblock row, plane) walks its row left to right.  Intra edges
@@ -809,6 +816,9 @@ __global__ void __launch_bounds__(192) k_loopfilter(const __grid_constant__ Fram
   // One persistent CTA per superblock ROW walks its row left to right.  The left neighbour is
   // the previous iteration of the same CTA (its right-most 8 columns stay in shared memory);
   // the above-right neighbour is tracked by a per-row progress counter of the row above.
+  // Global latency is kept off the row's critical path: the interior of superblock c+1 is
+  // prefetched into registers while superblock c is filtered, and the top halo (the only part
+  // that depends on the row above) is fetched before the vertical pass and consumed after it.
   extern __shared__ __align__(16) unsigned char lf_smem[];
   Px *tile = (Px *)lf_smem;
   typedef typename LfVec<Px>::T Vec;
@@ -817,58 +827,105 @@ __global__ void __launch_bounds__(192) k_loopfilter(const __grid_constant__ Fram
   // stride in samples: (stride bytes / 4) odd -> conflict-free row-per-thread walks
   const int tsY = sizeof(Px) == 1 ? 76 : 74, tsC = sub ? (sizeof(Px) == 1 ? 44 : 42) : tsY;
   const int nC = sub ? 32 : 64;
-  const int pl_n[3] = { 64, nC, nC };
-  const int pl_ts[3] = { tsY, tsC, tsC };
-  const int pl_off[3] = { 0, 72 * tsY, 72 * tsY + (nC + 8) * tsC };
+  const int offU = 72 * tsY, offV = 72 * tsY + (nC + 8) * tsC;
   int my_plane, my_idx;
   if (tid < 64) { my_plane = 0; my_idx = tid; }
   else if (tid < 64 + nC) { my_plane = 1; my_idx = tid - 64; }
   else { my_plane = 2; my_idx = tid - 64 - nC; }
   const bool uvsub = my_plane && sub;
   const int n = my_plane ? nC : 64, ts = my_plane ? tsC : tsY, nb = n >> 3;
-  Px *T = tile + (my_plane == 0 ? 0 : (my_plane == 1 ? 72 * tsY : 72 * tsY + (nC + 8) * tsC)) + 8 * ts + 8;
+  Px *T = tile + (my_plane == 0 ? 0 : (my_plane == 1 ? offU : offV)) + 8 * ts + 8;
   const int sbr = blockIdx.x;
   const int mi_row = sbr * 8;
   const int hy = sbr > 0 ? 8 : 0;
   uint32_t *prog = P.prog_lf;  // [sb_rows] prog_base + superblocks done in the row
   const uint32_t base = P.prog_base;
-  bool left_in_smem = false;
-  for (int sbc = 0; sbc < P.sb_cols; sbc++) {
+
+  // vectors of 8 samples, flattened over the three planes:  interior rows / top-halo rows
+  const int vY = 64 * 8, vC = nC * (nC >> 3);             // interior vectors per plane
+  const int nInt = vY + 2 * vC;
+  const int hYv = 8 * 8, hCv = 8 * (nC >> 3);             // top-halo vectors per plane
+  const int nHalo = hYv + 2 * hCv;
+  constexpr int kMaxInt = 12, kMaxHalo = 2;               // per-thread staging (128 thr: 6 / 1; 192 thr: 8 / 1)
+  auto vec_addr = [&](int i, bool halo, int sbc, const Px *&g, Px *&sm) {
+    // maps flat vector index -> global address and shared address
+    int p, r, v;
+    const int a = halo ? hYv : vY, bq = halo ? hCv : vC;
+    if (i < a) { p = 0; }
+    else if (i < a + bq) { p = 1; i -= a; }
+    else { p = 2; i -= a + bq; }
+    const int pn = p ? nC : 64, pts = p ? tsC : tsY, vpr = pn >> 3;
+    r = i / vpr; v = i % vpr;
+    if (halo) r -= 8;
+    const int stride = P.dst[p].stride;
+    g = (const Px *)P.dst[p].ptr + (ptrdiff_t)(sbr * pn + r) * stride + sbc * pn + v * 8;
+    sm = tile + (p == 0 ? 0 : (p == 1 ? offU : offV)) + (8 + r) * pts + 8 + v * 8;
+  };
+  auto has_work = [&](int sbc) -> bool {
     const vp9b_lfm &M = P.lfm[sbr * P.sb_cols + sbc];
     const uint64_t anyY = M.left_y[0] | M.left_y[1] | M.left_y[2] | M.above_y[0] | M.above_y[1] | M.above_y[2] | M.int_4x4_y;
     const uint32_t anyUV = M.left_uv[0] | M.left_uv[1] | M.left_uv[2] | M.above_uv[0] | M.above_uv[1] | M.above_uv[2] | M.int_4x4_uv;
-    const bool work = (anyY | anyUV) != 0;
-    const int hx = sbc > 0 ? 8 : 0;
-    if (work) {
-      // ---- (A) tile interior (no other superblock has touched it yet) + left halo if not carried
+    return (anyY | anyUV) != 0;
+  };
+  Vec pre[kMaxInt];
+  bool pre_valid = false;
+  auto prefetch = [&](int sbc) {
 #pragma unroll
-      for (int p = 0; p < 3; p++) {
-        const int pn = pl_n[p], vpr = (pn >> 3) + ((hx && !left_in_smem) ? 1 : 0), voff = vpr - (pn >> 3);
-        const int stride = P.dst[p].stride;
-        const Px *g = (const Px *)P.dst[p].ptr + (size_t)(sbr * pn) * stride + sbc * pn;
-        Px *Tp = tile + pl_off[p] + 8 * pl_ts[p] + 8;
-        for (int i = tid; i < pn * vpr; i += nthreads) {
-          const int r = i / vpr, v = i % vpr - voff;
-          smem_put(Tp + r * pl_ts[p] + v * 8, __ldcg((const Vec *)(g + (size_t)r * stride + v * 8)));
+    for (int k = 0; k < kMaxInt; k++) {
+      const int i = tid + k * nthreads;
+      if (i < nInt) {
+        const Px *g; Px *sm;
+        vec_addr(i, false, sbc, g, sm);
+        pre[k] = __ldcg((const Vec *)g);
+      }
+    }
+  };
+  bool work = has_work(0);
+  if (work) { prefetch(0); pre_valid = true; }
+  bool left_in_smem = false;
+  for (int sbc = 0; sbc < P.sb_cols; sbc++) {
+    const vp9b_lfm &M = P.lfm[sbr * P.sb_cols + sbc];
+    const int hx = sbc > 0 ? 8 : 0;
+    const bool work_next = (sbc + 1 < P.sb_cols) && has_work(sbc + 1);
+    if (work) {
+      // ---- (A) staged interior -> shared; left halo from global only if it was not carried
+#pragma unroll
+      for (int k = 0; k < kMaxInt; k++) {
+        const int i = tid + k * nthreads;
+        if (i < nInt) {
+          const Px *g; Px *sm;
+          vec_addr(i, false, sbc, g, sm);
+          smem_put(sm, pre[k]);
+        }
+      }
+      if (hx && !left_in_smem) {
+        for (int i = tid; i < 64 + 2 * nC; i += nthreads) {
+          const int p = i < 64 ? 0 : (i < 64 + nC ? 1 : 2), r = i < 64 ? i : (i < 64 + nC ? i - 64 : i - 64 - nC);
+          const int pn = p ? nC : 64, pts = p ? tsC : tsY, stride = P.dst[p].stride;
+          const Px *g = (const Px *)P.dst[p].ptr + (size_t)(sbr * pn + r) * stride + sbc * pn - 8;
+          smem_put(tile + (p == 0 ? 0 : (p == 1 ? offU : offV)) + (8 + r) * pts, __ldcg((const Vec *)g));
         }
       }
     }
+    // ---- prefetch the next superblock's interior (nobody else touches it before this CTA)
+    pre_valid = false;
+    if (work_next) { prefetch(sbc + 1); pre_valid = true; }
     // ---- (B) the row above must have finished superblock sbc+1 (above-right)
     if (hy) {
       if (tid == 0) wait_progress(prog + sbr - 1, base, min(sbc + 2, P.sb_cols));
       __syncthreads();
     }
     if (work) {
-      // ---- (C) top halo rows
+      // ---- (C) top halo: issue now, consume after the vertical pass
+      Vec halo[kMaxHalo];
       if (hy) {
 #pragma unroll
-        for (int p = 0; p < 3; p++) {
-          const int pn = pl_n[p], vpr = pn >> 3, stride = P.dst[p].stride;
-          const Px *g = (const Px *)P.dst[p].ptr + (size_t)(sbr * pn) * stride + sbc * pn;
-          Px *Tp = tile + pl_off[p] + 8 * pl_ts[p] + 8;
-          for (int i = tid; i < 8 * vpr; i += nthreads) {
-            const int r = i / vpr - 8, v = i % vpr;
-            smem_put(Tp + r * pl_ts[p] + v * 8, __ldcg((const Vec *)(g + (ptrdiff_t)r * stride + v * 8)));
+        for (int k = 0; k < kMaxHalo; k++) {
+          const int i = tid + k * nthreads;
+          if (i < nHalo) {
+            const Px *g; Px *sm;
+            vec_addr(i, true, sbc, g, sm);
+            halo[k] = __ldcg((const Vec *)g);
           }
         }
       }
@@ -909,6 +966,18 @@ __global__ void __launch_bounds__(192) k_loopfilter(const __grid_constant__ Fram
               lf_px<Px>(s, 1, 4, P.lf_mblim[lo], P.lf_lim[lo], lo >> 4, P.bd);
             }
             if ((m4i >> c) & 1) lf_px<Px>(s + 4, 1, 4, P.lf_mblim[lo], P.lf_lim[lo], lo >> 4, P.bd);
+          }
+        }
+      }
+      // ---- top halo registers -> shared (the vertical pass never touches halo rows)
+      if (hy) {
+#pragma unroll
+        for (int k = 0; k < kMaxHalo; k++) {
+          const int i = tid + k * nthreads;
+          if (i < nHalo) {
+            const Px *g; Px *sm;
+            vec_addr(i, true, sbc, g, sm);
+            smem_put(sm, halo[k]);
           }
         }
       }
@@ -961,37 +1030,32 @@ __global__ void __launch_bounds__(192) k_loopfilter(const __grid_constant__ Fram
       }
       __syncthreads();
       // ---- (F) store: top halo rows (columns of this superblock only), body rows incl. left halo
-#pragma unroll
-      for (int p = 0; p < 3; p++) {
-        const int pn = pl_n[p], pts = pl_ts[p], stride = P.dst[p].stride;
-        Px *g = (Px *)P.dst[p].ptr + (size_t)(sbr * pn) * stride + sbc * pn;
-        Px *Tp = tile + pl_off[p] + 8 * pts + 8;
-        const int vtop = pn >> 3, vbody = (pn >> 3) + (hx ? 1 : 0);
-        if (hy)
-          for (int i = tid; i < 8 * vtop; i += nthreads) {
-            const int r = i / vtop - 8, v = i % vtop;
-            Vec vv;
-            smem_get(Tp + r * pts + v * 8, vv);
-            __stcg((Vec *)(g + (ptrdiff_t)r * stride + v * 8), vv);
-          }
-        for (int i = tid; i < pn * vbody; i += nthreads) {
-          const int r = i / vbody, v = i % vbody - (hx ? 1 : 0);
-          Vec vv;
-          smem_get(Tp + r * pts + v * 8, vv);
-          __stcg((Vec *)(g + (size_t)r * stride + v * 8), vv);
-        }
+      for (int i = tid; i < nInt + (hy ? nHalo : 0); i += nthreads) {
+        const bool halo_part = i >= nInt;
+        const Px *g; Px *sm;
+        vec_addr(halo_part ? i - nInt : i, halo_part, sbc, g, sm);
+        Vec vv;
+        smem_get(sm, vv);
+        __stcg((Vec *)g, vv);
       }
+      if (hx)
+        for (int i = tid; i < 64 + 2 * nC; i += nthreads) {
+          const int p = i < 64 ? 0 : (i < 64 + nC ? 1 : 2), r = i < 64 ? i : (i < 64 + nC ? i - 64 : i - 64 - nC);
+          const int pn = p ? nC : 64, pts = p ? tsC : tsY, stride = P.dst[p].stride;
+          Px *g = (Px *)P.dst[p].ptr + (size_t)(sbr * pn + r) * stride + sbc * pn - 8;
+          Vec vv;
+          smem_get(tile + (p == 0 ? 0 : (p == 1 ? offU : offV)) + (8 + r) * pts, vv);
+          __stcg((Vec *)g, vv);
+        }
       __syncthreads();
       // ---- (G) carry the right-most 8 columns over as the next superblock's left halo
-#pragma unroll
-      for (int p = 0; p < 3; p++) {
-        const int pn = pl_n[p], pts = pl_ts[p];
-        Px *Tp = tile + pl_off[p] + 8 * pts + 8;
-        for (int r = tid; r < pn; r += nthreads) {
-          Vec vv;
-          smem_get(Tp + r * pts + pn - 8, vv);
-          smem_put(Tp + r * pts - 8, vv);
-        }
+      for (int i = tid; i < 64 + 2 * nC; i += nthreads) {
+        const int p = i < 64 ? 0 : (i < 64 + nC ? 1 : 2), r = i < 64 ? i : (i < 64 + nC ? i - 64 : i - 64 - nC);
+        const int pn = p ? nC : 64, pts = p ? tsC : tsY;
+        Px *rowp = tile + (p == 0 ? 0 : (p == 1 ? offU : offV)) + (8 + r) * pts;
+        Vec vv;
+        smem_get(rowp + 8 + pn - 8, vv);
+        smem_put(rowp, vv);
       }
       left_in_smem = true;
     } else {
@@ -1002,7 +1066,9 @@ __global__ void __launch_bounds__(192) k_loopfilter(const __grid_constant__ Fram
       __threadfence();
       st_release(prog + sbr, base + (uint32_t)(sbc + 1));
     }
+    work = work_next;
   }
+  (void)pre_valid;
 }
 
 }  // namespace vp9b
