@@ -1505,16 +1505,18 @@ int TileCtx::decode_block_tokens(int plane, int x, int y, int tx_size, int tx_ty
   const uint8_t *cat6_prob = bd == 12 ? kCat6ProbHigh12 : (bd == 10 ? kCat6ProbHigh12 + 2 : kCat6Prob);
   const int cat6_bits = bd == 12 ? 18 : (bd == 10 ? 16 : 14);
   const bool hbd = bd > 8;
+  // coefficient stream: grow geometrically, write through raw pointers (no per-block zero fill)
   size_t base;
   if (hbd) {
-    base = P->out_coef32_.size();
-    P->out_coef32_.resize(base + max_eob);
+    base = P->n_coef_;
+    if (P->out_coef32_.size() < base + max_eob) P->out_coef32_.resize(std::max(P->out_coef32_.size() * 2, base + 65536));
   } else {
-    base = P->out_coef16_.size();
-    P->out_coef16_.resize(base + max_eob);
+    base = P->n_coef_;
+    if (P->out_coef16_.size() < base + max_eob) P->out_coef16_.resize(std::max(P->out_coef16_.size() * 2, base + 65536));
   }
   int16_t *o16 = hbd ? nullptr : &P->out_coef16_[base];
   int32_t *o32 = hbd ? &P->out_coef32_[base] : nullptr;
+  BoolReader r = this->r;  // local copy: value/range/count live in registers for the whole block
   int c = 0;
   int dqv = dq[0];
   int band;
@@ -1588,7 +1590,8 @@ int TileCtx::decode_block_tokens(int plane, int x, int y, int tx_size, int tx_ty
     dqv = dq[1];
   }
   const int eob = c;
-  if (hbd) P->out_coef32_.resize(base + eob); else P->out_coef16_.resize(base + eob);
+  this->r = r;
+  P->n_coef_ = base + eob;
   *coef_off = (uint32_t)base;
   const uint8_t flag = eob > 0;
   for (int i = 0; i < n; i++) {
@@ -2024,8 +2027,8 @@ void Parser::pack() {
   for (int p = 0; p < 3; p++)
     set(VP9B_SEC_TXB_INTRA_Y + p, out_txb_intra_[p].data(), sizeof(vp9b_txb), out_txb_intra_[p].size());
   set(VP9B_SEC_SB_INTRA, out_sb_intra_.data(), sizeof(vp9b_sbrange), out_sb_intra_.size());
-  if (bit_depth_ > 8) set(VP9B_SEC_COEF, out_coef32_.data(), 4, out_coef32_.size());
-  else set(VP9B_SEC_COEF, out_coef16_.data(), 2, out_coef16_.size());
+  if (bit_depth_ > 8) set(VP9B_SEC_COEF, out_coef32_.data(), 4, n_coef_);
+  else set(VP9B_SEC_COEF, out_coef16_.data(), 2, n_coef_);
   if (lf_.filter_level) set(VP9B_SEC_LFM, out_lfm_.data(), sizeof(vp9b_lfm), out_lfm_.size());
   for (int i = 0; i < VP9B_SEC_COUNT; i++) {
     h.sec[i].offset = (uint32_t)off;
@@ -2079,8 +2082,7 @@ int Parser::parse(const uint8_t *data, size_t size) {
   out_submv_.clear();
   out_txb_inter_.clear();
   for (int p = 0; p < 3; p++) out_txb_intra_[p].clear();
-  out_coef16_.clear();
-  out_coef32_.clear();
+  n_coef_ = 0;
   out_sb_intra_.assign((size_t)3 * sb_cols_ * sb_rows_, vp9b_sbrange{ 0, 0 });
   out_lfm_.clear();
   if (lf_.filter_level) {

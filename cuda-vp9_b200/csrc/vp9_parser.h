@@ -167,6 +167,7 @@ class Parser {
   std::vector<vp9b_sbrange> out_sb_intra_;  // [3][sb_rows*sb_cols]
   std::vector<int16_t> out_coef16_;
   std::vector<int32_t> out_coef32_;
+  size_t n_coef_ = 0;  // coefficients written this frame (the vectors only grow)
   std::vector<vp9b_lfm> out_lfm_;
   uint32_t n_inter_px_[3], n_compound_px_[3];
   std::vector<uint8_t> packed_;

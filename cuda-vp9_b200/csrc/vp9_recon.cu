@@ -500,11 +500,9 @@ VP9B_DEV void warp_itx_add(int *tbuf, const void *coef_base, int coef_bytes, con
 }
 
 template <typename Px, typename PT>
-VP9B_DEV void warp_residual(const FrameParams &P, int *tbuf, const vp9b_txb &t, int lane) {
+VP9B_DEV void warp_residual_at(const FrameParams &P, int *tbuf, const vp9b_txb &t, Px *dst, int stride, int lane) {
   if (!t.eob) return;
-  const int plane = (t.tx >> 4) & 3, tx_size = t.tx & 3;
-  const int stride = P.dst[plane].stride;
-  Px *dst = (Px *)P.dst[plane].ptr + (size_t)t.y4 * 4 * stride + t.x4 * 4;
+  const int tx_size = t.tx & 3;
   const int cb = sizeof(Px) == 1 ? 2 : 4;
   switch (tx_size) {
     case 0: warp_itx_add<Px, PT, 4>(tbuf, P.coef, cb, t, dst, stride, P.bd, P.lossless, lane); break;
@@ -512,6 +510,14 @@ VP9B_DEV void warp_residual(const FrameParams &P, int *tbuf, const vp9b_txb &t, 
     case 2: warp_itx_add<Px, PT, 16>(tbuf, P.coef, cb, t, dst, stride, P.bd, 0, lane); break;
     default: warp_itx_add<Px, PT, 32>(tbuf, P.coef, cb, t, dst, stride, P.bd, 0, lane); break;
   }
+}
+
+template <typename Px, typename PT>
+VP9B_DEV void warp_residual(const FrameParams &P, int *tbuf, const vp9b_txb &t, int lane) {
+  const int plane = (t.tx >> 4) & 3;
+  const int stride = P.dst[plane].stride;
+  Px *dst = (Px *)P.dst[plane].ptr + (size_t)t.y4 * 4 * stride + t.x4 * 4;
+  warp_residual_at<Px, PT>(P, tbuf, t, dst, stride, lane);
 }
 
 constexpr int kResWarps = 4;
@@ -531,6 +537,15 @@ __global__ void __launch_bounds__(kResWarps * 32) k_residual(const __grid_consta
 // unavailable left -> base+1, unavailable above -> base-1, above-right only read for 4x4 blocks
 // with have_right, everything beyond the aligned frame size replicates the last sample.
 // Predictors: vpx_dsp/intrapred.c (closed-form per sample).
+template <typename Px> struct LfVec;       // vector type moving 8 samples
+template <> struct LfVec<uint8_t> { typedef uint2 T; };
+template <> struct LfVec<uint16_t> { typedef uint4 T; };
+// shared-memory rows are only 4-byte aligned (odd word stride): move vectors as 32-bit words
+VP9B_DEV void smem_put(void *d, uint2 v) { uint32_t *w = (uint32_t *)d; w[0] = v.x; w[1] = v.y; }
+VP9B_DEV void smem_put(void *d, uint4 v) { uint32_t *w = (uint32_t *)d; w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w; }
+VP9B_DEV void smem_get(const void *s, uint2 &v) { const uint32_t *w = (const uint32_t *)s; v.x = w[0]; v.y = w[1]; }
+VP9B_DEV void smem_get(const void *s, uint4 &v) { const uint32_t *w = (const uint32_t *)s; v.x = w[0]; v.y = w[1]; v.z = w[2]; v.w = w[3]; }
+
 #define AVG2(a, b) (((a) + (b) + 1) >> 1)
 #define AVG3(a, b, c) (((a) + 2 * (b) + (c) + 2) >> 2)
 
@@ -555,22 +570,20 @@ struct IntraEdge {
 };
 
 template <typename Px>
-VP9B_DEV void warp_intra_predict(const FrameParams &P, IntraEdge &E, const vp9b_txb &t, int lane) {
+VP9B_DEV void warp_intra_predict(const FrameParams &P, IntraEdge &E, const vp9b_txb &t, Px *dst, int stride, int lane) {
   const int tx_size = t.tx & 3, plane = (t.tx >> 4) & 3;
   const int mode = t.aux & 15, have_top = (t.aux >> 4) & 1, have_left = (t.aux >> 5) & 1, have_right = (t.aux >> 6) & 1;
   const int bs = 4 << tx_size, bd = P.bd;
   const int ss_x = plane ? P.ss_x : 0, ss_y = plane ? P.ss_y : 0;
   const int frame_w = (P.mi_cols * 8) >> ss_x, frame_h = (P.mi_rows * 8) >> ss_y;
   const int x0 = t.x4 * 4, y0 = t.y4 * 4;
-  const int stride = P.dst[plane].stride;
-  Px *dst = (Px *)P.dst[plane].ptr + (size_t)y0 * stride + x0;
   const int base = 128 << (bd - 8);
   // --- edges
   if (lane < bs) {
     int v = base + 1;
     if (have_left) {
       const int yy = (y0 + lane < frame_h) ? lane : frame_h - y0 - 1;
-      v = ld_px(dst + (size_t)yy * stride - 1);
+      v = dst[yy * stride - 1];
     }
     E.left[lane] = v;
   }
@@ -580,11 +593,11 @@ VP9B_DEV void warp_intra_predict(const FrameParams &P, IntraEdge &E, const vp9b_
       const bool real = (i < bs) || (have_right && bs == 4);
       int xx = real ? i : bs - 1;
       if (x0 + xx >= frame_w) xx = frame_w - x0 - 1;
-      v = ld_px(dst - stride + xx);
+      v = dst[xx - stride];
     }
     E.above[i] = v;
   }
-  if (lane == 0) E.tl = have_top ? (have_left ? ld_px(dst - stride - 1) : base + 1) : base - 1;
+  if (lane == 0) E.tl = have_top ? (have_left ? (int)dst[-stride - 1] : base + 1) : base - 1;
   __syncwarp();
   const int *a = E.above, *l = E.left;
   const int tl = E.tl;
@@ -651,7 +664,7 @@ VP9B_DEV void warp_intra_predict(const FrameParams &P, IntraEdge &E, const vp9b_
         break;
       }
     }
-    dst[(size_t)r * stride + c] = (Px)v;
+    dst[r * stride + c] = (Px)v;
   }
 #undef AT
 #undef LT
@@ -676,40 +689,86 @@ VP9B_DEV void wait_progress(const uint32_t *p, uint32_t base, int need) {
 // only reach into the left, above-left and above superblocks (above-right samples are taken
 // inside the prediction block only, vp9_reconintra.c:356-386,412), so row r may process
 // superblock c once row r-1 has finished superblock c: a wavefront with lag 1, tracked by one
-// progress counter per (plane, row).  Rows without intra blocks just publish their progress.
+// progress counter per (plane, row).  The superblock's samples (plus the row above and the
+// column to the left) are staged in shared memory, every transform block of the superblock is
+// predicted and reconstructed there in decode order, and the tile is written back once.
+template <typename Px> struct IntraTileGeom {
+  static constexpr int kMargin = 16 / sizeof(Px);            // left margin: interior rows 16-byte aligned
+  static constexpr int kTS = 64 + kMargin + 16 / sizeof(Px); // row stride in samples (16-byte multiple)
+  static constexpr int kRows = 65;
+  static constexpr size_t kTileBytes = (size_t)kRows * kTS * sizeof(Px);
+  static constexpr size_t kWarpBytes = (kTileBytes + 32 * 33 * sizeof(int) + sizeof(IntraEdge) + 15) & ~(size_t)15;
+};
+
 template <typename Px, typename PT>
 __global__ void __launch_bounds__(kWaveWarps * 32) k_intra(const __grid_constant__ FrameParams P) {
-  __shared__ int tbuf[kWaveWarps][32 * 33];
-  __shared__ IntraEdge edges[kWaveWarps];
+  extern __shared__ __align__(16) unsigned char intra_smem[];
+  typedef IntraTileGeom<Px> G;
+  typedef typename LfVec<Px>::T Vec;  // 8 samples
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  unsigned char *wbase = intra_smem + (size_t)warp * G::kWarpBytes;
+  Px *tile = (Px *)wbase;
+  int *tbuf = (int *)(wbase + G::kTileBytes);
+  IntraEdge &edge = *(IntraEdge *)(wbase + G::kTileBytes + 32 * 33 * sizeof(int));
   const int unit = blockIdx.x * kWaveWarps + warp;
   if (unit >= 3 * P.sb_rows) return;
   // units are ordered row-major so that a row's dependency (row-1, same plane) has a lower index
   const int sbr = unit / 3, plane = unit % 3;
   const int nsb = P.sb_cols * P.sb_rows;
+  const int n = (plane && P.ss_x) ? 32 : 64;  // superblock size in this plane
+  const int stride = P.dst[plane].stride;
+  Px *gplane = (Px *)P.dst[plane].ptr;
   uint32_t *prog = P.prog_intra + plane * P.sb_rows;
   const vp9b_sbrange *rgs = P.sb_intra + plane * nsb + sbr * P.sb_cols;
+  constexpr int TS = G::kTS, M = G::kMargin;
+  Px *T0 = tile + TS + M;  // sample (0,0) of the superblock; row -1 / column -1 hold the neighbours
+  bool left_in_smem = false;
   for (int sbc = 0; sbc < P.sb_cols; sbc++) {
     const vp9b_sbrange rg = rgs[sbc];
-    if (rg.count) {
-      if (sbr > 0) {
-        if (lane == 0) wait_progress(prog + sbr - 1, P.prog_base, min(sbc + 1, P.sb_cols));
-        __syncwarp();
-      }
-      const vp9b_txb *list = P.txb_intra[plane] + rg.start;
-      for (uint32_t i = 0; i < rg.count; i++) {
-        const vp9b_txb t = list[i];
-        warp_intra_predict<Px>(P, edges[warp], t, lane);
-        warp_residual<Px, PT>(P, tbuf[warp], t, lane);
-      }
-      __syncwarp();
-      if (lane == 0) {
-        __threadfence();
-        st_release(prog + sbr, P.prog_base + (uint32_t)(sbc + 1));
-      }
-    } else if (lane == 0) {
+    if (!rg.count) {
       // no intra block here: these samples were final after the inter stages, and everything to
       // the left in this row is done (program order), so just publish
+      if (lane == 0) st_release(prog + sbr, P.prog_base + (uint32_t)(sbc + 1));
+      left_in_smem = false;
+      continue;
+    }
+    Px *g = gplane + (size_t)(sbr * n) * stride + sbc * n;
+    // interior rows can be fetched before the dependency wait (nobody else writes them)
+    const int vpr = n >> 3;
+    for (int i = lane; i < n * vpr; i += 32) {
+      const int r = i / vpr, v = i % vpr;
+      *(Vec *)(T0 + r * TS + v * 8) = __ldcg((const Vec *)(g + (size_t)r * stride + v * 8));
+    }
+    if (sbc > 0 && !left_in_smem)
+      for (int r = lane; r < n; r += 32) T0[r * TS - 1] = __ldcg((const Px *)(g + (size_t)r * stride - 1));
+    if (sbr > 0) {
+      if (lane == 0) wait_progress(prog + sbr - 1, P.prog_base, min(sbc + 1, P.sb_cols));
+      __syncwarp();
+      // row above (incl. top-left)
+      for (int v = lane; v < vpr; v += 32) *(Vec *)(T0 - TS + v * 8) = __ldcg((const Vec *)(g - stride + v * 8));
+      if (lane == 0 && sbc > 0) T0[-TS - 1] = __ldcg((const Px *)(g - stride - 1));
+    }
+    __syncwarp();
+    const vp9b_txb *list = P.txb_intra[plane] + rg.start;
+    const int px0 = sbc * n, py0 = sbr * n;
+    for (uint32_t i = 0; i < rg.count; i++) {
+      const vp9b_txb t = list[i];
+      Px *d = T0 + (t.y4 * 4 - py0) * TS + (t.x4 * 4 - px0);
+      warp_intra_predict<Px>(P, edge, t, d, TS, lane);
+      warp_residual_at<Px, PT>(P, tbuf, t, d, TS, lane);
+    }
+    __syncwarp();
+    // write the superblock back and keep its right-most column as the next left neighbour
+    for (int i = lane; i < n * vpr; i += 32) {
+      const int r = i / vpr, v = i % vpr;
+      __stcg((Vec *)(g + (size_t)r * stride + v * 8), *(const Vec *)(T0 + r * TS + v * 8));
+    }
+    __syncwarp();
+    for (int r = lane; r < n; r += 32) T0[r * TS - 1] = T0[r * TS + n - 1];
+    left_in_smem = true;
+    __syncwarp();
+    if (lane == 0) {
+      __threadfence();
       st_release(prog + sbr, P.prog_base + (uint32_t)(sbc + 1));
     }
   }
@@ -750,23 +809,21 @@ VP9B_DEV void lf_px(Px *s, int step, int size, int blimit, int limit, int thresh
     const bool flat2 = !(abs(p4 - p0) > one || abs(q4 - q0) > one || abs(p5 - p0) > one || abs(q5 - q0) > one ||
                          abs(p6 - p0) > one || abs(q6 - q0) > one || abs(p7 - p0) > one || abs(q7 - q0) > one);
     if (flat2) {
-      // 15-tap: running sums
-      const int sp = p6 + p5 + p4 + p3 + p2 + p1 + p0, sq = q0 + q1 + q2 + q3 + q4 + q5 + q6;
-      int a = p7 * 7 + p6 + sp + q0 + 8;  // op6 numerator: p7*7 + p6*2 + p5..p0 + q0
-      s[-7 * step] = (Px)(a >> 4);
-      a += p5 - p7 + q1 - p6;  s[-6 * step] = (Px)(a >> 4);  // p7*6 + p6 + p5*2 + p4..p0 + q0 + q1
-      a += p4 - p7 + q2 - p5;  s[-5 * step] = (Px)(a >> 4);
-      a += p3 - p7 + q3 - p4;  s[-4 * step] = (Px)(a >> 4);
-      a += p2 - p7 + q4 - p3;  s[-3 * step] = (Px)(a >> 4);
-      a += p1 - p7 + q5 - p2;  s[-2 * step] = (Px)(a >> 4);
-      a += p0 - p7 + q6 - p1;  s[-1 * step] = (Px)(a >> 4);
-      a += q0 - p7 + q7 - p0;  s[0] = (Px)(a >> 4);
-      a += q1 - p6 + q7 - q0;  s[1 * step] = (Px)(a >> 4);
-      a += q2 - p5 + q7 - q1;  s[2 * step] = (Px)(a >> 4);
-      a += q3 - p4 + q7 - q2;  s[3 * step] = (Px)(a >> 4);
-      a += q4 - p3 + q7 - q3;  s[4 * step] = (Px)(a >> 4);
-      a += q5 - p2 + q7 - q4;  s[5 * step] = (Px)(a >> 4);
-      a += q6 - p1 + q7 - q5;  s[6 * step] = (Px)(a >> 4);
+      // 15-tap [1,1,1,1,1,1,1,2,1,1,1,1,1,1,1] with edge replication, evaluated from prefix
+      // sums so that the 14 outputs are independent of each other (short dependency chain)
+      const int v[16] = { p7, p6, p5, p4, p3, p2, p1, p0, q0, q1, q2, q3, q4, q5, q6, q7 };
+      int S[17];
+      S[0] = 0;
+#pragma unroll
+      for (int i = 0; i < 16; i++) S[i + 1] = S[i] + v[i];
+#pragma unroll
+      for (int k = 1; k <= 14; k++) {
+        const int lo = k - 7 > 0 ? k - 7 : 0, hi = k + 7 < 15 ? k + 7 : 15;
+        const int box = S[hi + 1] - S[lo] + (7 - k > 0 ? (7 - k) * p7 : 0) + (k - 8 > 0 ? (k - 8) * q7 : 0);
+        s[(k - 8) * step] = (Px)((box + v[k] + 8) >> 4);
+      }
+      const int sp = 0, sq = 0;
+      (void)sp;
       (void)sq;
       return;
     }
@@ -795,14 +852,6 @@ VP9B_DEV void lf_px(Px *s, int step, int size, int blimit, int limit, int thresh
   s[-2 * step] = (Px)(sc_clamp(ps1 + f, bd) + off);
 }
 
-template <typename Px> struct LfVec;       // vector type moving 8 samples
-template <> struct LfVec<uint8_t> { typedef uint2 T; };
-template <> struct LfVec<uint16_t> { typedef uint4 T; };
-// shared-memory rows are only 4-byte aligned (odd word stride): move vectors as 32-bit words
-VP9B_DEV void smem_put(void *d, uint2 v) { uint32_t *w = (uint32_t *)d; w[0] = v.x; w[1] = v.y; }
-VP9B_DEV void smem_put(void *d, uint4 v) { uint32_t *w = (uint32_t *)d; w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w; }
-VP9B_DEV void smem_get(const void *s, uint2 &v) { const uint32_t *w = (const uint32_t *)s; v.x = w[0]; v.y = w[1]; }
-VP9B_DEV void smem_get(const void *s, uint4 &v) { const uint32_t *w = (const uint32_t *)s; v.x = w[0]; v.y = w[1]; v.z = w[2]; v.w = w[3]; }
 
 // geometry of one plane's tile in shared memory
 struct LfPlane {
@@ -811,6 +860,15 @@ struct LfPlane {
   int off;      // offset (samples) of the tile in the shared array
 };
 
+// optional phase timing of one loop-filter row (compile with -DVP9B_LF_TIMING; tools read it back
+// through vp9gpu_debug_read)
+__device__ unsigned long long d_lf_dbg[64 * 8];
+#ifdef VP9B_LF_TIMING
+VP9B_DEV unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+#define LFT(k) if (tid == 0 && sbr == 2 && sbc < 64) d_lf_dbg[sbc * 8 + (k)] = gtime();
+#else
+#define LFT(k)
+#endif
 template <typename Px>
 __global__ void __launch_bounds__(192) k_loopfilter(const __grid_constant__ FrameParams P) {
   // One persistent CTA per superblock ROW walks its row left to right.  The left neighbour is
@@ -867,37 +925,55 @@ __global__ void __launch_bounds__(192) k_loopfilter(const __grid_constant__ Fram
     const uint32_t anyUV = M.left_uv[0] | M.left_uv[1] | M.left_uv[2] | M.above_uv[0] | M.above_uv[1] | M.above_uv[2] | M.int_4x4_uv;
     return (anyY | anyUV) != 0;
   };
+  // per-thread vector slots are fixed across superblocks: precompute their plane / offsets once
+  int int_goff[kMaxInt], int_soff[kMaxInt], int_pl[kMaxInt];
+  int halo_goff[kMaxHalo], halo_soff[kMaxHalo], halo_pl[kMaxHalo];
+#pragma unroll
+  for (int k = 0; k < kMaxInt; k++) {
+    const int i = tid + k * nthreads;
+    int_pl[k] = -1;
+    if (i < nInt) {
+      const Px *g; Px *sm;
+      vec_addr(i, false, 0, g, sm);
+      int_pl[k] = i < vY ? 0 : (i < vY + vC ? 1 : 2);
+      int_goff[k] = (int)(g - (const Px *)P.dst[int_pl[k]].ptr);   // offset for superblock column 0
+      int_soff[k] = (int)(sm - tile);
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < kMaxHalo; k++) {
+    const int i = tid + k * nthreads;
+    halo_pl[k] = -1;
+    if (i < nHalo) {
+      const Px *g; Px *sm;
+      vec_addr(i, true, 0, g, sm);
+      halo_pl[k] = i < hYv ? 0 : (i < hYv + hCv ? 1 : 2);
+      halo_goff[k] = (int)(g - (const Px *)P.dst[halo_pl[k]].ptr);
+      halo_soff[k] = (int)(sm - tile);
+    }
+  }
+  auto gptr = [&](int pl, int goff, int sbc) -> Px * { return (Px *)P.dst[pl].ptr + goff + sbc * (pl ? nC : 64); };
   Vec pre[kMaxInt];
-  bool pre_valid = false;
   auto prefetch = [&](int sbc) {
 #pragma unroll
-    for (int k = 0; k < kMaxInt; k++) {
-      const int i = tid + k * nthreads;
-      if (i < nInt) {
-        const Px *g; Px *sm;
-        vec_addr(i, false, sbc, g, sm);
-        pre[k] = __ldcg((const Vec *)g);
-      }
-    }
+    for (int k = 0; k < kMaxInt; k++)
+      if (int_pl[k] >= 0) pre[k] = __ldcg((const Vec *)gptr(int_pl[k], int_goff[k], sbc));
   };
   bool work = has_work(0);
-  if (work) { prefetch(0); pre_valid = true; }
+  if (work) prefetch(0);
   bool left_in_smem = false;
+  int pending_publish = 0;     // superblocks finished but not yet published (thread 0)
+  uint32_t seen = base;        // last progress value of the row above seen by thread 0
   for (int sbc = 0; sbc < P.sb_cols; sbc++) {
     const vp9b_lfm &M = P.lfm[sbr * P.sb_cols + sbc];
     const int hx = sbc > 0 ? 8 : 0;
     const bool work_next = (sbc + 1 < P.sb_cols) && has_work(sbc + 1);
+    LFT(0)
     if (work) {
       // ---- (A) staged interior -> shared; left halo from global only if it was not carried
 #pragma unroll
-      for (int k = 0; k < kMaxInt; k++) {
-        const int i = tid + k * nthreads;
-        if (i < nInt) {
-          const Px *g; Px *sm;
-          vec_addr(i, false, sbc, g, sm);
-          smem_put(sm, pre[k]);
-        }
-      }
+      for (int k = 0; k < kMaxInt; k++)
+        if (int_pl[k] >= 0) smem_put(tile + int_soff[k], pre[k]);
       if (hx && !left_in_smem) {
         for (int i = tid; i < 64 + 2 * nC; i += nthreads) {
           const int p = i < 64 ? 0 : (i < 64 + nC ? 1 : 2), r = i < 64 ? i : (i < 64 + nC ? i - 64 : i - 64 - nC);
@@ -908,28 +984,27 @@ __global__ void __launch_bounds__(192) k_loopfilter(const __grid_constant__ Fram
       }
     }
     // ---- prefetch the next superblock's interior (nobody else touches it before this CTA)
-    pre_valid = false;
-    if (work_next) { prefetch(sbc + 1); pre_valid = true; }
-    // ---- (B) the row above must have finished superblock sbc+1 (above-right)
-    if (hy) {
-      if (tid == 0) wait_progress(prog + sbr - 1, base, min(sbc + 2, P.sb_cols));
-      __syncthreads();
+    if (work_next) prefetch(sbc + 1);
+    // ---- (B) the row above must have finished superblock sbc+1 (above-right).  Polling uses
+    // relaxed loads; the data itself is read with L2-coherent (.cg) loads issued afterwards.
+    if (hy && tid == 0) {
+      const int need = min(sbc + 2, P.sb_cols);
+      while ((int)(seen - base) < need) {
+        seen = ld_relaxed(prog + sbr - 1);
+        if ((int)(seen - base) < need) __nanosleep(20);
+      }
     }
+    LFT(1)
+    __syncthreads();
+    LFT(2)
     if (work) {
       // ---- (C) top halo: issue now, consume after the vertical pass
       Vec halo[kMaxHalo];
       if (hy) {
 #pragma unroll
-        for (int k = 0; k < kMaxHalo; k++) {
-          const int i = tid + k * nthreads;
-          if (i < nHalo) {
-            const Px *g; Px *sm;
-            vec_addr(i, true, sbc, g, sm);
-            halo[k] = __ldcg((const Vec *)g);
-          }
-        }
+        for (int k = 0; k < kMaxHalo; k++)
+          if (halo_pl[k] >= 0) halo[k] = __ldcg((const Vec *)gptr(halo_pl[k], halo_goff[k], sbc));
       }
-      __syncthreads();
       // ---- (D) vertical edges: thread = sample row
       {
         const int y = my_idx, r8 = y >> 3, pr = r8 & ~1;
@@ -969,19 +1044,21 @@ __global__ void __launch_bounds__(192) k_loopfilter(const __grid_constant__ Fram
           }
         }
       }
+      LFT(3)
       // ---- top halo registers -> shared (the vertical pass never touches halo rows)
       if (hy) {
 #pragma unroll
-        for (int k = 0; k < kMaxHalo; k++) {
-          const int i = tid + k * nthreads;
-          if (i < nHalo) {
-            const Px *g; Px *sm;
-            vec_addr(i, true, sbc, g, sm);
-            smem_put(sm, halo[k]);
-          }
-        }
+        for (int k = 0; k < kMaxHalo; k++)
+          if (halo_pl[k] >= 0) smem_put(tile + halo_soff[k], halo[k]);
+      }
+      // publish the previous superblock now: its stores were issued a whole pass ago, so the
+      // release fence does not wait
+      if (tid == 0 && pending_publish) {
+        st_release(prog + sbr, base + (uint32_t)sbc);
+        pending_publish = 0;
       }
       __syncthreads();
+      LFT(4)
       // ---- (E) horizontal edges: thread = sample column
       {
         const int x = my_idx, c = x >> 3;
@@ -1028,47 +1105,56 @@ __global__ void __launch_bounds__(192) k_loopfilter(const __grid_constant__ Fram
             lf_px<Px>(s + 4 * ts, ts, 4, P.lf_mblim[lvl], P.lf_lim[lvl], lvl >> 4, P.bd);
         }
       }
+      LFT(5)
       __syncthreads();
-      // ---- (F) store: top halo rows (columns of this superblock only), body rows incl. left halo
-      for (int i = tid; i < nInt + (hy ? nHalo : 0); i += nthreads) {
-        const bool halo_part = i >= nInt;
-        const Px *g; Px *sm;
-        vec_addr(halo_part ? i - nInt : i, halo_part, sbc, g, sm);
-        Vec vv;
-        smem_get(sm, vv);
-        __stcg((Vec *)g, vv);
-      }
-      if (hx)
-        for (int i = tid; i < 64 + 2 * nC; i += nthreads) {
-          const int p = i < 64 ? 0 : (i < 64 + nC ? 1 : 2), r = i < 64 ? i : (i < 64 + nC ? i - 64 : i - 64 - nC);
-          const int pn = p ? nC : 64, pts = p ? tsC : tsY, stride = P.dst[p].stride;
-          Px *g = (Px *)P.dst[p].ptr + (size_t)(sbr * pn + r) * stride + sbc * pn - 8;
+      LFT(6)
+      // ---- (F) store: top halo rows (columns of this superblock only) and the interior
+#pragma unroll
+      for (int k = 0; k < kMaxInt; k++)
+        if (int_pl[k] >= 0) {
           Vec vv;
-          smem_get(tile + (p == 0 ? 0 : (p == 1 ? offU : offV)) + (8 + r) * pts, vv);
-          __stcg((Vec *)g, vv);
+          smem_get(tile + int_soff[k], vv);
+          __stcg((Vec *)gptr(int_pl[k], int_goff[k], sbc), vv);
         }
-      __syncthreads();
-      // ---- (G) carry the right-most 8 columns over as the next superblock's left halo
+      if (hy) {
+#pragma unroll
+        for (int k = 0; k < kMaxHalo; k++)
+          if (halo_pl[k] >= 0) {
+            Vec vv;
+            smem_get(tile + halo_soff[k], vv);
+            __stcg((Vec *)gptr(halo_pl[k], halo_goff[k], sbc), vv);
+          }
+      }
+      // ---- (G) per row: store the left halo, then overwrite it with this superblock's
+      // right-most 8 columns (the next superblock's left halo).  Same thread reads then writes
+      // the halo columns; nobody else touches them, so no barrier in between.
       for (int i = tid; i < 64 + 2 * nC; i += nthreads) {
         const int p = i < 64 ? 0 : (i < 64 + nC ? 1 : 2), r = i < 64 ? i : (i < 64 + nC ? i - 64 : i - 64 - nC);
-        const int pn = p ? nC : 64, pts = p ? tsC : tsY;
+        const int pn = p ? nC : 64, pts = p ? tsC : tsY, stride = P.dst[p].stride;
         Px *rowp = tile + (p == 0 ? 0 : (p == 1 ? offU : offV)) + (8 + r) * pts;
-        Vec vv;
-        smem_get(rowp + 8 + pn - 8, vv);
-        smem_put(rowp, vv);
+        Vec vl, vr;
+        smem_get(rowp, vl);
+        smem_get(rowp + pn, vr);
+        if (hx) __stcg((Vec *)((Px *)P.dst[p].ptr + (size_t)(sbr * pn + r) * stride + sbc * pn - 8), vl);
+        smem_put(rowp, vr);
       }
       left_in_smem = true;
     } else {
       left_in_smem = false;
     }
+    LFT(7)
     __syncthreads();
     if (tid == 0) {
-      __threadfence();
-      st_release(prog + sbr, base + (uint32_t)(sbc + 1));
+      if (!work || sbc == P.sb_cols - 1) {
+        // nothing in flight worth hiding (or end of row): publish right away
+        st_release(prog + sbr, base + (uint32_t)(sbc + 1));
+        pending_publish = 0;
+      } else {
+        pending_publish = 1;
+      }
     }
     work = work_next;
   }
-  (void)pre_valid;
 }
 
 }  // namespace vp9b
@@ -1197,6 +1283,7 @@ extern "C" int vp9gpu_get_stage_ms(vp9gpu_ctx *ctx, float ms[8], int reset) {
   if (reset) memset(ctx->stage_ms, 0, sizeof(ctx->stage_ms));
   return 0;
 }
+extern "C" int vp9gpu_debug_read(unsigned long long *out) { return (int)cudaMemcpyFromSymbol(out, vp9b::d_lf_dbg, sizeof(unsigned long long) * 512); }
 extern "C" int vp9gpu_sync(vp9gpu_ctx *ctx) {
   if (!ctx) return VP9B_ERR_INVALID;
   CK(cudaStreamSynchronize(ctx->stream));
@@ -1301,7 +1388,13 @@ static int launch_stages(vp9gpu_ctx *ctx, const FrameParams &P, const vp9b_frame
     const uint32_t n_intra = h->sec[VP9B_SEC_TXB_INTRA_Y].count + h->sec[VP9B_SEC_TXB_INTRA_U].count +
                              h->sec[VP9B_SEC_TXB_INTRA_V].count;
     if (n_intra) {
-      k_intra<Px, PT><<<wave_blocks, kWaveWarps * 32, 0, st>>>(P);
+      const size_t ismem = IntraTileGeom<Px>::kWarpBytes * kWaveWarps;
+      static bool attr_set = false;
+      if (!attr_set) {
+        cudaFuncSetAttribute(k_intra<Px, PT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ismem);
+        attr_set = true;
+      }
+      k_intra<Px, PT><<<wave_blocks, kWaveWarps * 32, ismem, st>>>(P);
       ctx->launches++;
     }
   }
