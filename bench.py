@@ -23,6 +23,10 @@ import sys
 import threading
 import time
 
+# One hardware work queue per decoder context: with the default of 8, streams beyond the 8th alias
+# onto the same queue and serialise (profiles/r01_summary.md).  Must be set before CUDA starts.
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
@@ -82,10 +86,8 @@ class ClockSampler(threading.Thread):
 
 
 def dist_setup(args):
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    return rank, world, local
+    from cuda_vp9_b200 import sharding
+    return sharding.dist_env()
 
 
 # --------------------------------------------------------------------------------------------
@@ -153,7 +155,9 @@ def run_ours(args, rank, world, local):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     w, h, chunks = load_clip(args.clip)
     S = args.streams
-    E = args.e2e_streams or (os.cpu_count() or S)
+    from cuda_vp9_b200 import sharding
+    # host parse threads: all ranks share this box's cores
+    E = args.e2e_streams or sharding.host_threads_for_rank(world)
     hdr_size = C.sizeof(vb.FrameHdr)
 
     # ---- host parse once: packed buffer per coded frame
@@ -266,8 +270,15 @@ def run_ours(args, rank, world, local):
     dom = max(cand, key=lambda k: cand[k][0])
     dms, dbytes, dlaunch = cand[dom]
     achieved = dbytes / (dms * 1e-3) / 1e9 if dms > 0 else 0.0
+    # dram bytes per launch of the dominant kernel from the committed `ncu --set full` capture
+    traffic = None
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        traffic = tr.get(args.clip, {}).get(dom)
+    except Exception:
+        pass
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": dbytes / max(dlaunch, 1),
                 "avg_launch_ms": dms / max(dlaunch, 1),
                 "per_stage_ms_per_clip_pass": per_stage,
@@ -278,6 +289,7 @@ def run_ours(args, rank, world, local):
     RING = 3
     res = [0] * E
     t_marks = {}
+    ready_bar = threading.Barrier(E + 1)
     start_bar = threading.Barrier(E + 1)
     end_bar = threading.Barrier(E + 1)
 
@@ -300,6 +312,7 @@ def run_ours(args, rank, world, local):
             return n
 
         run(1)                  # warm-up: sizes every pool
+        ready_bar.wait()
         start_bar.wait()
         res[i] = run(args.steps)
         end_bar.wait()
@@ -310,6 +323,8 @@ def run_ours(args, rank, world, local):
     th = [threading.Thread(target=e2e_worker, args=(i,)) for i in range(E)]
     for t in th:
         t.start()
+    ready_bar.wait()
+    barrier()                   # every rank has warmed up: start the timed region together
     start_bar.wait()
     t0 = time.perf_counter()
     end_bar.wait()
@@ -318,14 +333,10 @@ def run_ours(args, rank, world, local):
     for t in th:
         t.join()
     n_e2e = sum(res)
-    if world > 1:
-        import torch.distributed as dist
-        t = torch.tensor([e2e_s], device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = float(t.item())
-    e2e_fps = n_e2e * world / e2e_s
-    h2d = sum(len(p) for p in packed) * E
-    d2h = shown * int(w * h * 1.5 * bps) * E
+    n_e2e, e2e_s = sharding.combine(n_e2e, e2e_s, device="cuda")
+    e2e_fps = n_e2e / e2e_s
+    h2d = sum(len(p) for p in packed) * E * world
+    d2h = shown * int(w * h * 1.5 * bps) * E * world
 
     out = {"metric": "decoded frames/sec", "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -384,7 +395,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--streams", type=int, default=8)
+    ap.add_argument("--streams", type=int, default=32, help="independent decoder contexts per GPU")
     ap.add_argument("--e2e-streams", type=int, default=0, help="host threads for the e2e leg (default: host cores)")
     ap.add_argument("--clip", default="1440p", choices=sorted(CLIPS))
     ap.add_argument("--no-cpu", action="store_true")

@@ -85,6 +85,8 @@ def lib_gpu():
         p = os.path.join(_HERE, "libvp9b200.so")
         if not os.path.exists(p):
             raise ImportError("libvp9b200.so (CUDA extension) not built -- there is no CPU fallback")
+        # one hardware work queue per decoder context (effective only if CUDA has not started yet)
+        os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
         L = C.CDLL(p)
         _proto_host(L)
         vp = C.c_void_p
