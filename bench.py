@@ -177,6 +177,9 @@ def run_ours(args, rank, world, local):
 
     # ---- S independent reconstruction contexts, packed buffers resident in HBM
     ctxs = [vb.GpuRecon(local) for _ in range(S)]
+    if args.stop_stage:     # debugging aid: marginal cost of each stage under stream concurrency
+        for c in ctxs:
+            c.set_stop_stage(args.stop_stage)
     dptr = [[c.upload(p)[0] for p in packed] for c in ctxs]
     streams = [torch.cuda.ExternalStream(c.stream()) for c in ctxs]
     master = torch.cuda.Stream()
@@ -216,8 +219,10 @@ def run_ours(args, rank, world, local):
         e0.record()
     for s in streams:
         s.wait_event(e0)
+    t_host0 = time.perf_counter()
     for _ in range(args.steps):
         replay_step()
+    host_submit_ms = (time.perf_counter() - t_host0) * 1e3 / args.steps
     for s in streams:
         ev = torch.cuda.Event()
         ev.record(s)
@@ -345,7 +350,8 @@ def run_ours(args, rank, world, local):
                       "shown_frames": shown, "parallelism": "independent streams, %d per GPU, no collective" % S,
                       "l2": "working set %d MB per GPU (> 126 MB L2): %d streams x (frame pool + packed buffers)" %
                             (S * (12 * frame_bytes(hdrs[0]) + sum(len(p) for p in packed)) >> 20, S),
-                      "host_parse_fps_1thread": shown / parse_s},
+                      "host_parse_fps_1thread": shown / parse_s,
+                      "host_submit_ms_per_step": host_submit_ms},
            "clocks": clocks, "gpu_launches": launches, "roofline": roofline,
            "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                    "what": "vp9b_decoder_decode (host parse + H2D + kernels) + vp9b_decoder_read_frame (D2H) per shown "
@@ -399,6 +405,7 @@ def main():
     ap.add_argument("--e2e-streams", type=int, default=0, help="host threads for the e2e leg (default: host cores)")
     ap.add_argument("--clip", default="1440p", choices=sorted(CLIPS))
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--stop-stage", type=int, default=0, help=argparse.SUPPRESS)
     args = ap.parse_args()
     rank, world, local = dist_setup(args)
     if args.impl == "reference":

@@ -82,7 +82,7 @@ def lib_gpu():
     """libvp9b200.so: CUDA reconstruction + parser + decoder.  Raises if it was not built."""
     global _gpu
     if _gpu is None:
-        p = os.path.join(_HERE, "libvp9b200.so")
+        p = os.environ.get("VP9B_LIB") or os.path.join(_HERE, "libvp9b200.so")   # VP9B_LIB: A/B builds
         if not os.path.exists(p):
             raise ImportError("libvp9b200.so (CUDA extension) not built -- there is no CPU fallback")
         # one hardware work queue per decoder context (effective only if CUDA has not started yet)

@@ -322,6 +322,24 @@ VP9B_DEV bool mc_inside(int x0, int y0, int H, int rw, int rh) {
   return x0 - 3 >= 0 && y0 - 3 >= 0 && x0 + 8 <= rw && y0 + H + 4 <= rh;
 }
 
+// Exact per-sample path for one 4-sample row of a unit (frame edge / scaled reference).  Kept out
+// of line and rolled: it is rare, and inlining it bloats the kernel past the instruction cache.
+__device__ __noinline__ uint32_t mc_row_slow(const FrameParams &P, const RefGeom &R, int plane, const MiEntry &e,
+                                             int mi_row, int mi_col, int x, int y, int yy, int mvr, int mvc) {
+  const int ss_x = plane ? P.ss_x : 0, ss_y = plane ? P.ss_y : 0;
+  const bool sub8 = e.bsize < 3;
+  const int bw8 = d_bw8[e.bsize], bh8 = d_bh8[e.bsize];
+  const int mi_col0 = mi_col & ~(bw8 - 1), mi_row0 = mi_row & ~(bh8 - 1);
+  const int bx = x - ((mi_col0 * 8) >> ss_x), by = y - ((mi_row0 * 8) >> ss_y);
+  const int xoff = sub8 ? (bx & ~3) : 0, yoff = sub8 ? (by & ~3) : 0;
+  const PredPos pp = pred_position(P, R, plane, mi_row0, mi_col0, bw8, bh8, xoff, yoff, mvr, mvc);
+  uint32_t w = 0;
+#pragma unroll 1
+  for (int xx = 0; xx < 4; xx++)
+    w |= (uint32_t)predict_sample<uint8_t>(P, R, plane, pp, bx - xoff + xx, by - yoff + yy, e.filter) << (8 * xx);
+  return w;
+}
+
 // one 4xH unit: all references of the prediction unit, compound average
 template <int H>
 VP9B_DEV void mc_unit(const FrameParams &P, int plane, const MiEntry &e, int mi_row, int mi_col, int x, int y,
@@ -354,19 +372,8 @@ VP9B_DEV void mc_unit(const FrameParams &P, int plane, const MiEntry &e, int mi_
       }
     }
     if (!fast) {  // frame edge (clamped fetches) or scaled reference: exact per-sample path
-      const int bw8 = d_bw8[e.bsize], bh8 = d_bh8[e.bsize];
-      const int mi_col0 = mi_col & ~(bw8 - 1), mi_row0 = mi_row & ~(bh8 - 1);
-      const int bx = x - ((mi_col0 * 8) >> ss_x), by = y - ((mi_row0 * 8) >> ss_y);
-      const int xoff = sub8 ? (bx & ~3) : 0, yoff = sub8 ? (by & ~3) : 0;
-      const PredPos pp = pred_position(P, R, plane, mi_row0, mi_col0, bw8, bh8, xoff, yoff, mvr, mvc);
 #pragma unroll
-      for (int yy = 0; yy < H; yy++) {
-        uint32_t w = 0;
-#pragma unroll 1
-        for (int xx = 0; xx < 4; xx++)
-          w |= (uint32_t)predict_sample<uint8_t>(P, R, plane, pp, bx - xoff + xx, by - yoff + yy, e.filter) << (8 * xx);
-        pr[yy] = w;
-      }
+      for (int yy = 0; yy < H; yy++) pr[yy] = mc_row_slow(P, R, plane, e, mi_row, mi_col, x, y, yy, mvr, mvc);
     }
     if (r == 0) {
 #pragma unroll
@@ -394,13 +401,13 @@ VP9B_DEV void inter_pred_u8_body(const FrameParams &P, int plane, int bx_, int b
   const MiEntry e = P.mi[(size_t)mi_row * P.mi_cols + mi_col];
   if (!e.ref0) return;
   if (H == 8 && e.bsize < 3) {  // sub-8x8 block in an unsubsampled plane: two 4x4 units
-    uint32_t o[4];
-    mc_unit<4>(P, plane, e, mi_row, mi_col, x, y, o);
+#pragma unroll 1
+    for (int half = 0; half < 2; half++) {
+      uint32_t o[4];
+      mc_unit<4>(P, plane, e, mi_row, mi_col, x, y + 4 * half, o);
 #pragma unroll
-    for (int i = 0; i < 4; i++) *(uint32_t *)(dst + (size_t)i * dstride) = o[i];
-    mc_unit<4>(P, plane, e, mi_row, mi_col, x, y + 4, o);
-#pragma unroll
-    for (int i = 0; i < 4; i++) *(uint32_t *)(dst + (size_t)(i + 4) * dstride) = o[i];
+      for (int i = 0; i < 4; i++) *(uint32_t *)(dst + (size_t)(i + 4 * half) * dstride) = o[i];
+    }
     return;
   }
   uint32_t o[H];
@@ -413,16 +420,16 @@ VP9B_DEV void inter_pred_u8_body(const FrameParams &P, int plane, int bx_, int b
 // the two chroma planes (4:2:0: 32x64-sample tiles of 4x4 units; 4:4:4: same as luma).
 __global__ void __launch_bounds__(128) k_inter_pred_u8(const __grid_constant__ FrameParams P, int ncta_y, int ncta_c,
                                                        int gx_y, int gx_c) {
-  int b = blockIdx.x;
-  if (b < ncta_y) {
-    inter_pred_u8_body<8>(P, 0, b % gx_y, b / gx_y);
-    return;
+  int b = blockIdx.x, plane = 0, gx = gx_y;
+  if (b >= ncta_y) {
+    b -= ncta_y;
+    plane = 1 + b / ncta_c;
+    b %= ncta_c;
+    gx = gx_c;
   }
-  b -= ncta_y;
-  const int plane = 1 + b / ncta_c;
-  b %= ncta_c;
-  if (P.ss_x) inter_pred_u8_body<4>(P, plane, b % gx_c, b / gx_c);
-  else inter_pred_u8_body<8>(P, plane, b % gx_c, b / gx_c);
+  // one call site per unit height keeps the kernel inside the instruction cache
+  if (plane && P.ss_x) inter_pred_u8_body<4>(P, plane, b % gx, b / gx);
+  else inter_pred_u8_body<8>(P, plane, b % gx, b / gx);
 }
 
 // ------------------------------------------------------------------------------------------
