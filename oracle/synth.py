@@ -62,12 +62,16 @@ def make_frames(w, h, n, seed=1234, bit_depth=8, motion=(3, 2), detail=0.04, noi
 
 
 def encode_clip(path, w, h, n, seed=1234, bit_depth=8, scale_at=None, detail=0.04, noise_corner=True,
-                deadline=1000000, temporal_noise=0.0, force_lf=False, **enc_kw):
+                deadline=1000000, temporal_noise=0.0, force_lf=False, show_existing_at=None, intra_only_at=None,
+                force_kf_at=None, **enc_kw):
     """Encode n synthetic frames to an IVF.  scale_at: {frame_index: (hmode, vmode)} issues
     VP8E_SET_SCALEMODE mid-stream (scaled reference frames, test/resize_test.cc:283)."""
     two_pass = enc_kw.pop("two_pass", False)
     frames = make_frames(w, h, n, seed=seed, bit_depth=bit_depth, detail=detail,
                          noise_corner=noise_corner, temporal_noise=temporal_noise)
+    if enc_kw.get("chroma444"):  # full-resolution chroma planes
+        frames = [[f[0], np.repeat(np.repeat(f[1], 2, 0), 2, 1)[:h, :w], np.repeat(np.repeat(f[2], 2, 0), 2, 1)[:h, :w]]
+                  for f in frames]
     if two_pass:  # first pass collects stats (vpxenc.c two-pass loop)
         e1 = vo.Encoder(w, h, bit_depth=bit_depth, g_pass=1, **enc_kw)
         for f in frames:
@@ -82,11 +86,21 @@ def encode_clip(path, w, h, n, seed=1234, bit_depth=8, scale_at=None, detail=0.0
     for i, f in enumerate(frames):
         if scale_at and i in scale_at:
             enc.set_scalemode(*scale_at[i])
-        chunks += enc.encode(f, deadline=deadline)
+        flags = 1 if (force_kf_at and i in force_kf_at) else 0  # VPX_EFLAG_FORCE_KF
+        chunks += enc.encode(f, flags=flags, deadline=deadline)
     chunks += enc.flush()
     enc.close()
     if force_lf:
         chunks = force_loop_filter(chunks)
+    if intra_only_at:
+        chunks = [keyframe_to_intra_only(c) if i in intra_only_at else c for i, c in enumerate(chunks)]
+    if show_existing_at:
+        out = []
+        for i, c in enumerate(chunks):
+            out.append(c)
+            if i in show_existing_at:
+                out.append(show_existing_frame(show_existing_at[i]))
+        chunks = out
     vo.ivf_write(path, chunks, w, h)
     return chunks
 
@@ -209,3 +223,111 @@ def force_loop_filter(chunks, level_fn=None):
             off += len(fr)
         out.append(bytes(buf))
     return out
+
+
+def show_existing_frame(ref_index, profile=0):
+    """A one-byte (profile 0-2) frame: frame_marker 2, profile, show_existing_frame = 1, index
+    (vp9_decodeframe.c:3130-3160).  The decoder outputs reference buffer `ref_index` again."""
+    bits = [1, 0, profile & 1, profile >> 1]
+    if profile == 3:
+        bits.append(0)
+    bits += [1, (ref_index >> 2) & 1, (ref_index >> 1) & 1, ref_index & 1]
+    while len(bits) % 8:
+        bits.append(0)
+    return bytes(sum(b << (7 - j) for j, b in enumerate(bits[i:i + 8])) for i in range(0, len(bits), 8))
+
+
+def keyframe_to_intra_only(chunk, refresh_mask=0xFF):
+    """Rewrite the uncompressed header of a profile-0 key frame as an intra-only frame
+    (vp9_decodeframe.c:3162-3260).  Both use the key-frame mode syntax and default probabilities
+    (reset_frame_context = 3 is written), so the compressed header and tile data stay valid; only
+    the header fields differ:
+      key:         marker(2) profile(2) show_existing(1) frame_type=0 show_frame error_res
+                   sync(24) [profile0: color_space(3) color_range(1)] size(32) render(1..)
+      intra-only:  ... frame_type=1 show_frame error_res intra_only=1 reset_ctx(2)=3 sync(24)
+                   refresh_frame_flags(8) size(32) render(1..)
+    The rest of the header (loop filter, quantiser, segmentation, tiles, first-partition size) is
+    copied bit for bit.  Requires error_res == 0 and BT.601-style colour config (profile 0
+    intra-only frames imply 8-bit 4:2:0 BT.601)."""
+    r = _Bits(chunk)
+    assert r.lit(2) == 2
+    profile = r.bit() | (r.bit() << 1)
+    assert profile == 0, "only profile 0"
+    assert r.bit() == 0          # show_existing_frame
+    assert r.bit() == 0, "not a key frame"
+    show_frame, error_res = r.bit(), r.bit()
+    assert error_res == 0
+    assert r.lit(24) == 0x498342
+    color_space = r.lit(3)
+    r.bit()                       # color_range
+    assert color_space != 7
+    # intra_only can only be signalled on a hidden frame (show_frame = 0, vp9_decodeframe.c:3182)
+    out = [1, 0, 0, 0, 0, 1, 0, 0, 1, 1, 1]
+    out += [(0x498342 >> (23 - i)) & 1 for i in range(24)]
+    out += [(refresh_mask >> (7 - i)) & 1 for i in range(8)]
+    # remaining header bits up to the end of the uncompressed header are copied unchanged; the
+    # header ends with first_partition_size(16) followed by byte alignment, so find its length by
+    # parsing the common tail
+    start = r.pos
+    r.lit(16); r.lit(16)                       # width-1, height-1
+    if r.bit():
+        r.lit(32)                               # render size
+    # key frames: refresh_frame_context, frame_parallel, frame_context_idx follow
+    r.bit(); r.bit(); r.lit(2)
+    r.lit(6); r.lit(3)                          # lf level, sharpness
+    if r.bit():                                 # mode_ref_delta_enabled
+        if r.bit():
+            for _ in range(4 + 2):
+                if r.bit():
+                    r.lit(7)
+    r.lit(8)                                    # base_q_idx
+    for _ in range(3):
+        if r.bit():
+            r.lit(5)
+    if r.bit():                                 # segmentation enabled
+        if r.bit():                             # update_map
+            for _ in range(7):
+                if r.bit():
+                    r.lit(8)
+            if r.bit():
+                for _ in range(3):
+                    if r.bit():
+                        r.lit(8)
+        if r.bit():                             # update_data
+            r.bit()
+            for _ in range(8):
+                for bits_, sign in ((8, 1), (6, 1), (2, 0), (0, 0)):
+                    if r.bit():
+                        r.lit(bits_)
+                        if sign:
+                            r.bit()
+    # tile info: increment bits depend on the frame width
+    return _finish_intra_only(chunk, r, out, start)
+
+
+def _finish_intra_only(chunk, r, out, start):
+    # width is at `start`: recompute sb_cols to parse the tile-column increment bits
+    rr = _Bits(chunk)
+    rr.pos = start
+    width = rr.lit(16) + 1
+    sb_cols = (((width + 7) >> 3) + 7) >> 3
+    min_log2 = 0
+    while (64 << min_log2) < sb_cols:
+        min_log2 += 1
+    max_log2 = 1
+    while (sb_cols >> max_log2) >= 4:
+        max_log2 += 1
+    max_log2 -= 1
+    k = min_log2
+    while k < max_log2 and r.bit():
+        k += 1
+    if r.bit():
+        r.bit()                                 # tile rows
+    r.lit(16)                                   # first partition size
+    end = r.pos
+    rr.pos = start
+    out += [rr.bit() for _ in range(end - start)]
+    while len(out) % 8:
+        out.append(0)
+    hdr = bytes(sum(b << (7 - j) for j, b in enumerate(out[i:i + 8])) for i in range(0, len(out), 8))
+    return hdr + chunk[(end + 7) // 8:]

@@ -76,6 +76,7 @@ class VpxImage(C.Structure):
 VPX_IMG_FMT_I420 = 0x102
 VPX_IMG_FMT_HIGHBITDEPTH = 0x800
 VPX_IMG_FMT_I42016 = VPX_IMG_FMT_I420 | VPX_IMG_FMT_HIGHBITDEPTH
+VPX_IMG_FMT_I444 = 0x106
 
 # control ids (vpx/vp8dx.h:58-146, vpx/vp8cx.h:131-720)
 VP9_SET_SKIP_LOOP_FILTER = 265
@@ -241,7 +242,7 @@ class Encoder:
                  tile_rows_log2=0, lossless=0, cq_level=None, bitrate=None, min_q=0, max_q=63,
                  kf_max_dist=9999, error_resilient=0, frame_parallel=0, threads=4, aq_mode=0,
                  end_usage=None, resize_allowed=0, sharpness=None, g_pass=0, stats=None,
-                 arnr_maxframes=None, arnr_strength=None):
+                 arnr_maxframes=None, arnr_strength=None, chroma444=False):
         L = lib()
         self.L, self.w, self.h, self.bd = L, w, h, bit_depth
         iface = C.c_void_p(L.vpx_codec_vp9_cx())
@@ -260,6 +261,8 @@ class Encoder:
             cfg.g_profile = 2
             cfg.g_bit_depth = bit_depth
             cfg.g_input_bit_depth = bit_depth
+        if chroma444:  # profile 1 (8 bit) / 3 (high bit depth): non-4:2:0 sampling
+            cfg.g_profile = 3 if bit_depth > 8 else 1
         if end_usage is not None:
             cfg.rc_end_usage = end_usage
         elif cq_level is not None:
@@ -299,7 +302,9 @@ class Encoder:
         if arnr_strength is not None:
             self.ctrl(VP8E_SET_ARNR_STRENGTH, arnr_strength)
         self.stats_out = []
-        fmt = VPX_IMG_FMT_I42016 if bit_depth > 8 else VPX_IMG_FMT_I420
+        fmt = VPX_IMG_FMT_I444 if chroma444 else VPX_IMG_FMT_I420
+        if bit_depth > 8:
+            fmt |= VPX_IMG_FMT_HIGHBITDEPTH
         self.img_p = L.vpx_img_alloc(None, fmt, w, h, 32)
         self.img = VpxImage.from_address(self.img_p)
         self.pts = 0

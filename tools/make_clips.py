@@ -46,6 +46,18 @@ PARITY = {
     # reference scaling: the coded size changes mid-stream (VP8E_SET_SCALEMODE), so inter
     # prediction reads references of a different size (x_step_q4 != 16)
     "scaled": dict(w=352, h=288, n=12, cpu_used=3, cq_level=30, scale_at={3: (3, 3), 6: (1, 2), 9: (0, 0)}),
+    # profile 1 / 3: 4:4:4 sampling (vp9_filter_block_plane_non420, full-size chroma MC / intra)
+    "p444": dict(w=176, h=144, n=5, chroma444=True, deadline=1, cpu_used=5, bitrate=300),
+    "p444_hbd": dict(w=144, h=112, n=4, chroma444=True, bit_depth=10, deadline=1, cpu_used=5, bitrate=300),
+    # a forced key frame rewritten as a hidden intra-only frame, then shown with
+    # show_existing_frame (bitstream edits in oracle/synth.py).  frame_parallel: without backward
+    # adaptation the frames after the edit do not depend on last_frame_type == KEY_FRAME
+    # (vp9_entropy.c:1063-1071), so the edited stream stays consistent with what was encoded.
+    "intra_only": dict(w=352, h=288, n=8, deadline=1, cpu_used=5, bitrate=300, frame_parallel=1, force_kf_at={4},
+                       intra_only_at={4},
+                       show_existing_at={4: 0}),
+    # show_existing_frame of other reference slots between ordinary frames
+    "show_exist": dict(w=352, h=288, n=7, deadline=1, cpu_used=5, bitrate=300, show_existing_at={2: 1, 5: 2}),
     "scaled_rt": dict(w=416, h=240, n=10, cpu_used=6, deadline=1, bitrate=300,
                       scale_at={2: (3, 1), 5: (2, 3), 8: (0, 0)}, temporal_noise=2.0),
 }
