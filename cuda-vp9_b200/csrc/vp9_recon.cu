@@ -876,18 +876,31 @@ VP9B_DEV unsigned long long gtime() { unsigned long long t; asm volatile("mov.u6
 #else
 #define LFT(k)
 #endif
+VP9B_DEV void bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
 template <typename Px>
-__global__ void __launch_bounds__(192) k_loopfilter(const __grid_constant__ FrameParams P) {
-  // One persistent CTA per superblock ROW walks its row left to right.  The left neighbour is
-  // the previous iteration of the same CTA (its right-most 8 columns stay in shared memory);
-  // the above-right neighbour is tracked by a per-row progress counter of the row above.
-  // Global latency is kept off the row's critical path: the interior of superblock c+1 is
-  // prefetched into registers while superblock c is filtered, and the top halo (the only part
-  // that depends on the row above) is fetched before the vertical pass and consumed after it.
+__global__ void __launch_bounds__(224) k_loopfilter(const __grid_constant__ FrameParams P) {
+  // One persistent CTA per superblock ROW walks its row left to right: 4 (4:2:0) or 6 (4:4:4)
+  // worker warps filter, one control warp talks to the neighbouring rows.
+  //   workers, per superblock c:  staged interior -> shared | B1 | vertical edges (thread = sample
+  //     row), bottom 8 rows of the left halo stored right away | B2 | horizontal edges (thread =
+  //     sample column) | B3 | store interior, carry the right-most 8 columns as the next left halo.
+  //     The interior of c+1 is prefetched into registers while c is filtered; a thread stores and
+  //     re-fills only its own shared-memory slots, so no barrier separates two superblocks.
+  //   control warp: waits until the row above has finished superblock c (its bottom rows are
+  //     final once that row has run the vertical pass of c+1), loads the 8 halo rows above into
+  //     shared memory while the workers are still in the vertical pass | B2 | publishes "c-1 is
+  //     final" for the row below | B3 | stores the (now filtered) halo rows back.
+  // Only the first horizontal edge of a superblock depends on the row above, and only the
+  // control warp ever waits for it.
   extern __shared__ __align__(16) unsigned char lf_smem[];
   Px *tile = (Px *)lf_smem;
   typedef typename LfVec<Px>::T Vec;
-  const int tid = threadIdx.x, nthreads = blockDim.x;
+  const int tid = threadIdx.x, nworkers = blockDim.x - 32, nall = blockDim.x;
+  const bool is_ctrl = tid >= nworkers;
+  const int lane = tid & 31;
   const bool sub = P.ss_x != 0;  // 4:2:0 (else 4:4:4)
   // stride in samples: (stride bytes / 4) odd -> conflict-free row-per-thread walks
   const int tsY = sizeof(Px) == 1 ? 76 : 74, tsC = sub ? (sizeof(Px) == 1 ? 44 : 42) : tsY;
@@ -903,7 +916,7 @@ __global__ void __launch_bounds__(192) k_loopfilter(const __grid_constant__ Fram
   const int sbr = blockIdx.x;
   const int mi_row = sbr * 8;
   const int hy = sbr > 0 ? 8 : 0;
-  uint32_t *prog = P.prog_lf;  // [sb_rows] prog_base + superblocks done in the row
+  uint32_t *prog = P.prog_lf;  // [sb_rows] prog_base + number of leading superblocks that are final
   const uint32_t base = P.prog_base;
 
   // vectors of 8 samples, flattened over the three planes:  interior rows / top-halo rows
@@ -911,9 +924,9 @@ __global__ void __launch_bounds__(192) k_loopfilter(const __grid_constant__ Fram
   const int nInt = vY + 2 * vC;
   const int hYv = 8 * 8, hCv = 8 * (nC >> 3);             // top-halo vectors per plane
   const int nHalo = hYv + 2 * hCv;
-  constexpr int kMaxInt = 12, kMaxHalo = 2;               // per-thread staging (128 thr: 6 / 1; 192 thr: 8 / 1)
-  auto vec_addr = [&](int i, bool halo, int sbc, const Px *&g, Px *&sm) {
-    // maps flat vector index -> global address and shared address
+  constexpr int kMaxInt = 8, kMaxHalo = 6;                // per-thread slots (128 workers: 6, 192: 8; control lane: 4 / 6)
+  auto vec_addr = [&](int i, bool halo, const Px *&g, Px *&sm, int &pl, int &flags) {
+    // maps flat vector index -> global address (superblock column 0), shared address, plane
     int p, r, v;
     const int a = halo ? hYv : vY, bq = halo ? hCv : vC;
     if (i < a) { p = 0; }
@@ -921,10 +934,12 @@ __global__ void __launch_bounds__(192) k_loopfilter(const __grid_constant__ Fram
     else { p = 2; i -= a + bq; }
     const int pn = p ? nC : 64, pts = p ? tsC : tsY, vpr = pn >> 3;
     r = i / vpr; v = i % vpr;
+    flags = (v == vpr - 1 ? 1 : 0) | (r >= pn - 8 ? 2 : 0);
     if (halo) r -= 8;
     const int stride = P.dst[p].stride;
-    g = (const Px *)P.dst[p].ptr + (ptrdiff_t)(sbr * pn + r) * stride + sbc * pn + v * 8;
+    g = (const Px *)P.dst[p].ptr + (ptrdiff_t)(sbr * pn + r) * stride + v * 8;
     sm = tile + (p == 0 ? 0 : (p == 1 ? offU : offV)) + (8 + r) * pts + 8 + v * 8;
+    pl = p;
   };
   auto has_work = [&](int sbc) -> bool {
     const vp9b_lfm &M = P.lfm[sbr * P.sb_cols + sbc];
@@ -932,34 +947,76 @@ __global__ void __launch_bounds__(192) k_loopfilter(const __grid_constant__ Fram
     const uint32_t anyUV = M.left_uv[0] | M.left_uv[1] | M.left_uv[2] | M.above_uv[0] | M.above_uv[1] | M.above_uv[2] | M.int_4x4_uv;
     return (anyY | anyUV) != 0;
   };
-  // per-thread vector slots are fixed across superblocks: precompute their plane / offsets once
-  int int_goff[kMaxInt], int_soff[kMaxInt], int_pl[kMaxInt];
-  int halo_goff[kMaxHalo], halo_soff[kMaxHalo], halo_pl[kMaxHalo];
+  auto gptr = [&](int pl, int goff, int sbc) -> Px * { return (Px *)P.dst[pl].ptr + goff + sbc * (pl ? nC : 64); };
+
+  if (is_ctrl) {
+    // ------------------------------------------------------------------ control warp
+    int h_goff[kMaxHalo], h_soff[kMaxHalo], h_pl[kMaxHalo];
+#pragma unroll
+    for (int k = 0; k < kMaxHalo; k++) {
+      const int i = lane + k * 32;
+      h_pl[k] = -1;
+      if (hy && i < nHalo) {
+        const Px *g; Px *sm; int fl;
+        vec_addr(i, true, g, sm, h_pl[k], fl);
+        h_goff[k] = (int)(g - (const Px *)P.dst[h_pl[k]].ptr);
+        h_soff[k] = (int)(sm - tile);
+      }
+    }
+    uint32_t seen = base;
+    for (int sbc = 0; sbc < P.sb_cols; sbc++) {
+      const bool work = has_work(sbc);
+      if (work) {
+        if (hy) {
+          // the row above has finished superblock sbc (value counts leading final superblocks)
+          const int need = sbc + 1;
+          if ((int)(seen - base) < need) {
+            while ((int)((seen = ld_relaxed(prog + sbr - 1)) - base) < need) __nanosleep(20);
+            seen = ld_acquire(prog + sbr - 1);
+          }
+#pragma unroll
+          for (int k = 0; k < kMaxHalo; k++)
+            if (h_pl[k] >= 0) smem_put(tile + h_soff[k], __ldcg((const Vec *)gptr(h_pl[k], h_goff[k], sbc)));
+        }
+        bar_sync(2, nall);   // B2: vertical pass done everywhere, halo rows in place
+      } else {
+        bar_sync(2, nall);   // keeps the stores of the previous superblock ahead of the publish
+      }
+      // superblocks < sbc are final: their interior was stored a step ago, the bottom rows of the
+      // shared 8 columns right after this step's vertical pass
+      if (lane == 0) st_release(prog + sbr, base + (uint32_t)sbc);
+      if (work) {
+        bar_sync(3, nall);   // B3: horizontal pass done
+        if (hy) {
+#pragma unroll
+          for (int k = 0; k < kMaxHalo; k++)
+            if (h_pl[k] >= 0) {
+              Vec vv;
+              smem_get(tile + h_soff[k], vv);
+              __stcg((Vec *)gptr(h_pl[k], h_goff[k], sbc), vv);
+            }
+        }
+      }
+    }
+    bar_sync(2, nall);       // the last superblock's stores
+    if (lane == 0) st_release(prog + sbr, base + (uint32_t)P.sb_cols);
+    return;
+  }
+
+  // -------------------------------------------------------------------- worker warps
+  // per-thread vector slots are fixed across superblocks: precompute plane / offsets once
+  int int_goff[kMaxInt], int_soff[kMaxInt], int_pl[kMaxInt], int_fl[kMaxInt];
 #pragma unroll
   for (int k = 0; k < kMaxInt; k++) {
-    const int i = tid + k * nthreads;
+    const int i = tid + k * nworkers;
     int_pl[k] = -1;
     if (i < nInt) {
       const Px *g; Px *sm;
-      vec_addr(i, false, 0, g, sm);
-      int_pl[k] = i < vY ? 0 : (i < vY + vC ? 1 : 2);
-      int_goff[k] = (int)(g - (const Px *)P.dst[int_pl[k]].ptr);   // offset for superblock column 0
+      vec_addr(i, false, g, sm, int_pl[k], int_fl[k]);
+      int_goff[k] = (int)(g - (const Px *)P.dst[int_pl[k]].ptr);
       int_soff[k] = (int)(sm - tile);
     }
   }
-#pragma unroll
-  for (int k = 0; k < kMaxHalo; k++) {
-    const int i = tid + k * nthreads;
-    halo_pl[k] = -1;
-    if (i < nHalo) {
-      const Px *g; Px *sm;
-      vec_addr(i, true, 0, g, sm);
-      halo_pl[k] = i < hYv ? 0 : (i < hYv + hCv ? 1 : 2);
-      halo_goff[k] = (int)(g - (const Px *)P.dst[halo_pl[k]].ptr);
-      halo_soff[k] = (int)(sm - tile);
-    }
-  }
-  auto gptr = [&](int pl, int goff, int sbc) -> Px * { return (Px *)P.dst[pl].ptr + goff + sbc * (pl ? nC : 64); };
   Vec pre[kMaxInt];
   auto prefetch = [&](int sbc) {
 #pragma unroll
@@ -969,199 +1026,160 @@ __global__ void __launch_bounds__(192) k_loopfilter(const __grid_constant__ Fram
   bool work = has_work(0);
   if (work) prefetch(0);
   bool left_in_smem = false;
-  int pending_publish = 0;     // superblocks finished but not yet published (thread 0)
-  uint32_t seen = base;        // last progress value of the row above seen by thread 0
   for (int sbc = 0; sbc < P.sb_cols; sbc++) {
     const vp9b_lfm &M = P.lfm[sbr * P.sb_cols + sbc];
     const int hx = sbc > 0 ? 8 : 0;
     const bool work_next = (sbc + 1 < P.sb_cols) && has_work(sbc + 1);
     LFT(0)
-    if (work) {
-      // ---- (A) staged interior -> shared; left halo from global only if it was not carried
+    if (!work) {
+      bar_sync(2, nall);
+      left_in_smem = false;
+      if (work_next) prefetch(sbc + 1);
+      work = work_next;
+      continue;
+    }
+    // ---- (A) staged interior -> shared; left halo from global only if it was not carried
 #pragma unroll
-      for (int k = 0; k < kMaxInt; k++)
-        if (int_pl[k] >= 0) smem_put(tile + int_soff[k], pre[k]);
-      if (hx && !left_in_smem) {
-        for (int i = tid; i < 64 + 2 * nC; i += nthreads) {
-          const int p = i < 64 ? 0 : (i < 64 + nC ? 1 : 2), r = i < 64 ? i : (i < 64 + nC ? i - 64 : i - 64 - nC);
-          const int pn = p ? nC : 64, pts = p ? tsC : tsY, stride = P.dst[p].stride;
-          const Px *g = (const Px *)P.dst[p].ptr + (size_t)(sbr * pn + r) * stride + sbc * pn - 8;
-          smem_put(tile + (p == 0 ? 0 : (p == 1 ? offU : offV)) + (8 + r) * pts, __ldcg((const Vec *)g));
-        }
+    for (int k = 0; k < kMaxInt; k++)
+      if (int_pl[k] >= 0) smem_put(tile + int_soff[k], pre[k]);
+    if (hx && !left_in_smem) {
+      for (int i = tid; i < 64 + 2 * nC; i += nworkers) {
+        const int p = i < 64 ? 0 : (i < 64 + nC ? 1 : 2), r = i < 64 ? i : (i < 64 + nC ? i - 64 : i - 64 - nC);
+        const int pn = p ? nC : 64, pts = p ? tsC : tsY, stride = P.dst[p].stride;
+        const Px *g = (const Px *)P.dst[p].ptr + (size_t)(sbr * pn + r) * stride + sbc * pn - 8;
+        smem_put(tile + (p == 0 ? 0 : (p == 1 ? offU : offV)) + (8 + r) * pts, __ldcg((const Vec *)g));
       }
     }
     // ---- prefetch the next superblock's interior (nobody else touches it before this CTA)
     if (work_next) prefetch(sbc + 1);
-    // ---- (B) the row above must have finished superblock sbc+1 (above-right).  Polling uses
-    // relaxed loads; the data itself is read with L2-coherent (.cg) loads issued afterwards.
-    if (hy && tid == 0) {
-      const int need = min(sbc + 2, P.sb_cols);
-      while ((int)(seen - base) < need) {
-        seen = ld_relaxed(prog + sbr - 1);
-        if ((int)(seen - base) < need) __nanosleep(20);
-      }
-    }
     LFT(1)
-    __syncthreads();
+    bar_sync(1, nworkers);   // B1 (workers only)
     LFT(2)
-    if (work) {
-      // ---- (C) top halo: issue now, consume after the vertical pass
-      Vec halo[kMaxHalo];
-      if (hy) {
-#pragma unroll
-        for (int k = 0; k < kMaxHalo; k++)
-          if (halo_pl[k] >= 0) halo[k] = __ldcg((const Vec *)gptr(halo_pl[k], halo_goff[k], sbc));
-      }
-      // ---- (D) vertical edges: thread = sample row
-      {
-        const int y = my_idx, r8 = y >> 3, pr = r8 & ~1;
-        const int mrow = uvsub ? 2 * pr : pr;
-        if (mi_row + mrow < P.mi_rows) {
-          uint32_t m16, m16n, m8, m4, m4i;
-          if (!uvsub) {
-            m16 = (uint32_t)(M.left_y[2] >> (r8 * 8)) & 0xff;
-            m16n = (uint32_t)(M.left_y[2] >> (pr * 8)) & (uint32_t)(M.left_y[2] >> (pr * 8 + 8)) & 0xff;
-            m8 = (uint32_t)(M.left_y[1] >> (r8 * 8)) & 0xff;
-            m4 = (uint32_t)(M.left_y[0] >> (r8 * 8)) & 0xff;
-            m4i = (uint32_t)(M.int_4x4_y >> (r8 * 8)) & 0xff;
-          } else {
-            m16 = (uint32_t)(M.left_uv[2] >> (r8 * 4)) & 0xf;
-            m16n = (uint32_t)(M.left_uv[2] >> (pr * 4)) & (uint32_t)(M.left_uv[2] >> (pr * 4 + 4)) & 0xf;
-            m8 = (uint32_t)(M.left_uv[1] >> (r8 * 4)) & 0xf;
-            m4 = (uint32_t)(M.left_uv[0] >> (r8 * 4)) & 0xf;
-            m4i = (uint32_t)(M.int_4x4_uv >> (r8 * 4)) & 0xf;
+    // ---- (D) vertical edges: thread = sample row
+    {
+      const int y = my_idx, r8 = y >> 3, pr = r8 & ~1;
+      const int mrow = uvsub ? 2 * pr : pr;
+      Px *row = T + y * ts;
+      if (mi_row + mrow < P.mi_rows) {
+        uint32_t m16, m16n, m8, m4, m4i;
+        if (!uvsub) {
+          m16 = (uint32_t)(M.left_y[2] >> (r8 * 8)) & 0xff;
+          m16n = (uint32_t)(M.left_y[2] >> (pr * 8)) & (uint32_t)(M.left_y[2] >> (pr * 8 + 8)) & 0xff;
+          m8 = (uint32_t)(M.left_y[1] >> (r8 * 8)) & 0xff;
+          m4 = (uint32_t)(M.left_y[0] >> (r8 * 8)) & 0xff;
+          m4i = (uint32_t)(M.int_4x4_y >> (r8 * 8)) & 0xff;
+        } else {
+          m16 = (uint32_t)(M.left_uv[2] >> (r8 * 4)) & 0xf;
+          m16n = (uint32_t)(M.left_uv[2] >> (pr * 4)) & (uint32_t)(M.left_uv[2] >> (pr * 4 + 4)) & 0xf;
+          m8 = (uint32_t)(M.left_uv[1] >> (r8 * 4)) & 0xf;
+          m4 = (uint32_t)(M.left_uv[0] >> (r8 * 4)) & 0xf;
+          m4i = (uint32_t)(M.int_4x4_uv >> (r8 * 4)) & 0xf;
+        }
+        uint32_t all = m16 | m8 | m4 | m4i;
+        while (all) {
+          const int c = __ffs(all) - 1;
+          all &= all - 1;
+          const int lo = uvsub ? M.lfl_y[(2 * r8) * 8 + 2 * c] : M.lfl_y[r8 * 8 + c];
+          Px *s = row + c * 8;
+          if ((m16 >> c) & 1) {
+            // dual 16 (both rows of the pair set): both bands use the first band's level
+            const int lv = ((m16n >> c) & 1) ? (uvsub ? M.lfl_y[(2 * pr) * 8 + 2 * c] : M.lfl_y[pr * 8 + c]) : lo;
+            lf_px<Px>(s, 1, 16, P.lf_mblim[lv], P.lf_lim[lv], lv >> 4, P.bd);
+          } else if ((m8 >> c) & 1) {
+            lf_px<Px>(s, 1, 8, P.lf_mblim[lo], P.lf_lim[lo], lo >> 4, P.bd);
+          } else if ((m4 >> c) & 1) {
+            lf_px<Px>(s, 1, 4, P.lf_mblim[lo], P.lf_lim[lo], lo >> 4, P.bd);
           }
-          uint32_t all = m16 | m8 | m4 | m4i;
-          Px *row = T + y * ts;
-          while (all) {
-            const int c = __ffs(all) - 1;
-            all &= all - 1;
-            const int lo = uvsub ? M.lfl_y[(2 * r8) * 8 + 2 * c] : M.lfl_y[r8 * 8 + c];
-            Px *s = row + c * 8;
-            if ((m16 >> c) & 1) {
-              // dual 16 (both rows of the pair set): both bands use the first band's level
-              const int lv = ((m16n >> c) & 1) ? (uvsub ? M.lfl_y[(2 * pr) * 8 + 2 * c] : M.lfl_y[pr * 8 + c]) : lo;
-              lf_px<Px>(s, 1, 16, P.lf_mblim[lv], P.lf_lim[lv], lv >> 4, P.bd);
-            } else if ((m8 >> c) & 1) {
-              lf_px<Px>(s, 1, 8, P.lf_mblim[lo], P.lf_lim[lo], lo >> 4, P.bd);
-            } else if ((m4 >> c) & 1) {
-              lf_px<Px>(s, 1, 4, P.lf_mblim[lo], P.lf_lim[lo], lo >> 4, P.bd);
-            }
-            if ((m4i >> c) & 1) lf_px<Px>(s + 4, 1, 4, P.lf_mblim[lo], P.lf_lim[lo], lo >> 4, P.bd);
-          }
+          if ((m4i >> c) & 1) lf_px<Px>(s + 4, 1, 4, P.lf_mblim[lo], P.lf_lim[lo], lo >> 4, P.bd);
         }
       }
-      LFT(3)
-      // ---- top halo registers -> shared (the vertical pass never touches halo rows)
-      if (hy) {
-#pragma unroll
-        for (int k = 0; k < kMaxHalo; k++)
-          if (halo_pl[k] >= 0) smem_put(tile + halo_soff[k], halo[k]);
+      // the bottom 8 rows of the left halo are final now (the horizontal pass never touches the
+      // halo columns): store them so that the control warp can release superblock sbc-1 to the
+      // row below a whole pass earlier
+      if (hx && y >= n - 8) {
+        Vec vl;
+        smem_get(row - 8, vl);
+        __stcg((Vec *)((Px *)P.dst[my_plane].ptr + (size_t)(sbr * n + y) * P.dst[my_plane].stride + sbc * n - 8), vl);
       }
-      // publish the previous superblock now: its stores were issued a whole pass ago, so the
-      // release fence does not wait
-      if (tid == 0 && pending_publish) {
-        st_release(prog + sbr, base + (uint32_t)sbc);
-        pending_publish = 0;
-      }
-      __syncthreads();
-      LFT(4)
-      // ---- (E) horizontal edges: thread = sample column
-      {
-        const int x = my_idx, c = x >> 3;
-        Px *col = T + x;
-        for (int r = 0; r < nb; r++) {
-          const int mrow = uvsub ? 2 * r : r;
-          if (mi_row + mrow >= P.mi_rows) break;
-          uint32_t row16, row8, row4, row4i;
-          const uint8_t *lfl;
-          int lstep;
-          if (!uvsub) {
-            row16 = (uint32_t)(M.above_y[2] >> (r * 8)) & 0xff;
-            row8 = (uint32_t)(M.above_y[1] >> (r * 8)) & 0xff;
-            row4 = (uint32_t)(M.above_y[0] >> (r * 8)) & 0xff;
-            row4i = (uint32_t)(M.int_4x4_y >> (r * 8)) & 0xff;
-            lfl = &M.lfl_y[r * 8];
-            lstep = 1;
-          } else {
-            row16 = (uint32_t)(M.above_uv[2] >> (r * 4)) & 0xf;
-            row8 = (uint32_t)(M.above_uv[1] >> (r * 4)) & 0xf;
-            row4 = (uint32_t)(M.above_uv[0] >> (r * 4)) & 0xf;
-            row4i = (uint32_t)(M.int_4x4_uv >> (r * 4)) & 0xf;
-            if (mi_row + mrow == P.mi_rows - 1) row4i = 0;  // skip_border_4x4_r
-            lfl = &M.lfl_y[(2 * r) * 8];
-            lstep = 2;
-          }
-          if (mi_row + mrow == 0) row16 = row8 = row4 = 0;
-          if (!(((row16 | row8 | row4 | row4i) >> c) & 1)) continue;
-          Px *s = col + r * 8 * ts;
-          const int lvl = lfl[c * lstep];
-          if ((row16 >> c) & 1) {
-            // greedy pairing from the left (vpx_lpf_horizontal_16_dual): the second block of a
-            // pair is filtered with the first block's thresholds
-            int start = c;
-            while (start > 0 && ((row16 >> (start - 1)) & 1)) start--;
-            const int lv = ((c - start) & 1) ? lfl[(c - 1) * lstep] : lvl;
-            lf_px<Px>(s, ts, 16, P.lf_mblim[lv], P.lf_lim[lv], lv >> 4, P.bd);
-          } else if ((row8 >> c) & 1) {
-            lf_px<Px>(s, ts, 8, P.lf_mblim[lvl], P.lf_lim[lvl], lvl >> 4, P.bd);
-          } else if ((row4 >> c) & 1) {
-            lf_px<Px>(s, ts, 4, P.lf_mblim[lvl], P.lf_lim[lvl], lvl >> 4, P.bd);
-          }
-          if (!((row16 >> c) & 1) && ((row4i >> c) & 1))
-            lf_px<Px>(s + 4 * ts, ts, 4, P.lf_mblim[lvl], P.lf_lim[lvl], lvl >> 4, P.bd);
-        }
-      }
-      LFT(5)
-      __syncthreads();
-      LFT(6)
-      // ---- (F) store: top halo rows (columns of this superblock only) and the interior
-#pragma unroll
-      for (int k = 0; k < kMaxInt; k++)
-        if (int_pl[k] >= 0) {
-          Vec vv;
-          smem_get(tile + int_soff[k], vv);
-          __stcg((Vec *)gptr(int_pl[k], int_goff[k], sbc), vv);
-        }
-      if (hy) {
-#pragma unroll
-        for (int k = 0; k < kMaxHalo; k++)
-          if (halo_pl[k] >= 0) {
-            Vec vv;
-            smem_get(tile + halo_soff[k], vv);
-            __stcg((Vec *)gptr(halo_pl[k], halo_goff[k], sbc), vv);
-          }
-      }
-      // ---- (G) per row: store the left halo, then overwrite it with this superblock's
-      // right-most 8 columns (the next superblock's left halo).  Same thread reads then writes
-      // the halo columns; nobody else touches them, so no barrier in between.
-      for (int i = tid; i < 64 + 2 * nC; i += nthreads) {
-        const int p = i < 64 ? 0 : (i < 64 + nC ? 1 : 2), r = i < 64 ? i : (i < 64 + nC ? i - 64 : i - 64 - nC);
-        const int pn = p ? nC : 64, pts = p ? tsC : tsY, stride = P.dst[p].stride;
-        Px *rowp = tile + (p == 0 ? 0 : (p == 1 ? offU : offV)) + (8 + r) * pts;
-        Vec vl, vr;
-        smem_get(rowp, vl);
-        smem_get(rowp + pn, vr);
-        if (hx) __stcg((Vec *)((Px *)P.dst[p].ptr + (size_t)(sbr * pn + r) * stride + sbc * pn - 8), vl);
-        smem_put(rowp, vr);
-      }
-      left_in_smem = true;
-    } else {
-      left_in_smem = false;
     }
+    LFT(3)
+    bar_sync(2, nall);       // B2
+    LFT(4)
+    // ---- (E) horizontal edges: thread = sample column
+    {
+      const int x = my_idx, c = x >> 3;
+      Px *col = T + x;
+      for (int r = 0; r < nb; r++) {
+        const int mrow = uvsub ? 2 * r : r;
+        if (mi_row + mrow >= P.mi_rows) break;
+        uint32_t row16, row8, row4, row4i;
+        const uint8_t *lfl;
+        int lstep;
+        if (!uvsub) {
+          row16 = (uint32_t)(M.above_y[2] >> (r * 8)) & 0xff;
+          row8 = (uint32_t)(M.above_y[1] >> (r * 8)) & 0xff;
+          row4 = (uint32_t)(M.above_y[0] >> (r * 8)) & 0xff;
+          row4i = (uint32_t)(M.int_4x4_y >> (r * 8)) & 0xff;
+          lfl = &M.lfl_y[r * 8];
+          lstep = 1;
+        } else {
+          row16 = (uint32_t)(M.above_uv[2] >> (r * 4)) & 0xf;
+          row8 = (uint32_t)(M.above_uv[1] >> (r * 4)) & 0xf;
+          row4 = (uint32_t)(M.above_uv[0] >> (r * 4)) & 0xf;
+          row4i = (uint32_t)(M.int_4x4_uv >> (r * 4)) & 0xf;
+          if (mi_row + mrow == P.mi_rows - 1) row4i = 0;  // skip_border_4x4_r
+          lfl = &M.lfl_y[(2 * r) * 8];
+          lstep = 2;
+        }
+        if (mi_row + mrow == 0) row16 = row8 = row4 = 0;
+        if (!(((row16 | row8 | row4 | row4i) >> c) & 1)) continue;
+        Px *s = col + r * 8 * ts;
+        const int lvl = lfl[c * lstep];
+        if ((row16 >> c) & 1) {
+          // greedy pairing from the left (vpx_lpf_horizontal_16_dual): the second block of a
+          // pair is filtered with the first block's thresholds
+          int start = c;
+          while (start > 0 && ((row16 >> (start - 1)) & 1)) start--;
+          const int lv = ((c - start) & 1) ? lfl[(c - 1) * lstep] : lvl;
+          lf_px<Px>(s, ts, 16, P.lf_mblim[lv], P.lf_lim[lv], lv >> 4, P.bd);
+        } else if ((row8 >> c) & 1) {
+          lf_px<Px>(s, ts, 8, P.lf_mblim[lvl], P.lf_lim[lvl], lvl >> 4, P.bd);
+        } else if ((row4 >> c) & 1) {
+          lf_px<Px>(s, ts, 4, P.lf_mblim[lvl], P.lf_lim[lvl], lvl >> 4, P.bd);
+        }
+        if (!((row16 >> c) & 1) && ((row4i >> c) & 1))
+          lf_px<Px>(s + 4 * ts, ts, 4, P.lf_mblim[lvl], P.lf_lim[lvl], lvl >> 4, P.bd);
+      }
+    }
+    LFT(5)
+    bar_sync(3, nall);       // B3
+    LFT(6)
+    // ---- (F) store the interior.  The owner of a row's last vector also stores that row's left
+    // halo (upper rows only: the bottom 8 went out after the vertical pass) and replaces it with
+    // the right-most 8 columns, the next superblock's left halo.
+#pragma unroll
+    for (int k = 0; k < kMaxInt; k++)
+      if (int_pl[k] >= 0) {
+        Vec vv;
+        smem_get(tile + int_soff[k], vv);
+        Px *g = gptr(int_pl[k], int_goff[k], sbc);
+        __stcg((Vec *)g, vv);
+        if (int_fl[k] & 1) {
+          const int pn = int_pl[k] ? nC : 64;
+          Px *hp = tile + int_soff[k] - pn;
+          if (hx && !(int_fl[k] & 2)) {
+            Vec vl;
+            smem_get(hp, vl);
+            __stcg((Vec *)(g - pn), vl);
+          }
+          smem_put(hp, vv);
+        }
+      }
+    left_in_smem = true;
     LFT(7)
-    __syncthreads();
-    if (tid == 0) {
-      if (!work || sbc == P.sb_cols - 1) {
-        // nothing in flight worth hiding (or end of row): publish right away
-        st_release(prog + sbr, base + (uint32_t)(sbc + 1));
-        pending_publish = 0;
-      } else {
-        pending_publish = 1;
-      }
-    }
     work = work_next;
   }
+  bar_sync(2, nall);         // all stores of the row are issued: the control warp publishes the row end
 }
 
 }  // namespace vp9b
@@ -1409,7 +1427,7 @@ static int launch_stages(vp9gpu_ctx *ctx, const FrameParams &P, const vp9b_frame
   if (stop == 3) return 0;
   if (h->lf_level) {
     const bool sub = P.ss_x != 0;
-    const int threads = sub ? 128 : 192;
+    const int threads = (sub ? 128 : 192) + 32;  // worker warps + one control warp
     const int tsY = sizeof(Px) == 1 ? 76 : 74, tsC = sub ? (sizeof(Px) == 1 ? 44 : 42) : tsY, nC = sub ? 32 : 64;
     const size_t smem = sizeof(Px) * (size_t)(72 * tsY + 2 * (nC + 8) * tsC) + 32;
     k_loopfilter<Px><<<P.sb_rows, threads, smem, st>>>(P);
