@@ -872,61 +872,67 @@ struct LfPlane {
 __device__ unsigned long long d_lf_dbg[64 * 8];
 #ifdef VP9B_LF_TIMING
 VP9B_DEV unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
-#define LFT(k) if (tid == 0 && sbr == 2 && sbc < 64) d_lf_dbg[sbc * 8 + (k)] = gtime();
+#define LFT(k) if (tid == 0 && (sbr == 2 || sbr == 3) && sbc < 32) d_lf_dbg[((sbr - 2) * 32 + sbc) * 8 + (k)] = gtime();
 #else
 #define LFT(k)
 #endif
 VP9B_DEV void bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
+VP9B_DEV void bar_arrive(int id, int nthreads) {
+  asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
 
-template <typename Px>
-__global__ void __launch_bounds__(224) k_loopfilter(const __grid_constant__ FrameParams P) {
+template <typename Px, int NW>
+__global__ void __launch_bounds__(NW + 64, NW == 128 ? 3 : 2) k_loopfilter(const __grid_constant__ FrameParams P) {
   // One persistent CTA per superblock ROW walks its row left to right: 4 (4:2:0) or 6 (4:4:4)
-  // worker warps filter, one control warp talks to the neighbouring rows.
-  //   workers, per superblock c:  staged interior -> shared | B1 | vertical edges (thread = sample
-  //     row), bottom 8 rows of the left halo stored right away | B2 | horizontal edges (thread =
-  //     sample column) | B3 | store interior, carry the right-most 8 columns as the next left halo.
-  //     The interior of c+1 is prefetched into registers while c is filtered; a thread stores and
-  //     re-fills only its own shared-memory slots, so no barrier separates two superblocks.
-  //   control warp: waits until the row above has finished superblock c (its bottom rows are
-  //     final once that row has run the vertical pass of c+1), loads the 8 halo rows above into
-  //     shared memory while the workers are still in the vertical pass | B2 | publishes "c-1 is
-  //     final" for the row below | B3 | stores the (now filtered) halo rows back.
-  // Only the first horizontal edge of a superblock depends on the row above, and only the
-  // control warp ever waits for it.
+  // worker warps filter, a halo warp and a publish warp talk to the neighbouring rows.
+  //
+  // libvpx filters superblock by superblock: all vertical edges of c, all horizontal edges of c,
+  // then c+1 (vp9_loopfilter.c:1440-1467).  The only operation of c+1 that touches samples of c
+  // is its left-most vertical edge, so each step here runs
+  //     vertical edges 1..7 of c  ->  horizontal edges of c  ->  left edge of c+1
+  // which is the same order along every sample row and column, and leaves superblock c final at
+  // the end of its own step: the row below can start on c one step (not two) behind.
+  //
+  //   workers, per superblock c (tile = 64 columns of c + the first 8 of c+1, all planes):
+  //     staged interior -> shared | B1 | vertical edges (thread = sample row) | B2 | horizontal
+  //     edges (thread = sample column) | B3 | left edge of c+1 | B5 | store the 64 columns of c,
+  //     move the 8 look-ahead columns to the front | arrive B6.
+  //     The interior of c+1 is prefetched into registers while c is filtered, and a thread
+  //     stores and re-fills only its own shared-memory slots, so nothing separates two steps.
+  //   halo warp: waits until the row above has published superblock c, loads the 8 rows above
+  //     it into shared memory while the workers are in the vertical pass | B2 | B3 | stores the
+  //     (now filtered) rows back.
+  //   publish warp: B6 (all stores of c issued) -> st.release "c+1 superblocks final".
   extern __shared__ __align__(16) unsigned char lf_smem[];
   Px *tile = (Px *)lf_smem;
   typedef typename LfVec<Px>::T Vec;
-  const int tid = threadIdx.x, nworkers = blockDim.x - 32, nall = blockDim.x;
-  const bool is_ctrl = tid >= nworkers;
+  constexpr int nworkers = NW;   // 128: 4:2:0, 192: 4:4:4
+  const int tid = threadIdx.x;
+  const int n_b2 = nworkers + 64, n_b3 = nworkers + 32, n_b6 = nworkers + 32;
   const int lane = tid & 31;
-  const bool sub = P.ss_x != 0;  // 4:2:0 (else 4:4:4)
+  constexpr bool sub = NW == 128;  // 4:2:0 (else 4:4:4)
   // stride in samples: (stride bytes / 4) odd -> conflict-free row-per-thread walks
-  const int tsY = sizeof(Px) == 1 ? 76 : 74, tsC = sub ? (sizeof(Px) == 1 ? 44 : 42) : tsY;
-  const int nC = sub ? 32 : 64;
-  const int offU = 72 * tsY, offV = 72 * tsY + (nC + 8) * tsC;
-  int my_plane, my_idx;
-  if (tid < 64) { my_plane = 0; my_idx = tid; }
-  else if (tid < 64 + nC) { my_plane = 1; my_idx = tid - 64; }
-  else { my_plane = 2; my_idx = tid - 64 - nC; }
-  const bool uvsub = my_plane && sub;
-  const int n = my_plane ? nC : 64, ts = my_plane ? tsC : tsY, nb = n >> 3;
-  Px *T = tile + (my_plane == 0 ? 0 : (my_plane == 1 ? offU : offV)) + 8 * ts + 8;
-  const int sbr = blockIdx.x;
+  constexpr int tsY = sizeof(Px) == 1 ? 76 : 74, tsC = sub ? (sizeof(Px) == 1 ? 44 : 42) : tsY;
+  constexpr int nC = sub ? 32 : 64;
+  constexpr int offU = 72 * tsY, offV = 72 * tsY + (nC + 8) * tsC;
+  // has-work flag per superblock of this row, computed once (the loops below look two ahead)
+  uint8_t *wk = (uint8_t *)(tile + offV + (nC + 8) * tsC) + 16;
+  const int sbr = blockIdx.x, sb_cols = P.sb_cols;
   const int mi_row = sbr * 8;
   const int hy = sbr > 0 ? 8 : 0;
   uint32_t *prog = P.prog_lf;  // [sb_rows] prog_base + number of leading superblocks that are final
   const uint32_t base = P.prog_base;
 
   // vectors of 8 samples, flattened over the three planes:  interior rows / top-halo rows
-  const int vY = 64 * 8, vC = nC * (nC >> 3);             // interior vectors per plane
-  const int nInt = vY + 2 * vC;
-  const int hYv = 8 * 8, hCv = 8 * (nC >> 3);             // top-halo vectors per plane
-  const int nHalo = hYv + 2 * hCv;
-  constexpr int kMaxInt = 8, kMaxHalo = 6;                // per-thread slots (128 workers: 6, 192: 8; control lane: 4 / 6)
-  auto vec_addr = [&](int i, bool halo, const Px *&g, Px *&sm, int &pl, int &flags) {
-    // maps flat vector index -> global address (superblock column 0), shared address, plane
+  constexpr int vY = 64 * 8, vC = nC * (nC >> 3);         // interior vectors per plane
+  constexpr int nInt = vY + 2 * vC;
+  constexpr int hYv = 8 * 8, hCv = 8 * (nC >> 3);         // top-halo vectors per plane
+  constexpr int nHalo = hYv + 2 * hCv;
+  constexpr int kMaxInt = (nInt + NW - 1) / NW, kMaxHalo = (nHalo + 31) / 32;  // slots per worker thread / halo lane
+  auto vec_addr = [&](int i, bool halo, const Px *&g, Px *&sm, int &pl, int &first) {
+    // flat vector index -> global address (superblock column 0), shared address, plane
     int p, r, v;
     const int a = halo ? hYv : vY, bq = halo ? hCv : vC;
     if (i < a) { p = 0; }
@@ -934,42 +940,61 @@ __global__ void __launch_bounds__(224) k_loopfilter(const __grid_constant__ Fram
     else { p = 2; i -= a + bq; }
     const int pn = p ? nC : 64, pts = p ? tsC : tsY, vpr = pn >> 3;
     r = i / vpr; v = i % vpr;
-    flags = (v == vpr - 1 ? 1 : 0) | (r >= pn - 8 ? 2 : 0);
+    first = v == 0;
     if (halo) r -= 8;
     const int stride = P.dst[p].stride;
     g = (const Px *)P.dst[p].ptr + (ptrdiff_t)(sbr * pn + r) * stride + v * 8;
-    sm = tile + (p == 0 ? 0 : (p == 1 ? offU : offV)) + (8 + r) * pts + 8 + v * 8;
+    sm = tile + (p == 0 ? 0 : (p == 1 ? offU : offV)) + (8 + r) * pts + v * 8;
     pl = p;
   };
-  auto has_work = [&](int sbc) -> bool {
-    const vp9b_lfm &M = P.lfm[sbr * P.sb_cols + sbc];
-    const uint64_t anyY = M.left_y[0] | M.left_y[1] | M.left_y[2] | M.above_y[0] | M.above_y[1] | M.above_y[2] | M.int_4x4_y;
-    const uint32_t anyUV = M.left_uv[0] | M.left_uv[1] | M.left_uv[2] | M.above_uv[0] | M.above_uv[1] | M.above_uv[2] | M.int_4x4_uv;
-    return (anyY | anyUV) != 0;
-  };
+  for (int c = tid; c < sb_cols + 2; c += NW + 64) {
+    bool w = false;
+    if (c < sb_cols) {
+      const vp9b_lfm &M = P.lfm[sbr * sb_cols + c];
+      const uint64_t anyY = M.left_y[0] | M.left_y[1] | M.left_y[2] | M.above_y[0] | M.above_y[1] | M.above_y[2] | M.int_4x4_y;
+      const uint32_t anyUV = M.left_uv[0] | M.left_uv[1] | M.left_uv[2] | M.above_uv[0] | M.above_uv[1] | M.above_uv[2] | M.int_4x4_uv;
+      w = (anyY | anyUV) != 0;
+    }
+    wk[c] = w;
+  }
+  __syncthreads();
+  auto has_work = [&](int sbc) -> bool { return wk[sbc] != 0; };   // valid up to sb_cols + 1
   auto gptr = [&](int pl, int goff, int sbc) -> Px * { return (Px *)P.dst[pl].ptr + goff + sbc * (pl ? nC : 64); };
 
-  if (is_ctrl) {
-    // ------------------------------------------------------------------ control warp
+  if (tid >= nworkers + 32) {
+    // ------------------------------------------------------------------ publish warp
+    bool w0 = has_work(0);
+    for (int sbc = 0; sbc < sb_cols; sbc++) {
+      const bool w1 = has_work(sbc + 1);
+      if (w0 | w1) bar_sync(2, n_b2);   // keeps the workers at most one step ahead of the publishes
+      bar_sync(6, n_b6);                 // every store of superblock sbc has been issued
+      if (lane == 0) st_release(prog + sbr, base + (uint32_t)(sbc + 1));
+      w0 = w1;
+    }
+    return;
+  }
+  if (tid >= nworkers) {
+    // ------------------------------------------------------------------ halo warp
     int h_goff[kMaxHalo], h_soff[kMaxHalo], h_pl[kMaxHalo];
 #pragma unroll
     for (int k = 0; k < kMaxHalo; k++) {
       const int i = lane + k * 32;
       h_pl[k] = -1;
       if (hy && i < nHalo) {
-        const Px *g; Px *sm; int fl;
-        vec_addr(i, true, g, sm, h_pl[k], fl);
+        const Px *g; Px *sm; int f;
+        vec_addr(i, true, g, sm, h_pl[k], f);
         h_goff[k] = (int)(g - (const Px *)P.dst[h_pl[k]].ptr);
         h_soff[k] = (int)(sm - tile);
       }
     }
     uint32_t seen = base;
-    for (int sbc = 0; sbc < P.sb_cols; sbc++) {
-      const bool work = has_work(sbc);
-      if (work) {
-        if (hy) {
-          // the row above has finished superblock sbc (value counts leading final superblocks)
-          const int need = sbc + 1;
+    bool w0 = has_work(0);
+    for (int sbc = 0; sbc < sb_cols; sbc++) {
+      const bool w1 = has_work(sbc + 1);
+      if (w0 | w1) {
+        const bool need_halo = hy && w0;
+        if (need_halo) {
+          const int need = sbc + 1;   // the row above has finished superblock sbc
           if ((int)(seen - base) < need) {
             while ((int)((seen = ld_relaxed(prog + sbr - 1)) - base) < need) __nanosleep(20);
             seen = ld_acquire(prog + sbr - 1);
@@ -978,16 +1003,9 @@ __global__ void __launch_bounds__(224) k_loopfilter(const __grid_constant__ Fram
           for (int k = 0; k < kMaxHalo; k++)
             if (h_pl[k] >= 0) smem_put(tile + h_soff[k], __ldcg((const Vec *)gptr(h_pl[k], h_goff[k], sbc)));
         }
-        bar_sync(2, nall);   // B2: vertical pass done everywhere, halo rows in place
-      } else {
-        bar_sync(2, nall);   // keeps the stores of the previous superblock ahead of the publish
-      }
-      // superblocks < sbc are final: their interior was stored a step ago, the bottom rows of the
-      // shared 8 columns right after this step's vertical pass
-      if (lane == 0) st_release(prog + sbr, base + (uint32_t)sbc);
-      if (work) {
-        bar_sync(3, nall);   // B3: horizontal pass done
-        if (hy) {
+        bar_sync(2, n_b2);   // B2: halo rows in place / vertical pass done
+        bar_sync(3, n_b3);   // B3: horizontal pass done
+        if (need_halo) {
 #pragma unroll
           for (int k = 0; k < kMaxHalo; k++)
             if (h_pl[k] >= 0) {
@@ -997,116 +1015,121 @@ __global__ void __launch_bounds__(224) k_loopfilter(const __grid_constant__ Fram
             }
         }
       }
+      w0 = w1;
     }
-    bar_sync(2, nall);       // the last superblock's stores
-    if (lane == 0) st_release(prog + sbr, base + (uint32_t)P.sb_cols);
     return;
   }
 
   // -------------------------------------------------------------------- worker warps
-  // per-thread vector slots are fixed across superblocks: precompute plane / offsets once
-  int int_goff[kMaxInt], int_soff[kMaxInt], int_pl[kMaxInt], int_fl[kMaxInt];
+  int my_plane, my_idx;
+  if (tid < 64) { my_plane = 0; my_idx = tid; }
+  else if (tid < 64 + nC) { my_plane = 1; my_idx = tid - 64; }
+  else { my_plane = 2; my_idx = tid - 64 - nC; }
+  const bool uvsub = my_plane && sub;
+  const int n = my_plane ? nC : 64, ts = my_plane ? tsC : tsY, nb = n >> 3;
+  Px *T = tile + (my_plane == 0 ? 0 : (my_plane == 1 ? offU : offV)) + 8 * ts;   // sample (0,0) of superblock c
+  // per-thread vector slots are fixed across superblocks: precompute plane / offsets once.  Slot
+  // (row, v) holds columns 8v..8v+7 of the superblock; the v = 0 slot is also the one that loads
+  // the look-ahead columns (64.. of the tile = 0..7 of c+1) and moves them to the front.
+  int int_goff[kMaxInt], int_soff[kMaxInt], int_pl[kMaxInt], int_first[kMaxInt];
 #pragma unroll
   for (int k = 0; k < kMaxInt; k++) {
     const int i = tid + k * nworkers;
     int_pl[k] = -1;
+    int_first[k] = 0;
     if (i < nInt) {
       const Px *g; Px *sm;
-      vec_addr(i, false, g, sm, int_pl[k], int_fl[k]);
+      vec_addr(i, false, g, sm, int_pl[k], int_first[k]);
       int_goff[k] = (int)(g - (const Px *)P.dst[int_pl[k]].ptr);
       int_soff[k] = (int)(sm - tile);
     }
   }
   Vec pre[kMaxInt];
+  // registers <- interior of superblock sbc (columns 8..63) and the first 8 columns of sbc+1
   auto prefetch = [&](int sbc) {
 #pragma unroll
     for (int k = 0; k < kMaxInt; k++)
-      if (int_pl[k] >= 0) pre[k] = __ldcg((const Vec *)gptr(int_pl[k], int_goff[k], sbc));
+      if (int_pl[k] >= 0) {
+        if (!int_first[k]) pre[k] = __ldcg((const Vec *)gptr(int_pl[k], int_goff[k], sbc));
+        else if (sbc + 1 < sb_cols) pre[k] = __ldcg((const Vec *)gptr(int_pl[k], int_goff[k], sbc + 1));
+      }
   };
-  bool work = has_work(0);
-  if (work) prefetch(0);
-  bool left_in_smem = false;
-  for (int sbc = 0; sbc < P.sb_cols; sbc++) {
-    const vp9b_lfm &M = P.lfm[sbr * P.sb_cols + sbc];
-    const int hx = sbc > 0 ? 8 : 0;
-    const bool work_next = (sbc + 1 < P.sb_cols) && has_work(sbc + 1);
+  // vertical edge c (0..7) of the superblock described by M at row pointer `row` (sample 0 of
+  // that superblock in this thread's row); `edge` selects the 8-aligned edge, `inner` the 4x4 one
+  auto v_edges = [&](const vp9b_lfm &M, Px *row, uint32_t sel_edge, uint32_t sel_inner) {
+    const int y = my_idx, r8 = y >> 3, pr = r8 & ~1;
+    uint32_t m16, m16n, m8, m4, m4i;
+    if (!uvsub) {
+      m16 = (uint32_t)(M.left_y[2] >> (r8 * 8)) & 0xff;
+      m16n = (uint32_t)(M.left_y[2] >> (pr * 8)) & (uint32_t)(M.left_y[2] >> (pr * 8 + 8)) & 0xff;
+      m8 = (uint32_t)(M.left_y[1] >> (r8 * 8)) & 0xff;
+      m4 = (uint32_t)(M.left_y[0] >> (r8 * 8)) & 0xff;
+      m4i = (uint32_t)(M.int_4x4_y >> (r8 * 8)) & 0xff;
+    } else {
+      m16 = (uint32_t)(M.left_uv[2] >> (r8 * 4)) & 0xf;
+      m16n = (uint32_t)(M.left_uv[2] >> (pr * 4)) & (uint32_t)(M.left_uv[2] >> (pr * 4 + 4)) & 0xf;
+      m8 = (uint32_t)(M.left_uv[1] >> (r8 * 4)) & 0xf;
+      m4 = (uint32_t)(M.left_uv[0] >> (r8 * 4)) & 0xf;
+      m4i = (uint32_t)(M.int_4x4_uv >> (r8 * 4)) & 0xf;
+    }
+    m16 &= sel_edge; m8 &= sel_edge; m4 &= sel_edge; m4i &= sel_inner;
+    uint32_t all = m16 | m8 | m4 | m4i;
+    while (all) {
+      const int c = __ffs(all) - 1;
+      all &= all - 1;
+      const int lo = uvsub ? M.lfl_y[(2 * r8) * 8 + 2 * c] : M.lfl_y[r8 * 8 + c];
+      Px *s = row + c * 8;
+      if ((m16 >> c) & 1) {
+        // dual 16 (both rows of the pair set): both bands use the first band's level
+        const int lv = ((m16n >> c) & 1) ? (uvsub ? M.lfl_y[(2 * pr) * 8 + 2 * c] : M.lfl_y[pr * 8 + c]) : lo;
+        lf_px<Px>(s, 1, 16, P.lf_mblim[lv], P.lf_lim[lv], lv >> 4, P.bd);
+      } else if ((m8 >> c) & 1) {
+        lf_px<Px>(s, 1, 8, P.lf_mblim[lo], P.lf_lim[lo], lo >> 4, P.bd);
+      } else if ((m4 >> c) & 1) {
+        lf_px<Px>(s, 1, 4, P.lf_mblim[lo], P.lf_lim[lo], lo >> 4, P.bd);
+      }
+      if ((m4i >> c) & 1) lf_px<Px>(s + 4, 1, 4, P.lf_mblim[lo], P.lf_lim[lo], lo >> 4, P.bd);
+    }
+  };
+  const bool row_valid = mi_row + (uvsub ? 2 * ((my_idx >> 3) & ~1) : ((my_idx >> 3) & ~1)) < P.mi_rows;
+
+  bool w0 = has_work(0), w1 = has_work(1);
+  bool carry_valid = false;          // tile columns 0..7 hold the (left-edge filtered) start of superblock c
+  if (w0 | w1) prefetch(0);
+  for (int sbc = 0; sbc < sb_cols; sbc++) {
+    const bool w2 = has_work(sbc + 2);
+    const bool has_next = sbc + 1 < sb_cols;
     LFT(0)
-    if (!work) {
-      bar_sync(2, nall);
-      left_in_smem = false;
-      if (work_next) prefetch(sbc + 1);
-      work = work_next;
+    if (!(w0 | w1)) {                // nothing to filter in c, no left edge in c+1
+      bar_arrive(6, n_b6);
+      carry_valid = false;
+      if (w1 | w2) prefetch(sbc + 1);
+      w0 = w1; w1 = w2;
       continue;
     }
-    // ---- (A) staged interior -> shared; left halo from global only if it was not carried
+    const vp9b_lfm &M = P.lfm[sbr * sb_cols + sbc];
+    // ---- (A) staged registers -> shared; columns 0..7 from global only if they were not carried
 #pragma unroll
     for (int k = 0; k < kMaxInt; k++)
-      if (int_pl[k] >= 0) smem_put(tile + int_soff[k], pre[k]);
-    if (hx && !left_in_smem) {
-      for (int i = tid; i < 64 + 2 * nC; i += nworkers) {
-        const int p = i < 64 ? 0 : (i < 64 + nC ? 1 : 2), r = i < 64 ? i : (i < 64 + nC ? i - 64 : i - 64 - nC);
-        const int pn = p ? nC : 64, pts = p ? tsC : tsY, stride = P.dst[p].stride;
-        const Px *g = (const Px *)P.dst[p].ptr + (size_t)(sbr * pn + r) * stride + sbc * pn - 8;
-        smem_put(tile + (p == 0 ? 0 : (p == 1 ? offU : offV)) + (8 + r) * pts, __ldcg((const Vec *)g));
+      if (int_pl[k] >= 0) {
+        if (!int_first[k]) smem_put(tile + int_soff[k], pre[k]);
+        else {
+          if (has_next) smem_put(tile + int_soff[k] + (int_pl[k] ? nC : 64), pre[k]);
+          if (!carry_valid) smem_put(tile + int_soff[k], __ldcg((const Vec *)gptr(int_pl[k], int_goff[k], sbc)));
+        }
       }
-    }
-    // ---- prefetch the next superblock's interior (nobody else touches it before this CTA)
-    if (work_next) prefetch(sbc + 1);
+    // ---- prefetch the next step (nobody else touches those samples before this CTA is done with them)
+    if (w1 | w2) prefetch(sbc + 1);
     LFT(1)
     bar_sync(1, nworkers);   // B1 (workers only)
     LFT(2)
-    // ---- (D) vertical edges: thread = sample row
-    {
-      const int y = my_idx, r8 = y >> 3, pr = r8 & ~1;
-      const int mrow = uvsub ? 2 * pr : pr;
-      Px *row = T + y * ts;
-      if (mi_row + mrow < P.mi_rows) {
-        uint32_t m16, m16n, m8, m4, m4i;
-        if (!uvsub) {
-          m16 = (uint32_t)(M.left_y[2] >> (r8 * 8)) & 0xff;
-          m16n = (uint32_t)(M.left_y[2] >> (pr * 8)) & (uint32_t)(M.left_y[2] >> (pr * 8 + 8)) & 0xff;
-          m8 = (uint32_t)(M.left_y[1] >> (r8 * 8)) & 0xff;
-          m4 = (uint32_t)(M.left_y[0] >> (r8 * 8)) & 0xff;
-          m4i = (uint32_t)(M.int_4x4_y >> (r8 * 8)) & 0xff;
-        } else {
-          m16 = (uint32_t)(M.left_uv[2] >> (r8 * 4)) & 0xf;
-          m16n = (uint32_t)(M.left_uv[2] >> (pr * 4)) & (uint32_t)(M.left_uv[2] >> (pr * 4 + 4)) & 0xf;
-          m8 = (uint32_t)(M.left_uv[1] >> (r8 * 4)) & 0xf;
-          m4 = (uint32_t)(M.left_uv[0] >> (r8 * 4)) & 0xf;
-          m4i = (uint32_t)(M.int_4x4_uv >> (r8 * 4)) & 0xf;
-        }
-        uint32_t all = m16 | m8 | m4 | m4i;
-        while (all) {
-          const int c = __ffs(all) - 1;
-          all &= all - 1;
-          const int lo = uvsub ? M.lfl_y[(2 * r8) * 8 + 2 * c] : M.lfl_y[r8 * 8 + c];
-          Px *s = row + c * 8;
-          if ((m16 >> c) & 1) {
-            // dual 16 (both rows of the pair set): both bands use the first band's level
-            const int lv = ((m16n >> c) & 1) ? (uvsub ? M.lfl_y[(2 * pr) * 8 + 2 * c] : M.lfl_y[pr * 8 + c]) : lo;
-            lf_px<Px>(s, 1, 16, P.lf_mblim[lv], P.lf_lim[lv], lv >> 4, P.bd);
-          } else if ((m8 >> c) & 1) {
-            lf_px<Px>(s, 1, 8, P.lf_mblim[lo], P.lf_lim[lo], lo >> 4, P.bd);
-          } else if ((m4 >> c) & 1) {
-            lf_px<Px>(s, 1, 4, P.lf_mblim[lo], P.lf_lim[lo], lo >> 4, P.bd);
-          }
-          if ((m4i >> c) & 1) lf_px<Px>(s + 4, 1, 4, P.lf_mblim[lo], P.lf_lim[lo], lo >> 4, P.bd);
-        }
-      }
-      // the bottom 8 rows of the left halo are final now (the horizontal pass never touches the
-      // halo columns): store them so that the control warp can release superblock sbc-1 to the
-      // row below a whole pass earlier
-      if (hx && y >= n - 8) {
-        Vec vl;
-        smem_get(row - 8, vl);
-        __stcg((Vec *)((Px *)P.dst[my_plane].ptr + (size_t)(sbr * n + y) * P.dst[my_plane].stride + sbc * n - 8), vl);
-      }
-    }
+    // ---- vertical edges 1..7 and all inner 4x4 edges of c: thread = sample row
+    if (row_valid && w0) v_edges(M, T + my_idx * ts, 0xfe, 0xff);
     LFT(3)
-    bar_sync(2, nall);       // B2
+    bar_sync(2, n_b2);       // B2: + halo rows
     LFT(4)
-    // ---- (E) horizontal edges: thread = sample column
-    {
+    // ---- horizontal edges of c: thread = sample column
+    if (w0) {
       const int x = my_idx, c = x >> 3;
       Px *col = T + x;
       for (int r = 0; r < nb; r++) {
@@ -1152,34 +1175,28 @@ __global__ void __launch_bounds__(224) k_loopfilter(const __grid_constant__ Fram
       }
     }
     LFT(5)
-    bar_sync(3, nall);       // B3
+    bar_sync(3, n_b3);       // B3
     LFT(6)
-    // ---- (F) store the interior.  The owner of a row's last vector also stores that row's left
-    // halo (upper rows only: the bottom 8 went out after the vertical pass) and replaces it with
-    // the right-most 8 columns, the next superblock's left halo.
+    // ---- left edge of c+1 (reads / writes the last 8 columns of c and the look-ahead columns)
+    if (has_next && w1 && row_valid) v_edges(P.lfm[sbr * sb_cols + sbc + 1], T + my_idx * ts + n, 0x01, 0x00);
+    bar_sync(5, nworkers);   // B5 (workers only)
+    // ---- store the 64 columns of c (all final now); the v = 0 slot then takes the look-ahead columns
 #pragma unroll
     for (int k = 0; k < kMaxInt; k++)
       if (int_pl[k] >= 0) {
         Vec vv;
         smem_get(tile + int_soff[k], vv);
-        Px *g = gptr(int_pl[k], int_goff[k], sbc);
-        __stcg((Vec *)g, vv);
-        if (int_fl[k] & 1) {
-          const int pn = int_pl[k] ? nC : 64;
-          Px *hp = tile + int_soff[k] - pn;
-          if (hx && !(int_fl[k] & 2)) {
-            Vec vl;
-            smem_get(hp, vl);
-            __stcg((Vec *)(g - pn), vl);
-          }
-          smem_put(hp, vv);
+        __stcg((Vec *)gptr(int_pl[k], int_goff[k], sbc), vv);
+        if (int_first[k] && has_next) {
+          smem_get(tile + int_soff[k] + (int_pl[k] ? nC : 64), vv);
+          smem_put(tile + int_soff[k], vv);
         }
       }
-    left_in_smem = true;
+    bar_arrive(6, n_b6);     // the publish warp releases superblock c
+    carry_valid = true;
     LFT(7)
-    work = work_next;
+    w0 = w1; w1 = w2;
   }
-  bar_sync(2, nall);         // all stores of the row are issued: the control warp publishes the row end
 }
 
 }  // namespace vp9b
@@ -1427,10 +1444,11 @@ static int launch_stages(vp9gpu_ctx *ctx, const FrameParams &P, const vp9b_frame
   if (stop == 3) return 0;
   if (h->lf_level) {
     const bool sub = P.ss_x != 0;
-    const int threads = (sub ? 128 : 192) + 32;  // worker warps + one control warp
     const int tsY = sizeof(Px) == 1 ? 76 : 74, tsC = sub ? (sizeof(Px) == 1 ? 44 : 42) : tsY, nC = sub ? 32 : 64;
-    const size_t smem = sizeof(Px) * (size_t)(72 * tsY + 2 * (nC + 8) * tsC) + 32;
-    k_loopfilter<Px><<<P.sb_rows, threads, smem, st>>>(P);
+    // tiles + per-superblock work flags; threads = worker warps + halo warp + publish warp
+    const size_t smem = sizeof(Px) * (size_t)(72 * tsY + 2 * (nC + 8) * tsC) + 32 + ((P.sb_cols + 2 + 15) & ~15);
+    if (sub) k_loopfilter<Px, 128><<<P.sb_rows, 192, smem, st>>>(P);
+    else k_loopfilter<Px, 192><<<P.sb_rows, 256, smem, st>>>(P);
     ctx->launches++;
   }
   if (prof) {
