@@ -231,8 +231,8 @@ __global__ void k_inter_pred_generic(const __grid_constant__ FrameParams P, int 
 // 8-tap filters run as two DP4A (u8 samples x s8 taps) per output with byte windows built by
 // funnel shifts, the horizontally filtered rows are clipped and kept packed, transposed 4x4 by
 // PRMT so that the vertical pass is DP4A too, and results are packed with cvt.pack.sat.  The
-// compound average is a packed rounding byte average.  Units that touch the frame edge (need
-// clamped fetches) and scaled references fall back to predict_sample().
+// compound average is a packed rounding byte average.  Units that touch the frame edge run the
+// same code with clamped row loads; only scaled references fall back to predict_sample().
 __device__ __constant__ uint32_t d_taps4[4 * 16 * 2];  // [filter][phase][lo,hi] packed s8 taps
 
 VP9B_DEV int dp4a_us(uint32_t a, uint32_t b, int c) {
@@ -253,9 +253,31 @@ VP9B_DEV uint32_t avg_u8x4(uint32_t a, uint32_t b) {  // per byte (a + b + 1) >>
 // Predict a 4 x H unit (H = 4 or 8) from one reference; returns H packed rows in out[].
 // One code path for all sub-pel classes: lanes whose phase is 0 in a direction simply sit out
 // that direction's filter, so a warp pays for the most expensive class it contains, not the sum.
+// 16 bytes of reference row y starting at (4-aligned, possibly negative) column xa, every sample
+// position clamped to the reference crop size -- the frame-edge emulation of build_mc_border
+// (vp9_decodeframe.c:432-466).  Out of line: only units that touch the frame edge come here.
+__device__ __noinline__ uint4 mc_load_row_clamped(const uint8_t *__restrict__ ref, int rstride, int y, int xa, int rw,
+                                                  int rh) {
+  const uint8_t *row = ref + (ptrdiff_t)clampi(y, 0, rh - 1) * rstride;
+  uint32_t w[4];
+#pragma unroll
+  for (int j = 0; j < 4; j++) {
+    const int x = xa + 4 * j;
+    if (x >= 0 && x + 3 < rw) {
+      w[j] = __ldg((const uint32_t *)(row + x));
+    } else {
+      uint32_t v = 0;
+#pragma unroll
+      for (int k = 0; k < 4; k++) v |= (uint32_t)__ldg(row + clampi(x + k, 0, rw - 1)) << (8 * k);
+      w[j] = v;
+    }
+  }
+  return make_uint4(w[0], w[1], w[2], w[3]);
+}
+
 template <int H>
 VP9B_DEV void mc_unit_fast(const uint8_t *__restrict__ ref, int rstride, int x0, int y0, int sx, int sy, int filter,
-                           uint32_t *out) {
+                           bool edge, int rw, int rh, uint32_t *out) {
   constexpr int R = H + 7;  // rows y0-3 .. y0+H+3
   const uint32_t txl = d_taps4[(filter * 16 + sx) * 2], txh = d_taps4[(filter * 16 + sx) * 2 + 1];
   const uint32_t tyl = d_taps4[(filter * 16 + sy) * 2], tyh = d_taps4[(filter * 16 + sy) * 2 + 1];
@@ -266,7 +288,13 @@ VP9B_DEV void mc_unit_fast(const uint8_t *__restrict__ ref, int rstride, int x0,
   for (int r = 0; r < R; r++) {
     uint32_t v = 0;
     if (sy || (r >= 3 && r < 3 + H)) {
-      const uint32_t a0 = __ldg(p), a1 = __ldg(p + 1), a2 = __ldg(p + 2), a3 = __ldg(p + 3);
+      uint32_t a0, a1, a2, a3;
+      if (!edge) {
+        a0 = __ldg(p); a1 = __ldg(p + 1); a2 = __ldg(p + 2); a3 = __ldg(p + 3);
+      } else {
+        const uint4 a = mc_load_row_clamped(ref, rstride, y0 - 3 + r, xs & ~3, rw, rh);
+        a0 = a.x; a1 = a.y; a2 = a.z; a3 = a.w;
+      }
       const uint32_t v0 = __funnelshift_r(a0, a1, o), v1 = __funnelshift_r(a1, a2, o), v2 = __funnelshift_r(a2, a3, o);
       if (sx) {
         int s[4];
@@ -366,12 +394,12 @@ VP9B_DEV void mc_unit(const FrameParams &P, int plane, const MiEntry &e, int mi_
     if (R.x_step_q4 == 16 && R.y_step_q4 == 16) {
       const int smvr = mvr * (1 << (1 - ss_y)), smvc = mvc * (1 << (1 - ss_x));
       const int x0 = x + (smvc >> 4), y0 = y + (smvr >> 4);
-      if (mc_inside(x0, y0, H, R.w[plane], R.h[plane])) {
-        mc_unit_fast<H>((const uint8_t *)R.pl[plane].ptr, R.pl[plane].stride, x0, y0, smvc & 15, smvr & 15, e.filter, pr);
-        fast = true;
-      }
+      // units whose fetch window leaves the reference take the same path with clamped row loads
+      mc_unit_fast<H>((const uint8_t *)R.pl[plane].ptr, R.pl[plane].stride, x0, y0, smvc & 15, smvr & 15, e.filter,
+                      !mc_inside(x0, y0, H, R.w[plane], R.h[plane]), R.w[plane], R.h[plane], pr);
+      fast = true;
     }
-    if (!fast) {  // frame edge (clamped fetches) or scaled reference: exact per-sample path
+    if (!fast) {  // scaled reference: exact per-sample path
 #pragma unroll
       for (int yy = 0; yy < H; yy++) pr[yy] = mc_row_slow(P, R, plane, e, mi_row, mi_col, x, y, yy, mvr, mvc);
     }
