@@ -40,7 +40,8 @@ class FrameHdr(C.Structure):
                 ("dst_slot", C.c_int32), ("ref", RefDesc * 3), ("sec", Section * SEC_COUNT),
                 ("lf_lim", C.c_uint8 * 64), ("lf_mblim", C.c_uint8 * 64),
                 ("frame_index", C.c_uint32), ("n_inter_px", C.c_uint32 * 3),
-                ("n_compound_px", C.c_uint32 * 3), ("reserved2", C.c_uint32 * 8)]
+                ("n_compound_px", C.c_uint32 * 3), ("n_txb_inter_size", C.c_uint32 * 4),
+                ("reserved2", C.c_uint32 * 4)]
 
 
 class Image(C.Structure):

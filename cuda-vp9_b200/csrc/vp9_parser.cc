@@ -1650,7 +1650,7 @@ void TileCtx::residual_and_record() {
           eobtotal += eob;
         }
         if (!inter) P->out_txb_intra_[plane].push_back(t);
-        else if (t.eob > 0) P->out_txb_inter_.push_back(t);
+        else if (t.eob > 0) P->out_txb_inter_[tx_size].push_back(t);
       }
   }
   if (inter && !mi->skip && !less8x8 && eobtotal == 0) mi->skip = 1;  // skip loopfilter
@@ -2023,7 +2023,12 @@ void Parser::pack() {
   };
   set(VP9B_SEC_BLOCKS, out_blocks_.data(), sizeof(vp9b_block), out_blocks_.size());
   set(VP9B_SEC_SUBMV, out_submv_.data(), sizeof(vp9b_submv), out_submv_.size());
-  set(VP9B_SEC_TXB_INTER, out_txb_inter_.data(), sizeof(vp9b_txb), out_txb_inter_.size());
+  out_txb_inter_all_.clear();
+  for (int i = 0; i < 4; i++) {
+    h.n_txb_inter_size[i] = (uint32_t)out_txb_inter_[i].size();
+    out_txb_inter_all_.insert(out_txb_inter_all_.end(), out_txb_inter_[i].begin(), out_txb_inter_[i].end());
+  }
+  set(VP9B_SEC_TXB_INTER, out_txb_inter_all_.data(), sizeof(vp9b_txb), out_txb_inter_all_.size());
   for (int p = 0; p < 3; p++)
     set(VP9B_SEC_TXB_INTRA_Y + p, out_txb_intra_[p].data(), sizeof(vp9b_txb), out_txb_intra_[p].size());
   set(VP9B_SEC_SB_INTRA, out_sb_intra_.data(), sizeof(vp9b_sbrange), out_sb_intra_.size());
@@ -2080,7 +2085,7 @@ int Parser::parse(const uint8_t *data, size_t size) {
   blocks_.reserve((size_t)mi_cols_ * mi_rows_ + 64);
   out_blocks_.clear();
   out_submv_.clear();
-  out_txb_inter_.clear();
+  for (int i = 0; i < 4; i++) out_txb_inter_[i].clear();
   for (int p = 0; p < 3; p++) out_txb_intra_[p].clear();
   n_coef_ = 0;
   out_sb_intra_.assign((size_t)3 * sb_cols_ * sb_rows_, vp9b_sbrange{ 0, 0 });

@@ -162,7 +162,8 @@ class Parser {
   // ---- per frame output
   std::vector<vp9b_block> out_blocks_;
   std::vector<vp9b_submv> out_submv_;
-  std::vector<vp9b_txb> out_txb_inter_;
+  std::vector<vp9b_txb> out_txb_inter_[4];  // by transform size (blocks of one size share a warp on the GPU)
+  std::vector<vp9b_txb> out_txb_inter_all_;
   std::vector<vp9b_txb> out_txb_intra_[3];
   std::vector<vp9b_sbrange> out_sb_intra_;  // [3][sb_rows*sb_cols]
   std::vector<int16_t> out_coef16_;

@@ -68,6 +68,7 @@ struct FrameParams {
   const vp9b_submv *submv;
   const vp9b_txb *txb_inter;
   int n_txb_inter;
+  int n_txb_size[4];   // TXB_INTER is grouped by transform size
   const vp9b_txb *txb_intra[3];
   const vp9b_sbrange *sb_intra;  // [3][nsb]
   const void *coef;
@@ -555,15 +556,105 @@ VP9B_DEV void warp_residual(const FrameParams &P, int *tbuf, const vp9b_txb &t, 
   warp_residual_at<Px, PT>(P, tbuf, t, dst, stride, lane);
 }
 
+// Inter residuals: the list is grouped by transform size (hdr.n_txb_inter_size), so one warp takes
+// 32/N blocks of size N at a time -- a block uses N lanes (lane l = row l, then column l).
+template <typename Px, typename PT, int N>
+VP9B_DEV void group_itx_add(int *tbuf, const FrameParams &P, int first, int count, int lane) {
+  constexpr int S = N + 1;
+  const int sub = lane / N, l = lane % N;
+  int *tb = tbuf + sub * (N * S);
+  const bool active = sub < count;
+  vp9b_txb t;
+  t.coef_off = 0; t.x4 = t.y4 = 0; t.eob = 0; t.tx = 0; t.aux = 0;
+  if (active) t = P.txb_inter[first + sub];
+  const int plane = (t.tx >> 4) & 3;
+  const int stride = P.dst[plane].stride;
+  Px *dst = (Px *)P.dst[plane].ptr + (size_t)t.y4 * 4 * stride + t.x4 * 4;
+  const int lossless = (N == 4) ? P.lossless : 0;
+  const int tx_type = lossless ? 0 : ((t.tx >> 2) & 3);
+  const int eob = t.eob;
+  for (int i = l; i < N * S; i += N) tb[i] = 0;
+  __syncwarp();
+  if (active) {
+    const int16_t *scan = d_scan + scan_offset(t.tx & 3, tx_type);
+    if (sizeof(Px) == 1) {
+      const int16_t *c = (const int16_t *)P.coef + t.coef_off;
+      for (int i = l; i < eob; i += N) {
+        const int pos = scan[i];
+        tb[(pos / N) * S + (pos % N)] = c[i];
+      }
+    } else {
+      const int32_t *c = (const int32_t *)P.coef + t.coef_off;
+      for (int i = l; i < eob; i += N) {
+        const int pos = scan[i];
+        tb[(pos / N) * S + (pos % N)] = c[i];
+      }
+    }
+  }
+  __syncwarp();
+  const int maxv = (1 << P.bd) - 1;
+  if (N == 4 && lossless) {  // vpx_iwht4x4_16_add_c (inv_txfm.c:18-66)
+    int o[4];
+    if (active) {
+      iwht4(tb[l * S + 0] >> 2, tb[l * S + 1] >> 2, tb[l * S + 2] >> 2, tb[l * S + 3] >> 2, o);
+      for (int j = 0; j < 4; j++) tb[l * S + j] = o[j];
+    }
+    __syncwarp();
+    if (active) {
+      iwht4(tb[0 * S + l], tb[1 * S + l], tb[2 * S + l], tb[3 * S + l], o);
+      for (int j = 0; j < 4; j++) dst[j * stride + l] = (Px)clampi((int)dst[j * stride + l] + o[j], 0, maxv);
+    }
+    __syncwarp();
+    return;
+  }
+  const bool row_adst = (N < 32) && (tx_type & 2), col_adst = (N < 32) && (tx_type & 1);
+  if (active) {  // rows: lane l transforms row l (all-zero rows stay zero)
+    int in[N], out[N];
+    int any = 0;
+#pragma unroll
+    for (int j = 0; j < N; j++) { in[j] = tb[l * S + j]; any |= in[j]; }
+    if (any) {
+      txfm1d<PT, N>(in, out, row_adst);
+#pragma unroll
+      for (int j = 0; j < N; j++) tb[l * S + j] = out[j];
+    }
+  }
+  __syncwarp();
+  constexpr int shift = (N == 4) ? 4 : (N == 8 ? 5 : 6);
+  if (active) {  // columns
+    int in[N], out[N];
+#pragma unroll
+    for (int j = 0; j < N; j++) in[j] = tb[j * S + l];
+    txfm1d<PT, N>(in, out, col_adst);
+#pragma unroll
+    for (int j = 0; j < N; j++) {
+      Px *p = dst + (size_t)j * stride + l;
+      *p = (Px)clampi((int)*p + ((out[j] + (1 << (shift - 1))) >> shift), 0, maxv);
+    }
+  }
+  __syncwarp();
+}
+
 constexpr int kResWarps = 4;
 template <typename Px, typename PT>
 __global__ void __launch_bounds__(kResWarps * 32) k_residual(const __grid_constant__ FrameParams P) {
   __shared__ int tbuf[kResWarps][32 * 33];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nwarps = gridDim.x * kResWarps;
-  for (int i = blockIdx.x * kResWarps + warp; i < P.n_txb_inter; i += nwarps) {
-    const vp9b_txb t = P.txb_inter[i];
-    warp_residual<Px, PT>(P, tbuf[warp], t, lane);
+  // warp tasks: ceil(n/8) groups of 4x4, ceil(n/4) of 8x8, ceil(n/2) of 16x16, n of 32x32
+  const int n4 = P.n_txb_size[0], n8 = P.n_txb_size[1], n16 = P.n_txb_size[2], n32 = P.n_txb_size[3];
+  const int t4 = (n4 + 7) >> 3, t8 = (n8 + 3) >> 2, t16 = (n16 + 1) >> 1;
+  const int total = t4 + t8 + t16 + n32;
+  // big transforms first: they are the long tasks
+  for (int i = blockIdx.x * kResWarps + warp; i < total; i += nwarps) {
+    int k = i;
+    if (k < n32) { group_itx_add<Px, PT, 32>(tbuf[warp], P, n4 + n8 + n16 + k, 1, lane); continue; }
+    k -= n32;
+    if (k < t16) { group_itx_add<Px, PT, 16>(tbuf[warp], P, n4 + n8 + 2 * k, min(2, n16 - 2 * k), lane); continue; }
+    k -= t16;
+    if (k < t8) { group_itx_add<Px, PT, 8>(tbuf[warp], P, n4 + 4 * k, min(4, n8 - 4 * k), lane); continue; }
+    k -= t8;
+    group_itx_add<Px, PT, 4>(tbuf[warp], P, 8 * k, min(8, n4 - 8 * k), lane);
   }
 }
 
@@ -1443,7 +1534,8 @@ static int launch_stages(vp9gpu_ctx *ctx, const FrameParams &P, const vp9b_frame
     }
     if (prof) cudaEventRecord(ctx->prof_ev[2], st);
     if (stop != 1 && P.n_txb_inter) {
-      const int blocks = std::min((P.n_txb_inter + kResWarps - 1) / kResWarps, ctx->num_sms * 8);
+      const int tasks = ((P.n_txb_size[0] + 7) >> 3) + ((P.n_txb_size[1] + 3) >> 2) + ((P.n_txb_size[2] + 1) >> 1) + P.n_txb_size[3];
+      const int blocks = std::min((tasks + kResWarps - 1) / kResWarps, ctx->num_sms * 8);
       k_residual<Px, PT><<<blocks, kResWarps * 32, 0, st>>>(P);
       ctx->launches++;
     }
@@ -1545,6 +1637,11 @@ static int submit_device(vp9gpu_ctx *ctx, const uint8_t *d_packed, const vp9b_fr
   P.submv = (const vp9b_submv *)(d_packed + h->sec[VP9B_SEC_SUBMV].offset);
   P.txb_inter = (const vp9b_txb *)(d_packed + h->sec[VP9B_SEC_TXB_INTER].offset);
   P.n_txb_inter = h->sec[VP9B_SEC_TXB_INTER].count;
+  for (int i = 0; i < 4; i++) P.n_txb_size[i] = (int)h->n_txb_inter_size[i];
+  if (h->n_txb_inter_size[0] + h->n_txb_inter_size[1] + h->n_txb_inter_size[2] + h->n_txb_inter_size[3] != (uint32_t)P.n_txb_inter) {
+    ctx->err = "inter transform block counts do not add up";
+    return VP9B_ERR_INVALID;
+  }
   for (int p = 0; p < 3; p++) P.txb_intra[p] = (const vp9b_txb *)(d_packed + h->sec[VP9B_SEC_TXB_INTRA_Y + p].offset);
   P.sb_intra = (const vp9b_sbrange *)(d_packed + h->sec[VP9B_SEC_SB_INTRA].offset);
   P.coef = d_packed + h->sec[VP9B_SEC_COEF].offset;

@@ -46,7 +46,8 @@ enum {
 enum {
   VP9B_SEC_BLOCKS = 0,   /* vp9b_block[]      every prediction block in decode order          */
   VP9B_SEC_SUBMV = 1,    /* vp9b_submv[]      MVs of sub-8x8 inter blocks                     */
-  VP9B_SEC_TXB_INTER = 2,/* vp9b_txb[]        inter residual transform blocks, eob > 0 only   */
+  VP9B_SEC_TXB_INTER = 2,/* vp9b_txb[]        inter residual transform blocks, eob > 0 only,
+                                              grouped by transform size (hdr.n_txb_inter_size) */
   VP9B_SEC_TXB_INTRA_Y = 3, /* vp9b_txb[]     intra transform blocks per plane, decode order  */
   VP9B_SEC_TXB_INTRA_U = 4,
   VP9B_SEC_TXB_INTRA_V = 5,
@@ -91,7 +92,8 @@ typedef struct vp9b_frame_hdr {
   uint32_t frame_index;          /* decode-order counter, informational */
   uint32_t n_inter_px[3];        /* predicted samples per plane (roofline accounting)   */
   uint32_t n_compound_px[3];
-  uint32_t reserved2[8];
+  uint32_t n_txb_inter_size[4];  /* TXB_INTER is ordered by transform size: counts of 4x4, 8x8, 16x16, 32x32 */
+  uint32_t reserved2[4];
 } vp9b_frame_hdr;
 
 typedef struct vp9b_block { /* 16 bytes. role of MODE_INFO fields in vp9_blockd.h:74-97 */
