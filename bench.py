@@ -47,42 +47,59 @@ def load_clip(name):
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks + throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    """SM clock + throttle reasons DURING the timed region (B200_PROFILING.md), sampled through NVML
+    every few milliseconds (nvidia-smi's own loop is too slow to start for sub-second regions)."""
+
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
     def __init__(self, index):
         super().__init__(daemon=True)
-        self.index, self.rows, self.stop_flag = index, [], False
-        self.proc = None
+        self.index, self.sm, self.reasons, self.max_mhz, self.stop_flag = index, [], set(), None, False
+        self.nv = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = int(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.nv = None
+
+    def sample(self):
+        nv = self.nv
+        self.sm.append(int(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+        try:
+            mask = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+        except Exception:
+            mask = 0
+        for bit, name in self.REASONS.items():
+            if mask & bit:
+                self.reasons.add(name)
 
     def run(self):
-        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
-        try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            for line in self.proc.stdout:
-                self.rows.append([x.strip() for x in line.split(",")])
-                if self.stop_flag:
-                    break
-        except Exception:
-            pass
+        if self.nv is None:
+            return
+        while not self.stop_flag:
+            try:
+                self.sample()
+            except Exception:
+                break
+            time.sleep(0.004)
 
     def finish(self):
         self.stop_flag = True
-        if self.proc:
-            self.proc.terminate()
         self.join(timeout=2)
-        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
-        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
-        reasons = set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
-            for i, n in enumerate(names):
-                if len(r) > 2 + i and r[2 + i].lower().startswith("active"):
-                    reasons.add(n)
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        if self.nv is None:   # last resort: one nvidia-smi query
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=clocks.sm,clocks.max.sm",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=10).stdout
+                a, b = [int(x) for x in out.strip().split(",")]
+                self.sm, self.max_mhz = [a], b
+            except Exception:
+                pass
+        sm = sorted(self.sm)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(sm)}
 
 
 def dist_setup(args):
@@ -398,7 +415,7 @@ def cpu_baseline(chunks, budget_s=12.0):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--streams", type=int, default=32, help="independent decoder contexts per GPU")
