@@ -849,21 +849,43 @@ __global__ void __launch_bounds__(kWaveWarps * 32) k_intra(const __grid_constant
   constexpr int TS = G::kTS, M = G::kMargin;
   Px *T0 = tile + TS + M;  // sample (0,0) of the superblock; row -1 / column -1 hold the neighbours
   bool left_in_smem = false;
-  for (int sbc = 0; sbc < P.sb_cols; sbc++) {
-    const vp9b_sbrange rg = rgs[sbc];
-    if (!rg.count) {
-      // no intra block here: these samples were final after the inter stages, and everything to
-      // the left in this row is done (program order), so just publish
-      if (lane == 0) st_release(prog + sbr, P.prog_base + (uint32_t)(sbc + 1));
+  int published = 0;   // superblocks of this row already released to the row below
+  // Superblocks without intra blocks are final after the inter stages: walk only the non-empty
+  // ones (32 ranges at a time, one per lane) and release everything skipped in one store.
+  for (int c0 = 0; c0 < P.sb_cols; c0 += 32) {
+    vp9b_sbrange mine;
+    mine.start = 0; mine.count = 0;
+    if (c0 + lane < P.sb_cols) mine = rgs[c0 + lane];
+    uint32_t todo = __ballot_sync(0xffffffffu, mine.count != 0);
+    while (todo) {
+    const int src = __ffs(todo) - 1;
+    todo &= todo - 1;
+    const int sbc = c0 + src;
+    vp9b_sbrange rg;
+    rg.start = __shfl_sync(0xffffffffu, mine.start, src);
+    rg.count = __shfl_sync(0xffffffffu, mine.count, src);
+    if (sbc > published) {
+      // everything to the left is done (program order); nothing of it is in flight
+      if (lane == 0) st_release(prog + sbr, P.prog_base + (uint32_t)sbc);
       left_in_smem = false;
-      continue;
     }
     Px *g = gplane + (size_t)(sbr * n) * stride + sbc * n;
     // interior rows can be fetched before the dependency wait (nobody else writes them)
-    const int vpr = n >> 3;
-    for (int i = lane; i < n * vpr; i += 32) {
-      const int r = i / vpr, v = i % vpr;
-      *(Vec *)(T0 + r * TS + v * 8) = __ldcg((const Vec *)(g + (size_t)r * stride + v * 8));
+    const int vpr = n >> 3, vsh = n == 64 ? 3 : 2, nvec = n * vpr;
+    {
+      // all loads of the tile are issued before the first one is consumed (one L2 round trip)
+      constexpr int kPer = 64 * 8 / 32;
+      Vec tmp[kPer];
+#pragma unroll
+      for (int k = 0; k < kPer; k++) {
+        const int i = lane + 32 * k;
+        if (i < nvec) tmp[k] = __ldcg((const Vec *)(g + (size_t)(i >> vsh) * stride + (i & (vpr - 1)) * 8));
+      }
+#pragma unroll
+      for (int k = 0; k < kPer; k++) {
+        const int i = lane + 32 * k;
+        if (i < nvec) *(Vec *)(T0 + (i >> vsh) * TS + (i & (vpr - 1)) * 8) = tmp[k];
+      }
     }
     if (sbc > 0 && !left_in_smem)
       for (int r = lane; r < n; r += 32) T0[r * TS - 1] = __ldcg((const Px *)(g + (size_t)r * stride - 1));
@@ -885,19 +907,18 @@ __global__ void __launch_bounds__(kWaveWarps * 32) k_intra(const __grid_constant
     }
     __syncwarp();
     // write the superblock back and keep its right-most column as the next left neighbour
-    for (int i = lane; i < n * vpr; i += 32) {
-      const int r = i / vpr, v = i % vpr;
-      __stcg((Vec *)(g + (size_t)r * stride + v * 8), *(const Vec *)(T0 + r * TS + v * 8));
-    }
+#pragma unroll 4
+    for (int i = lane; i < nvec; i += 32)
+      __stcg((Vec *)(g + (size_t)(i >> vsh) * stride + (i & (vpr - 1)) * 8), *(const Vec *)(T0 + (i >> vsh) * TS + (i & (vpr - 1)) * 8));
     __syncwarp();
     for (int r = lane; r < n; r += 32) T0[r * TS - 1] = T0[r * TS + n - 1];
     left_in_smem = true;
     __syncwarp();
-    if (lane == 0) {
-      __threadfence();
-      st_release(prog + sbr, P.prog_base + (uint32_t)(sbc + 1));
+    if (lane == 0) st_release(prog + sbr, P.prog_base + (uint32_t)(sbc + 1));
+    published = sbc + 1;
     }
   }
+  if (published < P.sb_cols && lane == 0) st_release(prog + sbr, P.prog_base + (uint32_t)P.sb_cols);
 }
 
 // ------------------------------------------------------------------------------------------
