@@ -30,7 +30,7 @@ os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-CLIPS = {"1440p": "bench_1440p", "4k": "bench_4k"}
+CLIPS = {"1440p": "bench_1440p", "4k": "bench_4k", "hbd1080": "bench_hbd1080"}
 
 
 def clip_file(name):
@@ -155,8 +155,9 @@ def run_reference(args, rank, world):
 
 
 def workload_name(args, w, h):
-    return ("synthetic %dx%d 8-bit 4:2:0 VP9 clip (4 tile columns, alt-ref + compound, loop filter on; stand-in for "
-            "Bravia.1440.ivf which is absent from the reference checkout)" % (w, h))
+    bits = {"hbd1080": "10-bit profile 2"}.get(args.clip, "8-bit")
+    return ("synthetic %dx%d %s 4:2:0 VP9 clip (4 tile columns, alt-ref + compound, loop filter on; stand-in for "
+            "Bravia.1440.ivf / FoodMarket2.ivf which are absent from the reference checkout)" % (w, h, bits))
 
 
 # --------------------------------------------------------------------------------------------

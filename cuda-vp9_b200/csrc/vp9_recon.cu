@@ -447,7 +447,7 @@ VP9B_DEV void inter_pred_u8_body(const FrameParams &P, int plane, int bx_, int b
 
 // All three planes in one launch: a flat grid of CTAs, luma tiles (32x128 samples) first, then
 // the two chroma planes (4:2:0: 32x64-sample tiles of 4x4 units; 4:4:4: same as luma).
-__global__ void __launch_bounds__(128) k_inter_pred_u8(const __grid_constant__ FrameParams P, int ncta_y, int ncta_c,
+__global__ void __launch_bounds__(128, 8) k_inter_pred_u8(const __grid_constant__ FrameParams P, int ncta_y, int ncta_c,
                                                        int gx_y, int gx_c) {
   int b = blockIdx.x, plane = 0, gx = gx_y;
   if (b >= ncta_y) {

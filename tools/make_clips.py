@@ -68,6 +68,10 @@ BENCH = {
     "bench_1440p": dict(w=2560, h=1440, n=24, cpu_used=2, lag=16, auto_alt_ref=1, two_pass=True, bitrate=6000,
                         end_usage=0, tile_cols_log2=2, arnr_maxframes=7, arnr_strength=5, detail=0.02,
                         temporal_noise=3.5, noise_corner=False, threads=8, force_lf=True),
+    # BASELINE.json configs[4]: 1080p profile 2 (10-bit) -- highbd convolve / idct / lpf
+    "bench_hbd1080": dict(w=1920, h=1080, n=16, bit_depth=10, cpu_used=3, lag=16, auto_alt_ref=1, two_pass=True,
+                          bitrate=5000, end_usage=0, tile_cols_log2=2, arnr_maxframes=7, arnr_strength=5, detail=0.02,
+                          temporal_noise=3.5, noise_corner=False, threads=8, force_lf=True),
     "bench_4k": dict(w=3840, h=2160, n=20, cpu_used=2, lag=16, auto_alt_ref=1, two_pass=True, bitrate=12000,
                      end_usage=0, tile_cols_log2=2, arnr_maxframes=7, arnr_strength=5, detail=0.02,
                      temporal_noise=3.5, noise_corner=False, threads=8, force_lf=True),
