@@ -156,9 +156,8 @@ VP9B_DEV PredPos pred_position(const FrameParams &P, const RefGeom &R, int plane
   return p;
 }
 
-// Generic (any block size / scaling / bit depth) per-sample predictor.  Used for scaled
-// references, high bit depth and frame-edge tiles; the common 8-bit unscaled case goes through
-// k_inter_pred_tile below.
+// Generic (any block size / scaling / bit depth) per-sample predictor: the exact path for scaled
+// references (x_step_q4 != 16); unscaled prediction goes through the 4 x H unit kernels below.
 template <typename Px>
 VP9B_DEV int predict_sample(const FrameParams &P, const RefGeom &R, int plane, const PredPos &pp, int dx, int dy,
                             int filter) {
@@ -183,46 +182,6 @@ VP9B_DEV int predict_sample(const FrameParams &P, const RefGeom &R, int plane, c
     acc += s * fy[j];
   }
   return clampi((acc + 64) >> 7, 0, maxv);
-}
-
-template <typename Px>
-__global__ void k_inter_pred_generic(const __grid_constant__ FrameParams P, int plane) {
-  const int ss_x = plane ? P.ss_x : 0, ss_y = plane ? P.ss_y : 0;
-  const int pw = (P.mi_cols * 8) >> ss_x, ph = (P.mi_rows * 8) >> ss_y;
-  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
-  if (x >= pw || y >= ph) return;
-  const int mi_col = (x << ss_x) >> 3, mi_row = (y << ss_y) >> 3;
-  const MiEntry e = P.mi[(size_t)mi_row * P.mi_cols + mi_col];
-  if (!e.ref0) return;
-  const int bw8 = d_bw8[e.bsize], bh8 = d_bh8[e.bsize];
-  const int mi_col0 = mi_col & ~(bw8 - 1), mi_row0 = mi_row & ~(bh8 - 1);
-  // prediction unit inside the block: whole block, or one 4x4 for sub-8x8 blocks
-  int xoff = 0, yoff = 0, k = 0;
-  const int bx = x - ((mi_col0 * 8) >> ss_x), by = y - ((mi_row0 * 8) >> ss_y);
-  const bool sub8 = e.bsize < 3;
-  if (sub8) {
-    xoff = bx & ~3;
-    yoff = by & ~3;
-    k = (yoff >> 2) * 2 + (xoff >> 2);  // only meaningful for unsubsampled planes
-  }
-  int val = 0;
-#pragma unroll 1
-  for (int r = 0; r < (e.ref1 ? 2 : 1); r++) {
-    const RefGeom &R = P.ref[(r ? e.ref1 : e.ref0) - 1];
-    int mvr, mvc;
-    if (sub8) {
-      const vp9b_submv &s = P.submv[e.aux];
-      if (ss_x && ss_y) { mvr = s.chroma[r][0]; mvc = s.chroma[r][1]; }
-      else { mvr = s.luma[k][r][0]; mvc = s.luma[k][r][1]; }
-    } else {
-      mvr = e.mv[r][0];
-      mvc = e.mv[r][1];
-    }
-    const PredPos pp = pred_position(P, R, plane, mi_row0, mi_col0, bw8, bh8, xoff, yoff, mvr, mvc);
-    const int v = predict_sample<Px>(P, R, plane, pp, bx - xoff, by - yoff, e.filter);
-    val = r ? ((val + v + 1) >> 1) : v;
-  }
-  ((Px *)P.dst[plane].ptr)[(size_t)y * P.dst[plane].stride + x] = (Px)val;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -459,6 +418,219 @@ __global__ void __launch_bounds__(128, 8) k_inter_pred_u8(const __grid_constant_
   // one call site per unit height keeps the kernel inside the instruction cache
   if (plane && P.ss_x) inter_pred_u8_body<4>(P, plane, b % gx, b / gx);
   else inter_pred_u8_body<8>(P, plane, b % gx, b / gx);
+}
+
+// ------------------------------------------------------------------------------------------
+// stage 1 fast path, high bit depth (vpx_highbd_convolve8*, vpx_convolve.c:292-535): the same
+// 4 x H units on u16 samples.  Reference rows are fetched as aligned 32-bit words (two samples),
+// the window is normalised to an even start with one variable funnel shift per word, and the
+// 8-tap filters run as four DP2A (2 x u16 samples times 2 x s8 taps) per output.  The vertical
+// pass pairs rows with PRMT so that it is DP2A too.
+VP9B_DEV int dp2a_lo(uint32_t a, uint32_t b, int c) {
+  int d;
+  asm("dp2a.lo.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+  return d;
+}
+VP9B_DEV int dp2a_hi(uint32_t a, uint32_t b, int c) {
+  int d;
+  asm("dp2a.hi.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+  return d;
+}
+VP9B_DEV uint32_t avg_u16x2(uint32_t a, uint32_t b) {  // per half (a + b + 1) >> 1
+  return (a | b) - (((a ^ b) >> 1) & 0x7fff7fffu);
+}
+struct Row6 { uint32_t w[6]; };
+
+// 12 samples of reference row y starting at (even, possibly negative) column xa, positions
+// clamped to the reference crop size (highbd build_mc_border, vp9_decodeframe.c:469-504)
+__device__ __noinline__ Row6 mc16_load_row_clamped(const uint16_t *__restrict__ ref, int rstride, int y, int xa, int rw,
+                                                   int rh) {
+  const uint16_t *row = ref + (ptrdiff_t)clampi(y, 0, rh - 1) * rstride;
+  Row6 r;
+#pragma unroll
+  for (int j = 0; j < 6; j++) {
+    const int x = xa + 2 * j;
+    const uint32_t lo = __ldg(row + clampi(x, 0, rw - 1)), hi = __ldg(row + clampi(x + 1, 0, rw - 1));
+    r.w[j] = lo | (hi << 16);
+  }
+  return r;
+}
+
+template <int H>
+VP9B_DEV void mc_unit_fast16(const uint16_t *__restrict__ ref, int rstride, int x0, int y0, int sx, int sy, int filter,
+                             bool edge, int rw, int rh, int maxv, uint2 *out) {
+  constexpr int R = H + 7;  // rows y0-3 .. y0+H+3
+  const uint32_t txl = d_taps4[(filter * 16 + sx) * 2], txh = d_taps4[(filter * 16 + sx) * 2 + 1];
+  const uint32_t tyl = d_taps4[(filter * 16 + sy) * 2], tyh = d_taps4[(filter * 16 + sy) * 2 + 1];
+  const int xs = x0 - 3, par = xs & 1, xa = xs - par;
+  const uint16_t *p = ref + (ptrdiff_t)(y0 - 3) * rstride + xa;
+  uint2 im[R];
+#pragma unroll
+  for (int r = 0; r < R; r++) {
+    uint2 v = make_uint2(0, 0);
+    if (sy || (r >= 3 && r < 3 + H)) {
+      uint32_t w[6];
+      if (!edge) {
+#pragma unroll
+        for (int i = 0; i < 6; i++) w[i] = __ldg((const uint32_t *)p + i);
+      } else {
+        const Row6 t = mc16_load_row_clamped(ref, rstride, y0 - 3 + r, xa, rw, rh);
+#pragma unroll
+        for (int i = 0; i < 6; i++) w[i] = t.w[i];
+      }
+      // n[i] = samples (xs + 2i, xs + 2i + 1)
+      uint32_t n[6];
+#pragma unroll
+      for (int i = 0; i < 5; i++) n[i] = __funnelshift_r(w[i], w[i + 1], par * 16);
+      n[5] = w[5] >> (par * 16);
+      if (sx) {
+        uint32_t o[5];  // o[i] = samples (xs + 2i + 1, xs + 2i + 2)
+#pragma unroll
+        for (int i = 0; i < 5; i++) o[i] = __funnelshift_r(n[i], n[i + 1], 16);
+        int s[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          const uint32_t *a = (j & 1) ? o : n;
+          const int b = j >> 1;
+          int acc = dp2a_lo(a[b], txl, 64);
+          acc = dp2a_hi(a[b + 1], txl, acc);
+          acc = dp2a_lo(a[b + 2], txh, acc);
+          acc = dp2a_hi(a[b + 3], txh, acc);
+          s[j] = clampi(acc >> 7, 0, maxv);
+        }
+        v = make_uint2((uint32_t)s[0] | ((uint32_t)s[1] << 16), (uint32_t)s[2] | ((uint32_t)s[3] << 16));
+      } else {
+        v = make_uint2(__funnelshift_r(n[1], n[2], 16), __funnelshift_r(n[2], n[3], 16));  // samples x0 .. x0+3
+      }
+    }
+    im[r] = v;
+    p += rstride;
+  }
+  if (sy) {
+#pragma unroll
+    for (int y = 0; y < H; y++) {
+      int s[4];
+#pragma unroll
+      for (int c = 0; c < 4; c++) {
+        const uint32_t sel = (c & 1) ? 0x7632u : 0x5410u;
+        uint32_t pr[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+          const uint2 a = im[y + 2 * k], b = im[y + 2 * k + 1];
+          pr[k] = __byte_perm(c < 2 ? a.x : a.y, c < 2 ? b.x : b.y, sel);
+        }
+        int acc = dp2a_lo(pr[0], tyl, 64);
+        acc = dp2a_hi(pr[1], tyl, acc);
+        acc = dp2a_lo(pr[2], tyh, acc);
+        acc = dp2a_hi(pr[3], tyh, acc);
+        s[c] = clampi(acc >> 7, 0, maxv);
+      }
+      out[y] = make_uint2((uint32_t)s[0] | ((uint32_t)s[1] << 16), (uint32_t)s[2] | ((uint32_t)s[3] << 16));
+    }
+  } else {
+#pragma unroll
+    for (int y = 0; y < H; y++) out[y] = im[y + 3];
+  }
+}
+
+__device__ __noinline__ uint2 mc16_row_slow(const FrameParams &P, const RefGeom &R, int plane, const MiEntry &e,
+                                            int mi_row, int mi_col, int x, int y, int yy, int mvr, int mvc) {
+  const int ss_x = plane ? P.ss_x : 0, ss_y = plane ? P.ss_y : 0;
+  const bool sub8 = e.bsize < 3;
+  const int bw8 = d_bw8[e.bsize], bh8 = d_bh8[e.bsize];
+  const int mi_col0 = mi_col & ~(bw8 - 1), mi_row0 = mi_row & ~(bh8 - 1);
+  const int bx = x - ((mi_col0 * 8) >> ss_x), by = y - ((mi_row0 * 8) >> ss_y);
+  const int xoff = sub8 ? (bx & ~3) : 0, yoff = sub8 ? (by & ~3) : 0;
+  const PredPos pp = pred_position(P, R, plane, mi_row0, mi_col0, bw8, bh8, xoff, yoff, mvr, mvc);
+  uint32_t s[4];
+#pragma unroll 1
+  for (int xx = 0; xx < 4; xx++)
+    s[xx] = (uint32_t)predict_sample<uint16_t>(P, R, plane, pp, bx - xoff + xx, by - yoff + yy, e.filter);
+  return make_uint2(s[0] | (s[1] << 16), s[2] | (s[3] << 16));
+}
+
+template <int H>
+VP9B_DEV void mc_unit16(const FrameParams &P, int plane, const MiEntry &e, int mi_row, int mi_col, int x, int y,
+                        uint2 *out) {
+  const int ss_x = plane ? P.ss_x : 0, ss_y = plane ? P.ss_y : 0;
+  const bool sub8 = e.bsize < 3;
+  const int maxv = (1 << P.bd) - 1;
+#pragma unroll 1
+  for (int r = 0; r < (e.ref1 ? 2 : 1); r++) {
+    const RefGeom &R = P.ref[(r ? e.ref1 : e.ref0) - 1];
+    int mvr, mvc;
+    if (sub8) {
+      const vp9b_submv &s = P.submv[e.aux];
+      if (ss_x && ss_y) { mvr = s.chroma[r][0]; mvc = s.chroma[r][1]; }
+      else {
+        const int k = (((y << ss_y) & 7) >> 2) * 2 + (((x << ss_x) & 7) >> 2);
+        mvr = s.luma[k][r][0]; mvc = s.luma[k][r][1];
+      }
+    } else {
+      mvr = e.mv[r][0];
+      mvc = e.mv[r][1];
+    }
+    uint2 pr[H];
+    if (R.x_step_q4 == 16 && R.y_step_q4 == 16) {
+      const int smvr = mvr * (1 << (1 - ss_y)), smvc = mvc * (1 << (1 - ss_x));
+      const int x0 = x + (smvc >> 4), y0 = y + (smvr >> 4);
+      // fetch window (aligned word reads included): columns x0-4 .. x0+8, rows y0-3 .. y0+H+3
+      const bool inside = x0 - 4 >= 0 && y0 - 3 >= 0 && x0 + 9 <= R.w[plane] && y0 + H + 4 <= R.h[plane];
+      mc_unit_fast16<H>((const uint16_t *)R.pl[plane].ptr, R.pl[plane].stride, x0, y0, smvc & 15, smvr & 15, e.filter,
+                        !inside, R.w[plane], R.h[plane], maxv, pr);
+    } else {  // scaled reference: exact per-sample path
+#pragma unroll
+      for (int yy = 0; yy < H; yy++) pr[yy] = mc16_row_slow(P, R, plane, e, mi_row, mi_col, x, y, yy, mvr, mvc);
+    }
+    if (r == 0) {
+#pragma unroll
+      for (int i = 0; i < H; i++) out[i] = pr[i];
+    } else {
+#pragma unroll
+      for (int i = 0; i < H; i++) out[i] = make_uint2(avg_u16x2(out[i].x, pr[i].x), avg_u16x2(out[i].y, pr[i].y));
+    }
+  }
+}
+
+template <int H>
+VP9B_DEV void inter_pred_u16_body(const FrameParams &P, int plane, int bx_, int by_) {
+  const int ss_x = plane ? P.ss_x : 0, ss_y = plane ? P.ss_y : 0;
+  const int pw = (P.mi_cols * 8) >> ss_x, ph = (P.mi_rows * 8) >> ss_y;
+  const int x = (bx_ * 8 + (threadIdx.x & 7)) * 4;
+  const int y = (by_ * 16 + (threadIdx.x >> 3)) * H;
+  if (x >= pw || y >= ph) return;
+  const int dstride = P.dst[plane].stride;
+  uint16_t *dst = (uint16_t *)P.dst[plane].ptr + (size_t)y * dstride + x;
+  const int mi_col = (x << ss_x) >> 3, mi_row = (y << ss_y) >> 3;
+  const MiEntry e = P.mi[(size_t)mi_row * P.mi_cols + mi_col];
+  if (!e.ref0) return;
+  if (H == 8 && e.bsize < 3) {  // sub-8x8 block in an unsubsampled plane: two 4x4 units
+#pragma unroll 1
+    for (int half = 0; half < 2; half++) {
+      uint2 o[4];
+      mc_unit16<4>(P, plane, e, mi_row, mi_col, x, y + 4 * half, o);
+#pragma unroll
+      for (int i = 0; i < 4; i++) *(uint2 *)(dst + (size_t)(i + 4 * half) * dstride) = o[i];
+    }
+    return;
+  }
+  uint2 o[H];
+  mc_unit16<H>(P, plane, e, mi_row, mi_col, x, y, o);
+#pragma unroll
+  for (int i = 0; i < H; i++) *(uint2 *)(dst + (size_t)i * dstride) = o[i];
+}
+
+__global__ void __launch_bounds__(128, 4) k_inter_pred_u16(const __grid_constant__ FrameParams P, int ncta_y, int ncta_c,
+                                                          int gx_y, int gx_c) {
+  int b = blockIdx.x, plane = 0, gx = gx_y;
+  if (b >= ncta_y) {
+    b -= ncta_y;
+    plane = 1 + b / ncta_c;
+    b %= ncta_c;
+    gx = gx_c;
+  }
+  if (plane && P.ss_x) inter_pred_u16_body<4>(P, plane, b % gx, b / gx);
+  else inter_pred_u16_body<8>(P, plane, b % gx, b / gx);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1536,22 +1708,15 @@ static int launch_stages(vp9gpu_ctx *ctx, const FrameParams &P, const vp9b_frame
       ctx->launches++;
     }
     if (prof) cudaEventRecord(ctx->prof_ev[1], st);
-    if (sizeof(Px) == 1) {
+    {
       const int pwy = P.mi_cols * 8, phy = P.mi_rows * 8;
       const int pwc = pwy >> P.ss_x, phc = phy >> P.ss_y;
       const int gx_y = (pwy + 31) / 32, gy_y = (phy + 127) / 128;
       const int gx_c = (pwc + 31) / 32, gy_c = P.ss_x ? (phc + 63) / 64 : (phc + 127) / 128;
       const int ncta_y = gx_y * gy_y, ncta_c = gx_c * gy_c;
-      k_inter_pred_u8<<<ncta_y + 2 * ncta_c, 128, 0, st>>>(P, ncta_y, ncta_c, gx_y, gx_c);
+      if (sizeof(Px) == 1) k_inter_pred_u8<<<ncta_y + 2 * ncta_c, 128, 0, st>>>(P, ncta_y, ncta_c, gx_y, gx_c);
+      else k_inter_pred_u16<<<ncta_y + 2 * ncta_c, 128, 0, st>>>(P, ncta_y, ncta_c, gx_y, gx_c);
       ctx->launches++;
-    } else {
-      for (int p = 0; p < 3; p++) {
-        const int sx = p ? P.ss_x : 0, sy = p ? P.ss_y : 0;
-        const int pw = (P.mi_cols * 8) >> sx, ph = (P.mi_rows * 8) >> sy;
-        dim3 blk(32, 8), grd((pw + 31) / 32, (ph + 7) / 8);
-        k_inter_pred_generic<Px><<<grd, blk, 0, st>>>(P, p);
-        ctx->launches++;
-      }
     }
     if (prof) cudaEventRecord(ctx->prof_ev[2], st);
     if (stop != 1 && P.n_txb_inter) {

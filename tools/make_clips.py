@@ -58,6 +58,9 @@ PARITY = {
                        show_existing_at={4: 0}),
     # show_existing_frame of other reference slots between ordinary frames
     "show_exist": dict(w=352, h=288, n=7, deadline=1, cpu_used=5, bitrate=300, show_existing_at={2: 1, 5: 2}),
+    # scaled references at high bit depth (per-sample path of the u16 kernel)
+    "scaled_hbd": dict(w=256, h=176, n=8, bit_depth=10, cpu_used=5, deadline=1, bitrate=250,
+                       scale_at={2: (3, 1), 4: (1, 2), 6: (0, 0)}, temporal_noise=2.0),
     "scaled_rt": dict(w=416, h=240, n=10, cpu_used=6, deadline=1, bitrate=300,
                       scale_at={2: (3, 1), 5: (2, 3), 8: (0, 0)}, temporal_noise=2.0),
 }
