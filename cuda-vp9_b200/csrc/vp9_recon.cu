@@ -1181,8 +1181,8 @@ struct LfPlane {
 
 // optional phase timing of one loop-filter row (compile with -DVP9B_LF_TIMING; tools read it back
 // through vp9gpu_debug_read)
-__device__ unsigned long long d_lf_dbg[64 * 8];
 #ifdef VP9B_LF_TIMING
+__device__ unsigned long long d_lf_dbg[64 * 8];
 VP9B_DEV unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
 #define LFT(k) if (tid == 0 && (sbr == 2 || sbr == 3) && sbc < 32) d_lf_dbg[((sbr - 2) * 32 + sbc) * 8 + (k)] = gtime();
 #else
@@ -1637,7 +1637,9 @@ extern "C" int vp9gpu_get_stage_ms(vp9gpu_ctx *ctx, float ms[8], int reset) {
   if (reset) memset(ctx->stage_ms, 0, sizeof(ctx->stage_ms));
   return 0;
 }
+#ifdef VP9B_LF_TIMING
 extern "C" int vp9gpu_debug_read(unsigned long long *out) { return (int)cudaMemcpyFromSymbol(out, vp9b::d_lf_dbg, sizeof(unsigned long long) * 512); }
+#endif
 extern "C" int vp9gpu_sync(vp9gpu_ctx *ctx) {
   if (!ctx) return VP9B_ERR_INVALID;
   CK(cudaStreamSynchronize(ctx->stream));
@@ -1776,6 +1778,28 @@ static int submit_device(vp9gpu_ctx *ctx, const uint8_t *d_packed, const vp9b_fr
     ctx->err = "only 4:2:0 / 4:4:4 supported";
     return VP9B_ERR_UNSUP;
   }
+  {
+    // the header is the only part of a packed buffer the host can check cheaply: every section
+    // must lie inside the buffer and the per-superblock tables must have the frame's geometry
+    static const uint32_t elem[VP9B_SEC_COUNT] = { sizeof(vp9b_block), sizeof(vp9b_submv), sizeof(vp9b_txb), sizeof(vp9b_txb),
+                                                   sizeof(vp9b_txb), sizeof(vp9b_txb), sizeof(vp9b_sbrange), 0,
+                                                   sizeof(vp9b_lfm), 0, 0, 0 };
+    const uint32_t coef_elem = h->bit_depth > 8 ? 4 : 2;
+    for (int i = 0; i < VP9B_SEC_COUNT; i++) {
+      const uint64_t bytes = (uint64_t)h->sec[i].count * (i == VP9B_SEC_COEF ? coef_elem : elem[i]);
+      if ((h->sec[i].offset & 15) || (uint64_t)h->sec[i].offset + bytes > h->total_bytes) {
+        ctx->err = "packed buffer: section out of bounds";
+        return VP9B_ERR_INVALID;
+      }
+    }
+    const uint32_t nsb = h->sb_cols * h->sb_rows;
+    if (h->sb_cols != (h->mi_cols + 7) / 8 || h->sb_rows != (h->mi_rows + 7) / 8 || h->mi_cols != (h->width + 7) / 8 ||
+        h->mi_rows != (h->height + 7) / 8 || h->sec[VP9B_SEC_SB_INTRA].count != 3 * nsb ||
+        (h->lf_level && h->sec[VP9B_SEC_LFM].count != nsb) || (h->bit_depth != 8 && h->bit_depth != 10 && h->bit_depth != 12)) {
+      ctx->err = "packed buffer: inconsistent frame geometry";
+      return VP9B_ERR_INVALID;
+    }
+  }
   CK(cudaSetDevice(ctx->device));
   int e = 0;
   if (!ctx->slot[h->dst_slot].base) {
@@ -1833,7 +1857,6 @@ static int submit_device(vp9gpu_ctx *ctx, const uint8_t *d_packed, const vp9b_fr
   P.coef = d_packed + h->sec[VP9B_SEC_COEF].offset;
   P.lfm = (const vp9b_lfm *)(d_packed + h->sec[VP9B_SEC_LFM].offset);
   P.mi = ctx->d_mi;
-  const int nsb = h->sb_cols * h->sb_rows;
   // progress counters: [0, 3*1024) intra (plane, row), [3072, 4096) loop filter.  Values are
   // prog_base + count with prog_base advancing by 2048 per frame; cleared only when it wraps.
   if (h->sb_rows > 1024 || h->sb_cols >= 2048) { ctx->err = "frame too large"; return VP9B_ERR_UNSUP; }

@@ -77,3 +77,36 @@ def test_gpu_launches_counted():
         d.decode(ch)
         d.get_frame()
     assert d.gpu_launch_count() > len(chunks)
+
+
+@pytest.mark.gpu
+def test_gpu_rejects_corrupt_packed_buffers():
+    """vp9gpu_frame_submit checks what it can on the host and returns an error instead of
+    launching on a buffer whose sections or geometry are inconsistent."""
+    _, _, chunks = vb.ivf_read(clip_path("odd_rt"))
+    parser = vb.HostParser()
+    packed, _ = parser.parse(vb.parse_superframe(chunks[0])[0])
+    hdr_size = C.sizeof(vb.FrameHdr)
+    gpu = vb.GpuRecon(0)
+
+    def mutated(fn):
+        h = vb.FrameHdr.from_buffer_copy(packed[:hdr_size])
+        fn(h)
+        return bytes(h) + packed[hdr_size:]
+
+    def bad_magic(h): h.magic = 0
+    def bad_section(h): h.sec[3].offset = h.total_bytes   # TXB_INTRA_Y is not empty on a key frame
+    def bad_count(h): h.sec[7].count = 0x7fffffff
+    def bad_geometry(h): h.sb_cols += 1
+    def bad_slot(h): h.dst_slot = 99
+    def bad_depth(h): h.bit_depth = 9
+
+    for fn in (bad_magic, bad_section, bad_count, bad_geometry, bad_slot, bad_depth):
+        with pytest.raises(vb.VP9BError):
+            gpu.submit(mutated(fn))
+    with pytest.raises(vb.VP9BError):
+        gpu.submit(packed[:hdr_size - 8])
+    gpu.submit(packed)          # the context is still usable afterwards
+    gpu.sync()
+    gpu.close()
+    parser.close()
