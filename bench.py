@@ -309,7 +309,7 @@ def run_ours(args, rank, world, local):
                         for k, v in cand.items()}}
 
     # ---- e2e: compressed chunks in host memory -> frames in host memory, one thread per stream
-    RING = 3
+    RING = 6
     res = [0] * E
     t_marks = {}
     ready_bar = threading.Barrier(E + 1)
@@ -320,6 +320,7 @@ def run_ours(args, rank, world, local):
         # decoder + pinned output ring are created once (allocation is not part of the steady state)
         d = vb.Decoder(local)
         ring = [vb.PinnedFrame(w, h, hdrs[0].bit_depth, hdrs[0].ss_x, hdrs[0].ss_y) for _ in range(RING)]
+        tickets = [0] * RING
 
         def run(passes):
             n = 0
@@ -327,11 +328,16 @@ def run_ours(args, rank, world, local):
                 # a new pass restarts at the key frame, so the same decoder instance can be reused
                 for ch in chunks:
                     d.decode(ch)                            # host parse + H2D + kernels (async)
-                    if d.get_frame_into(ring[n % RING]):    # D2H of the shown frame into pinned memory (async)
+                    k = n % RING
+                    if tickets[k]:
+                        d.wait(tickets[k])                  # the frame that used this pinned buffer RING frames ago
+                        tickets[k] = 0                      # is complete in host memory: hand it to the consumer
+                    if d.get_frame_into(ring[k]):           # D2H of the shown frame into pinned memory (async)
+                        tickets[k] = d.mark()
                         n += 1
-                        if n % RING == 0:
-                            d.sync()                        # ring full: the last RING frames are readable
-            d.sync()
+            d.sync()                                        # every frame is in host memory
+            for k in range(RING):
+                tickets[k] = 0
             return n
 
         run(1)                  # warm-up: sizes every pool

@@ -108,6 +108,10 @@ def lib_gpu():
         L.vp9gpu_free_host.argtypes = [vp]
         L.vp9b_decoder_read_frame_async.argtypes = [vp, C.POINTER(Image), vp, vp, vp, C.c_int, C.c_int]
         L.vp9b_decoder_sync.argtypes = [vp]
+        L.vp9b_decoder_mark.argtypes = [vp, C.POINTER(C.c_uint64)]
+        L.vp9b_decoder_wait.argtypes = [vp, C.c_uint64]
+        L.vp9gpu_mark.argtypes = [vp, C.POINTER(C.c_uint64)]
+        L.vp9gpu_wait.argtypes = [vp, C.c_uint64]
         L.vp9gpu_set_frame.argtypes = [vp, C.c_int, C.c_uint32, C.c_uint32, C.c_int, C.c_int, C.c_int, vp, vp, vp,
                                        C.c_int, C.c_int]
         L.vp9gpu_set_stop_stage.argtypes = [vp, C.c_int]
@@ -337,6 +341,15 @@ class Decoder:
 
     def sync(self):
         self._chk(self.L.vp9b_decoder_sync(self.d))
+
+    def mark(self):
+        """Ticket for everything enqueued so far (e.g. the frame just handed to get_frame_into)."""
+        t = C.c_uint64()
+        self._chk(self.L.vp9b_decoder_mark(self.d, C.byref(t)))
+        return t.value
+
+    def wait(self, ticket):
+        self._chk(self.L.vp9b_decoder_wait(self.d, ticket))
 
     def gpu_launch_count(self):
         return int(self.L.vp9gpu_launch_count(self.L.vp9b_decoder_gpu(self.d)))

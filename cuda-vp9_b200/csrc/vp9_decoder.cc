@@ -109,4 +109,18 @@ int vp9b_decoder_sync(vp9b_decoder *d) {
   return e;
 }
 
+int vp9b_decoder_mark(vp9b_decoder *d, uint64_t *ticket) {
+  if (!d) return VP9B_ERR_INVALID;
+  const int e = vp9gpu_mark(d->gpu, ticket);
+  if (e) d->err = vp9gpu_last_error(d->gpu);
+  return e;
+}
+
+int vp9b_decoder_wait(vp9b_decoder *d, uint64_t ticket) {
+  if (!d) return VP9B_ERR_INVALID;
+  const int e = vp9gpu_wait(d->gpu, ticket);
+  if (e) d->err = vp9gpu_last_error(d->gpu);
+  return e;
+}
+
 }  // extern "C"

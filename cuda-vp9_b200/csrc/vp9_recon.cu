@@ -1543,6 +1543,11 @@ struct vp9gpu_ctx {
   MiEntry *d_mi = nullptr;
   uint32_t *d_tickets = nullptr;  // wavefront progress counters
   uint32_t epoch = 0;
+  // tickets (vp9gpu_mark / vp9gpu_wait)
+  static const int kTickets = 64;
+  cudaEvent_t ticket_ev[kTickets];
+  bool tickets_ready = false;
+  uint64_t next_ticket = 1;
   int stop_stage = 0;
   uint64_t launches = 0;
   int num_sms = 148;
@@ -1612,6 +1617,8 @@ extern "C" void vp9gpu_destroy(vp9gpu_ctx *ctx) {
     cudaEventDestroy(ctx->ring_ev[i]);
   }
   for (int i = 0; i < 6; i++) cudaEventDestroy(ctx->prof_ev[i]);
+  if (ctx->tickets_ready)
+    for (int i = 0; i < vp9gpu_ctx::kTickets; i++) cudaEventDestroy(ctx->ticket_ev[i]);
   cudaFree(ctx->d_mi);
   cudaFree(ctx->d_tickets);
   cudaStreamDestroy(ctx->stream);
@@ -1640,6 +1647,26 @@ extern "C" int vp9gpu_get_stage_ms(vp9gpu_ctx *ctx, float ms[8], int reset) {
 #ifdef VP9B_LF_TIMING
 extern "C" int vp9gpu_debug_read(unsigned long long *out) { return (int)cudaMemcpyFromSymbol(out, vp9b::d_lf_dbg, sizeof(unsigned long long) * 512); }
 #endif
+extern "C" int vp9gpu_mark(vp9gpu_ctx *ctx, uint64_t *ticket) {
+  if (!ctx || !ticket) return VP9B_ERR_INVALID;
+  CK(cudaSetDevice(ctx->device));
+  if (!ctx->tickets_ready) {
+    for (int i = 0; i < vp9gpu_ctx::kTickets; i++) CK(cudaEventCreateWithFlags(&ctx->ticket_ev[i], cudaEventDisableTiming));
+    ctx->tickets_ready = true;
+  }
+  const uint64_t t = ctx->next_ticket++;
+  CK(cudaEventRecord(ctx->ticket_ev[t % vp9gpu_ctx::kTickets], ctx->stream));
+  *ticket = t;
+  return 0;
+}
+extern "C" int vp9gpu_wait(vp9gpu_ctx *ctx, uint64_t ticket) {
+  if (!ctx || ticket == 0 || ticket >= ctx->next_ticket) return VP9B_ERR_INVALID;
+  CK(cudaSetDevice(ctx->device));
+  // a ticket whose event slot has been re-recorded is older than that record: stream order makes
+  // waiting for the newer record sufficient
+  CK(cudaEventSynchronize(ctx->ticket_ev[ticket % vp9gpu_ctx::kTickets]));
+  return 0;
+}
 extern "C" int vp9gpu_sync(vp9gpu_ctx *ctx) {
   if (!ctx) return VP9B_ERR_INVALID;
   CK(cudaStreamSynchronize(ctx->stream));

@@ -161,6 +161,11 @@ int vp9gpu_get_frame(vp9gpu_ctx *ctx, int slot, uint8_t *y, uint8_t *u, uint8_t 
  * Use pinned destination buffers (vp9gpu_alloc_host) so that the copy overlaps later frames. */
 int vp9gpu_get_frame_async(vp9gpu_ctx *ctx, int slot, uint8_t *y, uint8_t *u, uint8_t *v, int y_stride,
                            int uv_stride);
+/* Tickets: vp9gpu_mark() records a point on the ctx stream (e.g. right after a get_frame_async),
+ * vp9gpu_wait() blocks until that point has been reached.  Lets a host thread wait for the frame
+ * it handed out N frames ago instead of draining the stream.  Up to 64 tickets may be pending. */
+int vp9gpu_mark(vp9gpu_ctx *ctx, uint64_t *ticket);
+int vp9gpu_wait(vp9gpu_ctx *ctx, uint64_t ticket);
 /* Page-locked host memory for output frames / packed buffers. */
 void *vp9gpu_alloc_host(size_t bytes);
 void vp9gpu_free_host(void *p);
@@ -222,6 +227,9 @@ int vp9b_decoder_read_frame(vp9b_decoder *d, const vp9b_image *img, uint8_t *y, 
 int vp9b_decoder_read_frame_async(vp9b_decoder *d, const vp9b_image *img, uint8_t *y, uint8_t *u, uint8_t *v,
                                   int y_stride, int uv_stride);
 int vp9b_decoder_sync(vp9b_decoder *d);
+/* Ticket of everything enqueued so far / wait for a ticket (see vp9gpu_mark, vp9gpu_wait). */
+int vp9b_decoder_mark(vp9b_decoder *d, uint64_t *ticket);
+int vp9b_decoder_wait(vp9b_decoder *d, uint64_t ticket);
 vp9gpu_ctx *vp9b_decoder_gpu(vp9b_decoder *d);
 vp9b_parser *vp9b_decoder_parser(vp9b_decoder *d);
 
