@@ -1188,11 +1188,12 @@ VP9B_DEV unsigned long long gtime() { unsigned long long t; asm volatile("mov.u6
 #else
 #define LFT(k)
 #endif
+// Named barriers go through the compiler intrinsic, not inline PTX: bar.sync is warp-aligned, and
+// only the intrinsic tells the compiler that the warp has to reconverge before it (the filter
+// passes in front of these barriers diverge on the sample data; an opaque asm barrier hung there).
 VP9B_DEV void bar_sync(int id, int nthreads) {
-  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
-}
-VP9B_DEV void bar_arrive(int id, int nthreads) {
-  asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+  __syncwarp();
+  __barrier_sync_count((unsigned)id, (unsigned)nthreads);
 }
 
 template <typename Px, int NW>
@@ -1210,7 +1211,7 @@ __global__ void __launch_bounds__(NW + 64, NW == 128 ? 3 : 2) k_loopfilter(const
   //   workers, per superblock c (tile = 64 columns of c + the first 8 of c+1, all planes):
   //     staged interior -> shared | B1 | vertical edges (thread = sample row) | B2 | horizontal
   //     edges (thread = sample column) | B3 | left edge of c+1 | B5 | store the 64 columns of c,
-  //     move the 8 look-ahead columns to the front | arrive B6.
+  //     move the 8 look-ahead columns to the front | B6.
   //     The interior of c+1 is prefetched into registers while c is filtered, and a thread
   //     stores and re-fills only its own shared-memory slots, so nothing separates two steps.
   //   halo warp: waits until the row above has published superblock c, loads the 8 rows above
@@ -1222,7 +1223,7 @@ __global__ void __launch_bounds__(NW + 64, NW == 128 ? 3 : 2) k_loopfilter(const
   typedef typename LfVec<Px>::T Vec;
   constexpr int nworkers = NW;   // 128: 4:2:0, 192: 4:4:4
   const int tid = threadIdx.x;
-  const int n_b2 = nworkers + 64, n_b3 = nworkers + 32, n_b6 = nworkers + 32;
+  const int n_b2 = nworkers + 32, n_b3 = nworkers + 32, n_b6 = nworkers + 32;
   const int lane = tid & 31;
   constexpr bool sub = NW == 128;  // 4:2:0 (else 4:4:4)
   // stride in samples: (stride bytes / 4) odd -> conflict-free row-per-thread walks
@@ -1275,13 +1276,12 @@ __global__ void __launch_bounds__(NW + 64, NW == 128 ? 3 : 2) k_loopfilter(const
 
   if (tid >= nworkers + 32) {
     // ------------------------------------------------------------------ publish warp
-    bool w0 = has_work(0);
     for (int sbc = 0; sbc < sb_cols; sbc++) {
-      const bool w1 = has_work(sbc + 1);
-      if (w0 | w1) bar_sync(2, n_b2);   // keeps the workers at most one step ahead of the publishes
+      // The workers join this barrier with bar.sync too: the publish warp is normally waiting here
+      // already, so they do not stall, and they can never run a second step into the barrier
+      // while a release is still in flight.
       bar_sync(6, n_b6);                 // every store of superblock sbc has been issued
       if (lane == 0) st_release(prog + sbr, base + (uint32_t)(sbc + 1));
-      w0 = w1;
     }
     return;
   }
@@ -1413,7 +1413,7 @@ __global__ void __launch_bounds__(NW + 64, NW == 128 ? 3 : 2) k_loopfilter(const
     const bool has_next = sbc + 1 < sb_cols;
     LFT(0)
     if (!(w0 | w1)) {                // nothing to filter in c, no left edge in c+1
-      bar_arrive(6, n_b6);
+      bar_sync(6, n_b6);
       carry_valid = false;
       if (w1 | w2) prefetch(sbc + 1);
       w0 = w1; w1 = w2;
@@ -1504,7 +1504,7 @@ __global__ void __launch_bounds__(NW + 64, NW == 128 ? 3 : 2) k_loopfilter(const
           smem_put(tile + int_soff[k], vv);
         }
       }
-    bar_arrive(6, n_b6);     // the publish warp releases superblock c
+    bar_sync(6, n_b6);       // the publish warp releases superblock c
     carry_valid = true;
     LFT(7)
     w0 = w1; w1 = w2;
