@@ -155,8 +155,9 @@ def random_coefs(rng, n, tx_size, bd, eob=None):
     return v
 
 
-def add_inter_blocks(rng, f, far=0.1):
-    """Random partition of the frame into inter prediction blocks with random references."""
+def add_inter_blocks(rng, f, far=0.1, intra_sbs=()):
+    """Random partition of the frame into inter prediction blocks with random references.
+    Superblocks listed in intra_sbs (row, col) become one intra 64x64 block instead."""
     nref = len(f.refs)
 
     def rand_mv():
@@ -211,11 +212,17 @@ def add_inter_blocks(rng, f, far=0.1):
 
     for r in range(0, f.mi_rows, 8):
         for c in range(0, f.mi_cols, 8):
-            part(r, c, 8)
+            if (r // 8, c // 8) in intra_sbs:
+                b = np.zeros((), dtype=BLOCK_DT)
+                b["mi_col"], b["mi_row"], b["bsize"] = c, r, 12
+                f.blocks.append(b)
+            else:
+                part(r, c, 8)
 
 
-def add_inter_residuals(rng, f, density=0.3):
+def add_inter_residuals(rng, f, density=0.3, intra_sbs=()):
     for p in range(3):
+        sbn = 64 >> (f.ss if p else 0)
         pw, ph = f.plane_dims(p)
         for tx_size in range(4):
             n = 4 << tx_size
@@ -223,7 +230,7 @@ def add_inter_residuals(rng, f, density=0.3):
                 continue
             for y in range(0, ph, n):
                 for x in range(0, pw, n):
-                    if rng.random() > density / (1 + tx_size):
+                    if rng.random() > density / (1 + tx_size) or (y // sbn, x // sbn) in intra_sbs:
                         continue
                     v = random_coefs(rng, n * n, tx_size, f.bd)
                     t = np.zeros((), dtype=TXB_DT)
@@ -246,7 +253,7 @@ def add_inter_residuals(rng, f, density=0.3):
         f.txb_inter[tx_size] = keep
 
 
-def add_intra_blocks(rng, f, tx_size_of_sb=None, coef_prob=0.7, tile_cols=()):
+def add_intra_blocks(rng, f, tx_size_of_sb=None, coef_prob=0.7, tile_cols=(), only_sbs=None):
     """Every plane is covered with intra transform blocks, one transform size per superblock,
     raster order inside the superblock (a valid decode order for equal-size blocks)."""
     for p in range(3):
@@ -254,6 +261,8 @@ def add_intra_blocks(rng, f, tx_size_of_sb=None, coef_prob=0.7, tile_cols=()):
         sbn = 64 >> (f.ss if p else 0)
         for sy in range(0, ph, sbn):
             for sx in range(0, pw, sbn):
+                if only_sbs is not None and (sy // sbn, sx // sbn) not in only_sbs:
+                    continue
                 tx_size = 0 if f.lossless else int(rng.integers(0, 4))
                 if tx_size_of_sb is not None:
                     tx_size = tx_size_of_sb

@@ -31,6 +31,22 @@ def build_inter(seed, w, h, bd, ss, scaled, lf):
     return f, refs
 
 
+def build_mixed(seed, w, h, bd, ss):
+    """Inter frame in which a random third of the superblocks is intra coded."""
+    rng = np.random.default_rng(seed)
+    f = sp.Frame(w, h, bd=bd, ss=ss, dst_slot=DST)
+    refs = []
+    for slot in range(3):
+        f.refs.append((slot, w, h))
+        refs.append((slot, sp.random_planes(rng, w, h, bd, ss, smooth=True)))
+    intra_sbs = {(r, c) for r in range(f.sb_rows) for c in range(f.sb_cols) if rng.random() < 0.35}
+    sp.add_inter_blocks(rng, f, intra_sbs=intra_sbs)
+    sp.add_inter_residuals(rng, f, intra_sbs=intra_sbs)
+    sp.add_intra_blocks(rng, f, only_sbs=intra_sbs)
+    sp.add_loop_filter(rng, f)
+    return f, refs
+
+
 def build_intra(seed, w, h, bd, ss, lf, lossless=False, tx=None):
     rng = np.random.default_rng(seed)
     f = sp.Frame(w, h, bd=bd, ss=ss, dst_slot=DST, intra_only=True, lossless=lossless)
@@ -57,6 +73,8 @@ CASES = [
     ("inter12_scaled", lambda s: build_inter(s, 144, 112, 12, 1, True, True)),
     ("inter8_444", lambda s: build_inter(s, 136, 136, 8, 0, False, True)),
     ("inter10_444", lambda s: build_inter(s, 128, 72, 10, 0, True, True)),
+    ("mixed8", lambda s: build_mixed(s, 328, 200, 8, 1)),
+    ("mixed10_444", lambda s: build_mixed(s, 200, 136, 10, 0)),
     ("intra8", lambda s: build_intra(s, 200, 136, 8, 1, True)),
     ("intra8_tx32", lambda s: build_intra(s, 192, 128, 8, 1, False, tx=3)),
     ("intra12", lambda s: build_intra(s, 136, 200, 12, 1, True)),
