@@ -89,7 +89,8 @@ VP9B_DEV int clampi(int v, int lo, int hi) { return min(max(v, lo), hi); }
 // stage 0: block list -> dense mi map
 __global__ void k_expand_blocks(const vp9b_block *__restrict__ blocks, int n, MiEntry *__restrict__ mi, int mi_cols,
                                 int mi_rows) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  // 8 threads per block: thread l fills row l of the block's footprint in the 8x8 map
+  const int t = blockIdx.x * blockDim.x + threadIdx.x, i = t >> 3, l = t & 7;
   if (i >= n) return;
   const vp9b_block b = blocks[i];
   MiEntry e;
@@ -102,8 +103,8 @@ __global__ void k_expand_blocks(const vp9b_block *__restrict__ blocks, int n, Mi
     e.aux = idx;
   }
   const int bw = min((int)d_bw8[b.bsize], mi_cols - b.mi_col), bh = min((int)d_bh8[b.bsize], mi_rows - b.mi_row);
-  for (int y = 0; y < bh; y++)
-    for (int x = 0; x < bw; x++) mi[(size_t)(b.mi_row + y) * mi_cols + b.mi_col + x] = e;
+  if (l < bh)
+    for (int x = 0; x < bw; x++) mi[(size_t)(b.mi_row + l) * mi_cols + b.mi_col + x] = e;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1733,7 +1734,7 @@ static int launch_stages(vp9gpu_ctx *ctx, const FrameParams &P, const vp9b_frame
   if (prof) cudaEventRecord(ctx->prof_ev[0], st);
   if (!h->intra_only) {
     if (P.n_blocks) {
-      k_expand_blocks<<<(P.n_blocks + 127) / 128, 128, 0, st>>>(P.blocks, P.n_blocks, P.mi, P.mi_cols, P.mi_rows);
+      k_expand_blocks<<<(P.n_blocks * 8 + 127) / 128, 128, 0, st>>>(P.blocks, P.n_blocks, P.mi, P.mi_cols, P.mi_rows);
       ctx->launches++;
     }
     if (prof) cudaEventRecord(ctx->prof_ev[1], st);
