@@ -644,6 +644,19 @@ VP9B_DEV void warp_itx_add(int *tbuf, const void *coef_base, int coef_bytes, con
   constexpr int S = N + 1;
   const int tx_size = t.tx & 3, tx_type = lossless ? 0 : ((t.tx >> 2) & 3);
   const int eob = t.eob;
+  if (eob == 1 && tx_type == 0 && !lossless) {  // DC only: vpx_idctNxN_1_add_c
+    constexpr int sh = (N == 4) ? 4 : (N == 8 ? 5 : 6);
+    const int dc = coef_bytes == 2 ? (int)((const int16_t *)coef_base)[t.coef_off] : ((const int32_t *)coef_base)[t.coef_off];
+    const int v1 = rs14<PT>((PT)dc * (PT)c16);
+    const int a1 = (rs14<PT>((PT)v1 * (PT)c16) + (1 << (sh - 1))) >> sh;
+    const int mx = (1 << bd) - 1;
+    for (int p = lane; p < N * N; p += 32) {
+      Px *q = dst + (size_t)(p / N) * stride + (p % N);
+      *q = (Px)clampi((int)*q + a1, 0, mx);
+    }
+    __syncwarp();
+    return;
+  }
   for (int i = lane; i < N * S; i += 32) tbuf[i] = 0;
   __syncwarp();
   const int16_t *scan = d_scan + scan_offset(tx_size, tx_type);
@@ -736,7 +749,7 @@ VP9B_DEV void group_itx_add(int *tbuf, const FrameParams &P, int first, int coun
   constexpr int S = N + 1;
   const int sub = lane / N, l = lane % N;
   int *tb = tbuf + sub * (N * S);
-  const bool active = sub < count;
+  bool active = sub < count;
   vp9b_txb t;
   t.coef_off = 0; t.x4 = t.y4 = 0; t.eob = 0; t.tx = 0; t.aux = 0;
   if (active) t = P.txb_inter[first + sub];
@@ -746,7 +759,24 @@ VP9B_DEV void group_itx_add(int *tbuf, const FrameParams &P, int first, int coun
   const int lossless = (N == 4) ? P.lossless : 0;
   const int tx_type = lossless ? 0 : ((t.tx >> 2) & 3);
   const int eob = t.eob;
-  for (int i = l; i < N * S; i += N) tb[i] = 0;
+  constexpr int shift = (N == 4) ? 4 : (N == 8 ? 5 : 6);
+  const int maxv = (1 << P.bd) - 1;
+  // DC-only DCT blocks (more than half of all inter blocks): both passes reduce to one value
+  // (vpx_idctNxN_1_add_c, inv_txfm.c:159-173 and the 8/16/32 twins)
+  const bool dc_only = active && eob == 1 && tx_type == 0 && !lossless;
+  if (dc_only) {
+    const int dc = sizeof(Px) == 1 ? (int)((const int16_t *)P.coef)[t.coef_off] : ((const int32_t *)P.coef)[t.coef_off];
+    const int v1 = rs14<PT>((PT)dc * (PT)c16);
+    const int a1 = (rs14<PT>((PT)v1 * (PT)c16) + (1 << (shift - 1))) >> shift;
+#pragma unroll 4
+    for (int j = 0; j < N; j++) {
+      Px *p = dst + (size_t)j * stride + l;
+      *p = (Px)clampi((int)*p + a1, 0, maxv);
+    }
+  }
+  active = active && !dc_only;
+  if (active)
+    for (int i = l; i < N * S; i += N) tb[i] = 0;
   __syncwarp();
   if (active) {
     const int16_t *scan = d_scan + scan_offset(t.tx & 3, tx_type);
@@ -765,7 +795,6 @@ VP9B_DEV void group_itx_add(int *tbuf, const FrameParams &P, int first, int coun
     }
   }
   __syncwarp();
-  const int maxv = (1 << P.bd) - 1;
   if (N == 4 && lossless) {  // vpx_iwht4x4_16_add_c (inv_txfm.c:18-66)
     int o[4];
     if (active) {
@@ -793,7 +822,6 @@ VP9B_DEV void group_itx_add(int *tbuf, const FrameParams &P, int first, int coun
     }
   }
   __syncwarp();
-  constexpr int shift = (N == 4) ? 4 : (N == 8 ? 5 : 6);
   if (active) {  // columns
     int in[N], out[N];
 #pragma unroll
