@@ -202,10 +202,10 @@ def run_ours(args, rank, world, local):
     streams = [torch.cuda.ExternalStream(c.stream()) for c in ctxs]
     master = torch.cuda.Stream()
 
+    batches = [ctxs[ci].make_batch([(dptr[ci][f], hdrs[f]) for f in range(n_coded)]) for ci in range(S)]
+
     def submit_all(ci):
-        c = ctxs[ci]
-        for f in range(n_coded):
-            c.submit_device(dptr[ci][f], hdrs[f])
+        ctxs[ci].submit_batch(batches[ci])      # one C-ABI call queues the whole clip pass
 
     def replay_step(threads=True):
         if threads and S > 1:

@@ -101,6 +101,7 @@ def lib_gpu():
         L.vp9gpu_upload_packed.argtypes = [vp, vp, C.c_size_t, C.POINTER(vp)]
         L.vp9gpu_free_packed.argtypes = [vp, vp]
         L.vp9gpu_sync.argtypes = [vp]
+        L.vp9gpu_frame_submit_device_n.argtypes = [vp, C.POINTER(C.c_void_p), C.POINTER(C.POINTER(FrameHdr)), C.c_int]
         L.vp9gpu_get_frame.argtypes = [vp, C.c_int, vp, vp, vp, C.c_int, C.c_int]
         L.vp9gpu_get_frame_async.argtypes = [vp, C.c_int, vp, vp, vp, C.c_int, C.c_int]
         L.vp9gpu_alloc_host.restype = vp
@@ -224,6 +225,16 @@ class GpuRecon:
 
     def submit_device(self, d_packed, hdr):
         self._chk(self.L.vp9gpu_frame_submit_device(self.ctx, d_packed, C.byref(hdr)))
+
+    def make_batch(self, frames):
+        """frames: [(device pointer, FrameHdr)] -> opaque batch for submit_batch (one C call per pass)."""
+        n = len(frames)
+        ptrs = (C.c_void_p * n)(*[d.value if isinstance(d, C.c_void_p) else d for d, _ in frames])
+        hdrs = (C.POINTER(FrameHdr) * n)(*[C.pointer(h) for _, h in frames])
+        return (ptrs, hdrs, n, frames)          # keeps the headers alive
+
+    def submit_batch(self, batch):
+        self._chk(self.L.vp9gpu_frame_submit_device_n(self.ctx, batch[0], batch[1], batch[2]))
 
     def free(self, d_packed):
         self._chk(self.L.vp9gpu_free_packed(self.ctx, d_packed))

@@ -1935,6 +1935,17 @@ extern "C" int vp9gpu_frame_submit_device(vp9gpu_ctx *ctx, const void *d_packed,
   return submit_device(ctx, (const uint8_t *)d_packed, hdr);
 }
 
+extern "C" int vp9gpu_frame_submit_device_n(vp9gpu_ctx *ctx, const void *const *d_packed,
+                                            const vp9b_frame_hdr *const *hdr, int n) {
+  if (!ctx || !d_packed || !hdr || n < 0) return VP9B_ERR_INVALID;
+  for (int i = 0; i < n; i++) {
+    if (!d_packed[i] || !hdr[i]) return VP9B_ERR_INVALID;
+    const int e = submit_device(ctx, (const uint8_t *)d_packed[i], hdr[i]);
+    if (e) return e;
+  }
+  return 0;
+}
+
 extern "C" int vp9gpu_frame_submit(vp9gpu_ctx *ctx, const void *packed, size_t bytes) {
   if (!ctx || !packed || bytes < sizeof(vp9b_frame_hdr)) return VP9B_ERR_INVALID;
   const vp9b_frame_hdr *h = (const vp9b_frame_hdr *)packed;

@@ -147,6 +147,10 @@ const char *vp9gpu_last_error(vp9gpu_ctx *ctx);
 int vp9gpu_frame_submit(vp9gpu_ctx *ctx, const void *packed, size_t bytes);
 /* Same, but the packed buffer already lives in DEVICE memory (recon-only replay, bench). */
 int vp9gpu_frame_submit_device(vp9gpu_ctx *ctx, const void *d_packed, const vp9b_frame_hdr *hdr);
+/* The same for n device-resident frames in decode order with one call (replay / transcoding
+ * front ends that queue a whole GOP): stops at the first error. */
+int vp9gpu_frame_submit_device_n(vp9gpu_ctx *ctx, const void *const *d_packed,
+                                 const vp9b_frame_hdr *const *hdr, int n);
 /* Upload a packed buffer to a ctx-owned device allocation for later submit_device calls. */
 int vp9gpu_upload_packed(vp9gpu_ctx *ctx, const void *packed, size_t bytes, void **d_packed);
 int vp9gpu_free_packed(vp9gpu_ctx *ctx, void *d_packed);
