@@ -77,6 +77,11 @@ struct FrameParams {
   uint32_t *prog_intra;         // [3][sb_rows] progress counters: prog_base + superblocks done in the row
   uint32_t *prog_lf;            // [sb_rows]
   uint32_t prog_base;           // per-frame epoch offset: counters never need clearing between frames
+  // Work tickets: a wavefront CTA / warp takes its row from a counter instead of blockIdx, so a
+  // unit that waits for a lower-numbered one can only be running if that one was started before
+  // it -- forward progress does not depend on the order in which the hardware dispatches CTAs.
+  uint32_t *ticket_lf, *ticket_intra;
+  uint32_t ticket_lf_base, ticket_intra_base;
   uint8_t lf_lim[64], lf_mblim[64];
 };
 
@@ -1037,7 +1042,11 @@ __global__ void __launch_bounds__(kWaveWarps * 32) k_intra(const __grid_constant
   Px *tile = (Px *)wbase;
   int *tbuf = (int *)(wbase + G::kTileBytes);
   IntraEdge &edge = *(IntraEdge *)(wbase + G::kTileBytes + 32 * 33 * sizeof(int));
-  const int unit = blockIdx.x * kWaveWarps + warp;
+  // one ticket per CTA: its warps take four consecutive units, as with a blockIdx mapping
+  __shared__ int s_cta;
+  if (threadIdx.x == 0) s_cta = (int)(atomicAdd(P.ticket_intra, 1u) - P.ticket_intra_base);
+  __syncthreads();
+  const int unit = s_cta * kWaveWarps + warp;
   if (unit >= 3 * P.sb_rows) return;
   // units are ordered row-major so that a row's dependency (row-1, same plane) has a lower index
   const int sbr = unit / 3, plane = unit % 3;
@@ -1261,7 +1270,10 @@ __global__ void __launch_bounds__(NW + 64, NW == 128 ? 3 : 2) k_loopfilter(const
   constexpr int offU = 72 * tsY, offV = 72 * tsY + (nC + 8) * tsC;
   // has-work flag per superblock of this row, computed once (the loops below look two ahead)
   uint8_t *wk = (uint8_t *)(tile + offV + (nC + 8) * tsC) + 16;
-  const int sbr = blockIdx.x, sb_cols = P.sb_cols;
+  __shared__ int s_row;
+  if (threadIdx.x == 0) s_row = (int)(atomicAdd(P.ticket_lf, 1u) - P.ticket_lf_base);
+  __syncthreads();
+  const int sbr = s_row, sb_cols = P.sb_cols;
   const int mi_row = sbr * 8;
   const int hy = sbr > 0 ? 8 : 0;
   uint32_t *prog = P.prog_lf;  // [sb_rows] prog_base + number of leading superblocks that are final
@@ -1572,6 +1584,7 @@ struct vp9gpu_ctx {
   MiEntry *d_mi = nullptr;
   uint32_t *d_tickets = nullptr;  // wavefront progress counters
   uint32_t epoch = 0;
+  uint32_t ticket_lf_base = 0, ticket_intra_base = 0;   // running totals of tickets handed out
   // tickets (vp9gpu_mark / vp9gpu_wait)
   static const int kTickets = 64;
   cudaEvent_t ticket_ev[kTickets];
@@ -1744,8 +1757,8 @@ static int setup_workspace(vp9gpu_ctx *ctx, const vp9b_frame_hdr *h) {
     CK(cudaMalloc(&ctx->d_mi, sizeof(MiEntry) * (size_t)h->mi_cols * h->mi_rows));
     CK(cudaMemsetAsync(ctx->d_mi, 0, sizeof(MiEntry) * (size_t)h->mi_cols * h->mi_rows, ctx->stream));
     if (!ctx->d_tickets) {
-      CK(cudaMalloc(&ctx->d_tickets, sizeof(uint32_t) * 4096));
-      CK(cudaMemsetAsync(ctx->d_tickets, 0, sizeof(uint32_t) * 4096, ctx->stream));
+      CK(cudaMalloc(&ctx->d_tickets, sizeof(uint32_t) * (4096 + 64)));
+      CK(cudaMemsetAsync(ctx->d_tickets, 0, sizeof(uint32_t) * (4096 + 64), ctx->stream));
     }
     CK(cudaStreamSynchronize(ctx->stream));
     ctx->ws_mi_cols = h->mi_cols; ctx->ws_mi_rows = h->mi_rows;
@@ -1801,6 +1814,7 @@ static int launch_stages(vp9gpu_ctx *ctx, const FrameParams &P, const vp9b_frame
         attr_set = true;
       }
       k_intra<Px, PT><<<wave_blocks, kWaveWarps * 32, ismem, st>>>(P);
+      ctx->ticket_intra_base += (uint32_t)wave_blocks;
       ctx->launches++;
     }
   }
@@ -1813,6 +1827,7 @@ static int launch_stages(vp9gpu_ctx *ctx, const FrameParams &P, const vp9b_frame
     const size_t smem = sizeof(Px) * (size_t)(72 * tsY + 2 * (nC + 8) * tsC) + 32 + ((P.sb_cols + 2 + 15) & ~15);
     if (sub) k_loopfilter<Px, 128><<<P.sb_rows, 192, smem, st>>>(P);
     else k_loopfilter<Px, 192><<<P.sb_rows, 256, smem, st>>>(P);
+    ctx->ticket_lf_base += (uint32_t)P.sb_rows;
     ctx->launches++;
   }
   if (prof) {
@@ -1921,6 +1936,10 @@ static int submit_device(vp9gpu_ctx *ctx, const uint8_t *d_packed, const vp9b_fr
   P.prog_intra = ctx->d_tickets;
   P.prog_lf = ctx->d_tickets + 3072;
   P.prog_base = (ctx->epoch & 0xfffff) << 11;
+  P.ticket_lf = ctx->d_tickets + 4096;
+  P.ticket_intra = ctx->d_tickets + 4097;
+  P.ticket_lf_base = ctx->ticket_lf_base;
+  P.ticket_intra_base = ctx->ticket_intra_base;
   memcpy(P.lf_lim, h->lf_lim, 64);
   memcpy(P.lf_mblim, h->lf_mblim, 64);
   if (h->bit_depth == 8) e = launch_stages<uint8_t, int>(ctx, P, h);
