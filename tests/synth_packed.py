@@ -319,6 +319,20 @@ def add_loop_filter(rng, f, level=None):
                             v |= 1 << b
                     m[name][size] = v & valid & ~edge_clear
             m["int_4x4_y"] = int(rng.integers(0, 1 << 63)) & valid_y
-            m["int_4x4_uv"] = int(rng.integers(0, 1 << 16)) & valid_uv
+            # Chroma of an odd number of 8x8 columns / rows ends in a half block: libvpx applies no
+            # inner 4x4 edge there and replaces a wide filter by the 8-wide one, so that no filter
+            # reads beyond the decoded area (vp9_adjust_mask, vp9_loopfilter.c:805-823, 846-870)
+            int_uv = 0
+            for r in range(rows >> 1):
+                int_uv |= ((1 << (cols >> 1)) - 1) << (4 * r)
+            m["int_4x4_uv"] = int(rng.integers(0, 1 << 16)) & int_uv
+            if cols & 1:
+                last_col = 0x1111 << (cols_uv - 1)
+                m["left_uv"][1] |= m["left_uv"][2] & last_col
+                m["left_uv"][2] &= ~last_col & 0xFFFF
+            if rows & 1:
+                last_row = 0xF << (4 * (rows_uv - 1))
+                m["above_uv"][1] |= m["above_uv"][2] & last_row
+                m["above_uv"][2] &= ~last_row & 0xFFFF
             m["lfl_y"] = rng.integers(1, 64, size=64)
     f.lfm = lfm

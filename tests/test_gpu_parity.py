@@ -110,3 +110,30 @@ def test_gpu_rejects_corrupt_packed_buffers():
     gpu.sync()
     gpu.close()
     parser.close()
+
+
+@pytest.mark.gpu
+def test_gpu_concurrent_streams_stay_bit_exact():
+    """Independent decoder contexts on concurrent host threads / CUDA streams (how the engine is
+    deployed): every stream must still match its golden MD5 list."""
+    import threading
+    names = ["comp_lf", "tiles_rt", "hbd10", "scaled_rt", "sub8", "p444", "aq", "odd_rt", "intra_only", "lossless",
+             "comp_lf", "tiles_rt"]
+    results = {}
+
+    def work(i, name):
+        try:
+            got = []
+            for _ in range(3):               # several passes: contexts overlap in every phase
+                got = vb.decode_ivf_md5(clip_path(name))
+            results[i] = (name, got == golden_md5(name))
+        except Exception as e:               # noqa: BLE001
+            results[i] = (name, repr(e))
+
+    th = [threading.Thread(target=work, args=(i, n)) for i, n in enumerate(names)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    bad = {i: r for i, r in results.items() if r[1] is not True}
+    assert not bad and len(results) == len(names), bad
