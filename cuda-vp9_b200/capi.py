@@ -104,6 +104,7 @@ def lib_gpu():
         L.vp9gpu_frame_submit_device_n.argtypes = [vp, C.POINTER(C.c_void_p), C.POINTER(C.POINTER(FrameHdr)), C.c_int]
         L.vp9gpu_get_frame.argtypes = [vp, C.c_int, vp, vp, vp, C.c_int, C.c_int]
         L.vp9gpu_get_frame_async.argtypes = [vp, C.c_int, vp, vp, vp, C.c_int, C.c_int]
+        L.vp9gpu_get_frame_8bit_async.argtypes = [vp, C.c_int, vp, vp, vp, C.c_int, C.c_int]
         L.vp9gpu_alloc_host.restype = vp
         L.vp9gpu_alloc_host.argtypes = [C.c_size_t]
         L.vp9gpu_free_host.argtypes = [vp]
@@ -249,6 +250,14 @@ class GpuRecon:
         pl = _alloc_planes(w, h, bd, sx, sy)
         self._chk(self.L.vp9gpu_get_frame(self.ctx, slot, pl[0].ctypes.data, pl[1].ctypes.data, pl[2].ctypes.data,
                                           pl[0].strides[0], pl[1].strides[0]))
+        return pl
+
+    def get_frame_8bit(self, slot, w, h, sx, sy):
+        """Shown frame at 8 bits per sample (high-bit-depth slots are shifted down on the GPU)."""
+        pl = _alloc_planes(w, h, 8, sx, sy)
+        self._chk(self.L.vp9gpu_get_frame_8bit_async(self.ctx, slot, pl[0].ctypes.data, pl[1].ctypes.data,
+                                                     pl[2].ctypes.data, pl[0].strides[0], pl[1].strides[0]))
+        self.sync()
         return pl
 
     def set_frame(self, slot, planes, bd, sx, sy):

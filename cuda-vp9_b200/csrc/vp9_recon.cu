@@ -1552,6 +1552,22 @@ __global__ void __launch_bounds__(NW + 64, NW == 128 ? 3 : 2) k_loopfilter(const
   }
 }
 
+// output path: 16-bit samples -> 8 bits (truncating shift, highbd_img_downshift in tools_common.c)
+__global__ void k_downshift(const uint16_t *__restrict__ src, int sstride, uint8_t *__restrict__ dst, int dstride, int w,
+                            int h, int shift) {
+  const int x = (blockIdx.x * blockDim.x + threadIdx.x) * 4, y = blockIdx.y;
+  if (x >= w || y >= h) return;
+  const uint16_t *s = src + (size_t)y * sstride + x;
+  uint8_t *d = dst + (size_t)y * dstride + x;
+  if (x + 4 <= w) {
+    const uint2 v = *(const uint2 *)s;   // plane rows are 128-byte aligned, x is a multiple of 4
+    const uint32_t a = (v.x & 0xffffu) >> shift, b = (v.x >> 16) >> shift, c = (v.y & 0xffffu) >> shift, e = (v.y >> 16) >> shift;
+    *(uint32_t *)d = a | (b << 8) | (c << 16) | (e << 24);
+  } else {
+    for (int i = 0; x + i < w; i++) d[i] = (uint8_t)(s[i] >> shift);
+  }
+}
+
 }  // namespace vp9b
 
 // ==========================================================================================
@@ -1584,6 +1600,8 @@ struct vp9gpu_ctx {
   MiEntry *d_mi = nullptr;
   uint32_t *d_tickets = nullptr;  // wavefront progress counters
   uint32_t epoch = 0;
+  uint8_t *d_out8 = nullptr;      // staging for 8-bit output of high-bit-depth frames
+  size_t out8_bytes = 0;
   uint32_t ticket_lf_base = 0, ticket_intra_base = 0;   // running totals of tickets handed out
   // tickets (vp9gpu_mark / vp9gpu_wait)
   static const int kTickets = 64;
@@ -1662,6 +1680,7 @@ extern "C" void vp9gpu_destroy(vp9gpu_ctx *ctx) {
   if (ctx->tickets_ready)
     for (int i = 0; i < vp9gpu_ctx::kTickets; i++) cudaEventDestroy(ctx->ticket_ev[i]);
   cudaFree(ctx->d_mi);
+  cudaFree(ctx->d_out8);
   cudaFree(ctx->d_tickets);
   cudaStreamDestroy(ctx->stream);
   delete ctx;
@@ -1689,6 +1708,42 @@ extern "C" int vp9gpu_get_stage_ms(vp9gpu_ctx *ctx, float ms[8], int reset) {
 #ifdef VP9B_LF_TIMING
 extern "C" int vp9gpu_debug_read(unsigned long long *out) { return (int)cudaMemcpyFromSymbol(out, vp9b::d_lf_dbg, sizeof(unsigned long long) * 512); }
 #endif
+extern "C" int vp9gpu_get_frame_8bit_async(vp9gpu_ctx *ctx, int slot, uint8_t *y, uint8_t *u, uint8_t *v, int y_stride,
+                                           int uv_stride) {
+  if (!ctx || slot < 0 || slot >= VP9B_NUM_SLOTS || !ctx->slot[slot].valid) return VP9B_ERR_INVALID;
+  const DevFrame &f = ctx->slot[slot];
+  if (f.bd == 8) return vp9gpu_get_frame_async(ctx, slot, y, u, v, y_stride, uv_stride);
+  CK(cudaSetDevice(ctx->device));
+  int pw[3], ph[3], ps[3];
+  size_t off[3], total = 0;
+  for (int p = 0; p < 3; p++) {
+    pw[p] = p ? (int)((f.width + f.ss_x) >> f.ss_x) : (int)f.width;
+    ph[p] = p ? (int)((f.height + f.ss_y) >> f.ss_y) : (int)f.height;
+    ps[p] = (pw[p] + 127) & ~127;
+    off[p] = total;
+    total += (size_t)ps[p] * ph[p];
+  }
+  if (ctx->out8_bytes < total) {
+    CK(cudaStreamSynchronize(ctx->stream));
+    cudaFree(ctx->d_out8);
+    ctx->d_out8 = nullptr;
+    ctx->out8_bytes = 0;
+    CK(cudaMalloc(&ctx->d_out8, total));
+    ctx->out8_bytes = total;
+  }
+  uint8_t *out[3] = { y, u, v };
+  for (int p = 0; p < 3; p++) {
+    dim3 blk(64), grd((pw[p] / 4 + 64) / 64, ph[p]);
+    k_downshift<<<grd, blk, 0, ctx->stream>>>((const uint16_t *)f.pl[p].ptr, f.pl[p].stride, ctx->d_out8 + off[p], ps[p], pw[p],
+                                              ph[p], f.bd - 8);
+    ctx->launches++;
+    CK(cudaMemcpy2DAsync(out[p], p ? uv_stride : y_stride, ctx->d_out8 + off[p], ps[p], pw[p], ph[p], cudaMemcpyDeviceToHost,
+                         ctx->stream));
+  }
+  CK(cudaGetLastError());
+  return 0;
+}
+
 extern "C" int vp9gpu_mark(vp9gpu_ctx *ctx, uint64_t *ticket) {
   if (!ctx || !ticket) return VP9B_ERR_INVALID;
   CK(cudaSetDevice(ctx->device));

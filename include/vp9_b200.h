@@ -165,6 +165,12 @@ int vp9gpu_get_frame(vp9gpu_ctx *ctx, int slot, uint8_t *y, uint8_t *u, uint8_t 
  * Use pinned destination buffers (vp9gpu_alloc_host) so that the copy overlaps later frames. */
 int vp9gpu_get_frame_async(vp9gpu_ctx *ctx, int slot, uint8_t *y, uint8_t *u, uint8_t *v, int y_stride,
                            int uv_stride);
+/* High-bit-depth output at 8 bits: samples are shifted down by (bit_depth - 8) on the GPU
+ * (vpx_img_downshift, vpxdec --output-bit-depth=8, vpxdec.c:950-978) and copied as 1 byte per
+ * sample, i.e. half the D2H bytes.  Asynchronous like vp9gpu_get_frame_async; for an 8-bit slot it
+ * is identical to it. */
+int vp9gpu_get_frame_8bit_async(vp9gpu_ctx *ctx, int slot, uint8_t *y, uint8_t *u, uint8_t *v, int y_stride,
+                                int uv_stride);
 /* Tickets: vp9gpu_mark() records a point on the ctx stream (e.g. right after a get_frame_async),
  * vp9gpu_wait() blocks until that point has been reached.  Lets a host thread wait for the frame
  * it handed out N frames ago instead of draining the stream.  Up to 64 tickets may be pending. */

@@ -137,3 +137,28 @@ def test_gpu_concurrent_streams_stay_bit_exact():
         t.join()
     bad = {i: r for i, r in results.items() if r[1] is not True}
     assert not bad and len(results) == len(names), bad
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["hbd10", "hbd12", "p444_hbd", "odd_rt"])
+def test_gpu_8bit_output_is_the_shifted_frame(name):
+    """vp9gpu_get_frame_8bit_async == vpx_img_downshift of the full-depth frame (vpxdec.c:950-978)."""
+    _, _, chunks = vb.ivf_read(clip_path(name))
+    parser, gpu = vb.HostParser(), vb.GpuRecon(0)
+    shown = 0
+    for ch in chunks:
+        for fr in vb.parse_superframe(ch):
+            packed, show = parser.parse(fr)
+            if packed is not None:
+                gpu.submit(packed)
+            if show < 0:
+                continue
+            w, h, bd, sx, sy = parser.slot_info(show)
+            full = gpu.get_frame(show, w, h, bd, sx, sy)
+            eight = gpu.get_frame_8bit(show, w, h, sx, sy)
+            for a, b in zip(full, eight):
+                assert b.dtype == np.uint8 and np.array_equal((a >> (bd - 8)).astype(np.uint8), b)
+            shown += 1
+    assert shown > 0
+    gpu.close()
+    parser.close()
