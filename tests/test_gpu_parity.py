@@ -162,3 +162,17 @@ def test_gpu_8bit_output_is_the_shifted_frame(name):
     assert shown > 0
     gpu.close()
     parser.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["odd_rt", "hbd10", "p444"])
+def test_c_client_prints_the_golden_md5_list(name):
+    """examples/vpxdec_md5.c: a plain C program on the C ABI reproduces `vpxdec --md5`."""
+    import os
+    import subprocess
+    from conftest import ROOT
+    exe = os.path.join(ROOT, "examples", "vpxdec_md5")
+    assert os.path.exists(exe), "examples/vpxdec_md5 not built (python __graft_entry__.py)"
+    r = subprocess.run([exe, clip_path(name)], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr
+    assert [l.split()[0] for l in r.stdout.splitlines()] == golden_md5(name)
