@@ -172,7 +172,10 @@ def test_c_client_prints_the_golden_md5_list(name):
     import subprocess
     from conftest import ROOT
     exe = os.path.join(ROOT, "examples", "vpxdec_md5")
-    assert os.path.exists(exe), "examples/vpxdec_md5 not built (python __graft_entry__.py)"
+    if not os.path.exists(exe):      # normally built by __graft_entry__.build(); it is one gcc call
+        subprocess.check_call(["gcc", "-O2", "-I" + os.path.join(ROOT, "include"), os.path.join(ROOT, "examples", "vpxdec_md5.c"),
+                               "-L" + os.path.join(ROOT, "cuda-vp9_b200"), "-lvp9b200",
+                               "-Wl,-rpath,$ORIGIN/../cuda-vp9_b200", "-o", exe])
     r = subprocess.run([exe, clip_path(name)], capture_output=True, text=True, timeout=120)
     assert r.returncode == 0, r.stderr
     assert [l.split()[0] for l in r.stdout.splitlines()] == golden_md5(name)
