@@ -68,6 +68,8 @@ struct FrameParams {
   const vp9b_submv *submv;
   const vp9b_txb *txb_inter;
   int n_txb_inter;
+  int n_txb_intra[3];
+  void *resid[3];      // residual planes of the intra blocks (int16 / int32), same stride as dst
   int n_txb_size[4];   // TXB_INTER is grouped by transform size
   const vp9b_txb *txb_intra[3];
   const vp9b_sbrange *sb_intra;  // [3][nsb]
@@ -643,9 +645,25 @@ __global__ void __launch_bounds__(128, 4) k_inter_pred_u16(const __grid_constant
 // stages 2/3: inverse transform + add, one warp per transform block.  Rows then columns
 // (vpx_idctNxN_add_c), final shift 4/5/6/6, clip to the pixel range.  tbuf: per-warp shared
 // scratch of N*(N+1) ints.
-template <typename Px, typename PT, int N>
-VP9B_DEV void warp_itx_add(int *tbuf, const void *coef_base, int coef_bytes, const vp9b_txb &t, Px *dst, int stride,
-                           int bd, int lossless, int lane) {
+// where the samples of an inverse transform go: added to the prediction in place, or stored as a
+// residual plane for the intra wavefront (which then only predicts and adds)
+template <typename Px> struct SinkAdd {
+  Px *d; int stride, maxv;
+  VP9B_DEV void put(int r, int c, int v) const {
+    Px *q = d + (size_t)r * stride + c;
+    *q = (Px)clampi((int)*q + v, 0, maxv);
+  }
+};
+template <typename R> struct SinkRaw {
+  R *d; int stride;
+  VP9B_DEV void put(int r, int c, int v) const { d[(size_t)r * stride + c] = (R)v; }
+};
+template <typename Px> struct ResidT { typedef int16_t T; };
+template <> struct ResidT<uint16_t> { typedef int32_t T; };
+
+template <typename PT, int N, typename Sink>
+VP9B_DEV void warp_itx(int *tbuf, const void *coef_base, int coef_bytes, const vp9b_txb &t, const Sink &sink,
+                       int lossless, int lane) {
   constexpr int S = N + 1;
   const int tx_size = t.tx & 3, tx_type = lossless ? 0 : ((t.tx >> 2) & 3);
   const int eob = t.eob;
@@ -654,11 +672,7 @@ VP9B_DEV void warp_itx_add(int *tbuf, const void *coef_base, int coef_bytes, con
     const int dc = coef_bytes == 2 ? (int)((const int16_t *)coef_base)[t.coef_off] : ((const int32_t *)coef_base)[t.coef_off];
     const int v1 = rs14<PT>((PT)dc * (PT)c16);
     const int a1 = (rs14<PT>((PT)v1 * (PT)c16) + (1 << (sh - 1))) >> sh;
-    const int mx = (1 << bd) - 1;
-    for (int p = lane; p < N * N; p += 32) {
-      Px *q = dst + (size_t)(p / N) * stride + (p % N);
-      *q = (Px)clampi((int)*q + a1, 0, mx);
-    }
+    for (int p = lane; p < N * N; p += 32) sink.put(p / N, p % N, a1);
     __syncwarp();
     return;
   }
@@ -679,7 +693,6 @@ VP9B_DEV void warp_itx_add(int *tbuf, const void *coef_base, int coef_bytes, con
     }
   }
   __syncwarp();
-  const int maxv = (1 << bd) - 1;
   if (lossless) {  // vpx_iwht4x4_16_add_c (inv_txfm.c:18-66)
     if (N == 4) {
       int o[4];
@@ -690,7 +703,7 @@ VP9B_DEV void warp_itx_add(int *tbuf, const void *coef_base, int coef_bytes, con
       __syncwarp();
       if (lane < 4) {
         iwht4(tbuf[0 * S + lane], tbuf[1 * S + lane], tbuf[2 * S + lane], tbuf[3 * S + lane], o);
-        for (int j = 0; j < 4; j++) dst[j * stride + lane] = (Px)clampi((int)dst[j * stride + lane] + o[j], 0, maxv);
+        for (int j = 0; j < 4; j++) sink.put(j, lane, o[j]);
       }
     }
     __syncwarp();
@@ -718,37 +731,26 @@ VP9B_DEV void warp_itx_add(int *tbuf, const void *coef_base, int coef_bytes, con
     for (int j = 0; j < N; j++) in[j] = tbuf[j * S + lane];
     txfm1d<PT, N>(in, out, col_adst);
 #pragma unroll
-    for (int j = 0; j < N; j++) {
-      Px *p = dst + (size_t)j * stride + lane;
-      *p = (Px)clampi((int)*p + ((out[j] + (1 << (shift - 1))) >> shift), 0, maxv);
-    }
+    for (int j = 0; j < N; j++) sink.put(j, lane, (out[j] + (1 << (shift - 1))) >> shift);
   }
   __syncwarp();
 }
 
+// inverse transform of one intra block into the residual plane
 template <typename Px, typename PT>
-VP9B_DEV void warp_residual_at(const FrameParams &P, int *tbuf, const vp9b_txb &t, Px *dst, int stride, int lane) {
-  if (!t.eob) return;
-  const int tx_size = t.tx & 3;
+VP9B_DEV void warp_intra_residual(const FrameParams &P, int *tbuf, const vp9b_txb &t, int plane, int lane) {
+  typedef typename ResidT<Px>::T R;
+  const int stride = P.dst[plane].stride;
+  const SinkRaw<R> sink = { (R *)P.resid[plane] + (size_t)t.y4 * 4 * stride + t.x4 * 4, stride };
   const int cb = sizeof(Px) == 1 ? 2 : 4;
-  switch (tx_size) {
-    case 0: warp_itx_add<Px, PT, 4>(tbuf, P.coef, cb, t, dst, stride, P.bd, P.lossless, lane); break;
-    case 1: warp_itx_add<Px, PT, 8>(tbuf, P.coef, cb, t, dst, stride, P.bd, 0, lane); break;
-    case 2: warp_itx_add<Px, PT, 16>(tbuf, P.coef, cb, t, dst, stride, P.bd, 0, lane); break;
-    default: warp_itx_add<Px, PT, 32>(tbuf, P.coef, cb, t, dst, stride, P.bd, 0, lane); break;
+  switch (t.tx & 3) {
+    case 0: warp_itx<PT, 4>(tbuf, P.coef, cb, t, sink, P.lossless, lane); break;
+    case 1: warp_itx<PT, 8>(tbuf, P.coef, cb, t, sink, 0, lane); break;
+    case 2: warp_itx<PT, 16>(tbuf, P.coef, cb, t, sink, 0, lane); break;
+    default: warp_itx<PT, 32>(tbuf, P.coef, cb, t, sink, 0, lane); break;
   }
 }
 
-template <typename Px, typename PT>
-VP9B_DEV void warp_residual(const FrameParams &P, int *tbuf, const vp9b_txb &t, int lane) {
-  const int plane = (t.tx >> 4) & 3;
-  const int stride = P.dst[plane].stride;
-  Px *dst = (Px *)P.dst[plane].ptr + (size_t)t.y4 * 4 * stride + t.x4 * 4;
-  warp_residual_at<Px, PT>(P, tbuf, t, dst, stride, lane);
-}
-
-// Inter residuals: the list is grouped by transform size (hdr.n_txb_inter_size), so one warp takes
-// 32/N blocks of size N at a time -- a block uses N lanes (lane l = row l, then column l).
 template <typename Px, typename PT, int N>
 VP9B_DEV void group_itx_add(int *tbuf, const FrameParams &P, int first, int count, int lane) {
   constexpr int S = N + 1;
@@ -864,6 +866,23 @@ __global__ void __launch_bounds__(kResWarps * 32) k_residual(const __grid_consta
   }
 }
 
+// Residuals of the intra blocks: every block's inverse transform is independent of the prediction,
+// so it is taken off the intra wavefront's dependency chain and computed here, one warp per block,
+// into a residual plane; the wavefront (k_intra) then only predicts and adds.
+template <typename Px, typename PT>
+__global__ void __launch_bounds__(kResWarps * 32) k_intra_residual(const __grid_constant__ FrameParams P) {
+  __shared__ int tbuf[kResWarps][32 * 33];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nwarps = gridDim.x * kResWarps;
+  const int n0 = P.n_txb_intra[0], n1 = P.n_txb_intra[1], total = n0 + n1 + P.n_txb_intra[2];
+  for (int i = blockIdx.x * kResWarps + warp; i < total; i += nwarps) {
+    int plane = 0, k = i;
+    if (k >= n0) { k -= n0; plane = 1; if (k >= n1) { k -= n1; plane = 2; } }
+    const vp9b_txb t = P.txb_intra[plane][k];
+    if (t.eob) warp_intra_residual<Px, PT>(P, tbuf[warp], t, plane, lane);
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // stage 3: intra prediction.  Edge rules of build_intra_predictors (vp9_reconintra.c:113-402):
 // unavailable left -> base+1, unavailable above -> base-1, above-right only read for 4x4 blocks
@@ -946,61 +965,95 @@ VP9B_DEV void warp_intra_predict(const FrameParams &P, IntraEdge &E, const vp9b_
   }
 #define AT(i) ((i) < 0 ? tl : a[i])   /* above with above[-1] = top-left */
 #define LT(i) ((i) < 0 ? tl : l[i])   /* left with left[-1] = top-left  */
-  for (int p = lane; p < bs * bs; p += 32) {
-    const int r = p / bs, c = p % bs;
-    int v;
-    switch (mode) {
-      case 0: v = dc; break;
-      case 1: v = a[c]; break;
-      case 2: v = l[r]; break;
-      case 9: v = clampi(l[r] + a[c] - tl, 0, maxv); break;
-      case 3: {  // D45
+  const int lgb = 2 + tx_size, npx = bs * bs;
+  // one sample loop per mode: the dispatch is outside the loop, row / column come from shifts
+#define INTRA_LOOP(...)                                    \
+  for (int p = lane; p < npx; p += 32) {                   \
+    const int r = p >> lgb, c = p & (bs - 1);              \
+    int v;                                                 \
+    __VA_ARGS__                                            \
+    dst[r * stride + c] = (Px)v;                           \
+  }
+  switch (mode) {
+    case 0: INTRA_LOOP(v = dc;) break;
+    case 1: INTRA_LOOP(v = a[c];) break;
+    case 2: INTRA_LOOP(v = l[r];) break;
+    case 9: INTRA_LOOP(v = clampi(l[r] + a[c] - tl, 0, maxv);) break;
+    case 3:  // D45
+      INTRA_LOOP({
         const int i = r + c;
         if (bs == 4) v = (i == 6) ? a[7] : AVG3(a[i], a[i + 1], a[i + 2]);
         else v = (i < bs - 1) ? AVG3(a[i], a[i + 1], a[i + 2]) : a[bs - 1];
-        break;
-      }
-      case 8: {  // D63
+      })
+      break;
+    case 8:  // D63
+      INTRA_LOOP({
         const int k = r >> 1, i = k + c;
         if (bs != 4 && r >= 2 && c >= bs - 1 - k) v = a[bs - 1];
         else v = (r & 1) ? AVG3(a[i], a[i + 1], a[i + 2]) : AVG2(a[i], a[i + 1]);
-        break;
-      }
-      case 7: {  // D207
+      })
+      break;
+    case 7:  // D207
+      INTRA_LOOP({
         const int j = r + (c >> 1);
         if (j >= bs - 1) v = l[bs - 1];
         else if (!(c & 1)) v = AVG2(l[j], l[j + 1]);
         else v = AVG3(l[j], l[j + 1], l[min(j + 2, bs - 1)]);
-        break;
-      }
-      case 5: {  // D117
+      })
+      break;
+    case 5:  // D117
+      INTRA_LOOP({
         const int k = min(r >> 1, c), rr = r - 2 * k, cc = c - k;
         if (rr == 0) v = AVG2(AT(cc - 1), a[cc]);
         else if (rr == 1) v = cc == 0 ? AVG3(l[0], tl, a[0]) : AVG3(AT(cc - 2), a[cc - 1], a[cc]);
         else v = AVG3(LT(rr - 3), l[rr - 2], l[rr - 1]);
-        break;
-      }
-      case 4: {  // D135
+      })
+      break;
+    case 4:  // D135
+      INTRA_LOOP({
         const int d = c - r;
         if (d == 0) v = AVG3(l[0], tl, a[0]);
         else if (d > 0) v = AVG3(AT(d - 2), a[d - 1], a[d]);
         else v = AVG3(LT(-d - 2), l[-d - 1], l[-d]);
-        break;
-      }
-      default: {  // 6: D153
+      })
+      break;
+    default:  // 6: D153
+      INTRA_LOOP({
         const int k = min(r, c >> 1), rr = r - k, cc = c - 2 * k;
         if (cc >= 2) v = AVG3(AT(cc - 3), a[cc - 2], a[cc - 1]);
         else if (cc == 0) v = AVG2(LT(rr - 1), l[rr]);
         else if (rr == 0) v = AVG3(l[0], tl, a[0]);
         else v = AVG3(LT(rr - 2), l[rr - 1], l[rr]);
-        break;
-      }
-    }
-    dst[r * stride + c] = (Px)v;
+      })
+      break;
   }
+#undef INTRA_LOOP
 #undef AT
 #undef LT
   __syncwarp();
+}
+
+// residual of one block: 2^LG x 2^LG samples spread over the warp, lane + 32k -> (row, column)
+template <typename R, int LG>
+VP9B_DEV void resid_fetch(const R *rp, int stride, int lane, R *rv) {
+  constexpr int bs = 1 << LG, npx = bs * bs, it = (npx + 31) / 32;
+#pragma unroll
+  for (int k = 0; k < it; k++) {
+    const int p = lane + 32 * k;
+    if (npx >= 32 || p < npx) rv[k] = __ldg(rp + (size_t)(p >> LG) * stride + (p & (bs - 1)));
+  }
+}
+template <typename Px, typename R, int LG>
+VP9B_DEV void resid_add(Px *d, int ts, int lane, const R *rv, int maxv) {
+  constexpr int bs = 1 << LG, npx = bs * bs, it = (npx + 31) / 32;
+#pragma unroll
+  for (int k = 0; k < it; k++) {
+    const int p = lane + 32 * k;
+    if (npx >= 32 || p < npx) {
+      Px *q = d + (p >> LG) * ts + (p & (bs - 1));
+      *q = (Px)clampi((int)*q + (int)rv[k], 0, maxv);
+    }
+  }
 }
 
 constexpr int kWaveWarps = 4;
@@ -1109,23 +1162,53 @@ __global__ void __launch_bounds__(kWaveWarps * 32) k_intra(const __grid_constant
     __syncwarp();
     const vp9b_txb *list = P.txb_intra[plane] + rg.start;
     const int px0 = sbc * n, py0 = sbr * n;
+    typedef typename ResidT<Px>::T R;
+    const R *rplane = (const R *)P.resid[plane];
+    const int maxv = (1 << P.bd) - 1;
+    vp9b_txb t = list[0];
     for (uint32_t i = 0; i < rg.count; i++) {
-      const vp9b_txb t = list[i];
+      const vp9b_txb tn = list[min(i + 1, rg.count - 1)];   // next record: off the dependency chain
       Px *d = T0 + (t.y4 * 4 - py0) * TS + (t.x4 * 4 - px0);
+      // the block's residual (k_intra_residual) is fetched before the prediction and added after it
+      const int lg = 2 + (t.tx & 3);
+      const R *rp = rplane + (size_t)t.y4 * 4 * stride + t.x4 * 4;
+      R rv[32];
+      if (t.eob) {
+        switch (lg) {
+          case 2: resid_fetch<R, 2>(rp, stride, lane, rv); break;
+          case 3: resid_fetch<R, 3>(rp, stride, lane, rv); break;
+          case 4: resid_fetch<R, 4>(rp, stride, lane, rv); break;
+          default: resid_fetch<R, 5>(rp, stride, lane, rv); break;
+        }
+      }
       warp_intra_predict<Px>(P, edge, t, d, TS, lane);
-      warp_residual_at<Px, PT>(P, tbuf, t, d, TS, lane);
+      if (t.eob) {
+        switch (lg) {
+          case 2: resid_add<Px, R, 2>(d, TS, lane, rv, maxv); break;
+          case 3: resid_add<Px, R, 3>(d, TS, lane, rv, maxv); break;
+          case 4: resid_add<Px, R, 4>(d, TS, lane, rv, maxv); break;
+          default: resid_add<Px, R, 5>(d, TS, lane, rv, maxv); break;
+        }
+        __syncwarp();
+      }
+      t = tn;
     }
     __syncwarp();
-    // write the superblock back and keep its right-most column as the next left neighbour
+    // The row below only ever reads this superblock's bottom row (its "above" samples): store
+    // that row first and publish -- the release then waits for 64 samples, not for the whole tile
+    for (int v = lane; v < vpr; v += 32)
+      __stcg((Vec *)(g + (size_t)(n - 1) * stride + v * 8), *(const Vec *)(T0 + (n - 1) * TS + v * 8));
+    __syncwarp();
+    if (lane == 0) st_release(prog + sbr, P.prog_base + (uint32_t)(sbc + 1));
+    published = sbc + 1;
+    // the rest of the tile (read again only by the next launch) and the next left neighbour column
 #pragma unroll 4
-    for (int i = lane; i < nvec; i += 32)
+    for (int i = lane; i < nvec - vpr; i += 32)
       __stcg((Vec *)(g + (size_t)(i >> vsh) * stride + (i & (vpr - 1)) * 8), *(const Vec *)(T0 + (i >> vsh) * TS + (i & (vpr - 1)) * 8));
     __syncwarp();
     for (int r = lane; r < n; r += 32) T0[r * TS - 1] = T0[r * TS + n - 1];
     left_in_smem = true;
     __syncwarp();
-    if (lane == 0) st_release(prog + sbr, P.prog_base + (uint32_t)(sbc + 1));
-    published = sbc + 1;
     }
   }
   if (published < P.sb_cols && lane == 0) st_release(prog + sbr, P.prog_base + (uint32_t)P.sb_cols);
@@ -1601,6 +1684,8 @@ struct vp9gpu_ctx {
   uint32_t *d_tickets = nullptr;  // wavefront progress counters
   uint32_t epoch = 0;
   uint8_t *d_out8 = nullptr;      // staging for 8-bit output of high-bit-depth frames
+  uint8_t *d_resid = nullptr;     // residual planes of intra blocks
+  size_t resid_bytes = 0;
   size_t out8_bytes = 0;
   uint32_t ticket_lf_base = 0, ticket_intra_base = 0;   // running totals of tickets handed out
   // tickets (vp9gpu_mark / vp9gpu_wait)
@@ -1681,6 +1766,7 @@ extern "C" void vp9gpu_destroy(vp9gpu_ctx *ctx) {
     for (int i = 0; i < vp9gpu_ctx::kTickets; i++) cudaEventDestroy(ctx->ticket_ev[i]);
   cudaFree(ctx->d_mi);
   cudaFree(ctx->d_out8);
+  cudaFree(ctx->d_resid);
   cudaFree(ctx->d_tickets);
   cudaStreamDestroy(ctx->stream);
   delete ctx;
@@ -1868,6 +1954,9 @@ static int launch_stages(vp9gpu_ctx *ctx, const FrameParams &P, const vp9b_frame
         cudaFuncSetAttribute(k_intra<Px, PT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ismem);
         attr_set = true;
       }
+      const int rblocks = std::min((int)((n_intra + kResWarps - 1) / kResWarps), ctx->num_sms * 8);
+      k_intra_residual<Px, PT><<<rblocks, kResWarps * 32, 0, st>>>(P);
+      ctx->launches++;
       k_intra<Px, PT><<<wave_blocks, kWaveWarps * 32, ismem, st>>>(P);
       ctx->ticket_intra_base += (uint32_t)wave_blocks;
       ctx->launches++;
@@ -1978,7 +2067,29 @@ static int submit_device(vp9gpu_ctx *ctx, const uint8_t *d_packed, const vp9b_fr
     ctx->err = "inter transform block counts do not add up";
     return VP9B_ERR_INVALID;
   }
-  for (int p = 0; p < 3; p++) P.txb_intra[p] = (const vp9b_txb *)(d_packed + h->sec[VP9B_SEC_TXB_INTRA_Y + p].offset);
+  for (int p = 0; p < 3; p++) {
+    P.txb_intra[p] = (const vp9b_txb *)(d_packed + h->sec[VP9B_SEC_TXB_INTRA_Y + p].offset);
+    P.n_txb_intra[p] = (int)h->sec[VP9B_SEC_TXB_INTRA_Y + p].count;
+  }
+  if (P.n_txb_intra[0] + P.n_txb_intra[1] + P.n_txb_intra[2]) {
+    // residual planes: same sample stride and rows as the destination planes
+    const size_t rsz = h->bit_depth > 8 ? 4 : 2;
+    size_t off[3], total = 0;
+    for (int p = 0; p < 3; p++) {
+      const int rows = (int)((((h->height + 7) & ~7u) >> (p ? h->ss_y : 0)) + 64);
+      off[p] = total;
+      total += ((size_t)D.pl[p].stride * rows * rsz + 255) & ~(size_t)255;
+    }
+    if (ctx->resid_bytes < total) {
+      CK(cudaStreamSynchronize(ctx->stream));
+      cudaFree(ctx->d_resid);
+      ctx->d_resid = nullptr;
+      ctx->resid_bytes = 0;
+      CK(cudaMalloc(&ctx->d_resid, total));
+      ctx->resid_bytes = total;
+    }
+    for (int p = 0; p < 3; p++) P.resid[p] = ctx->d_resid + off[p];
+  }
   P.sb_intra = (const vp9b_sbrange *)(d_packed + h->sec[VP9B_SEC_SB_INTRA].offset);
   P.coef = d_packed + h->sec[VP9B_SEC_COEF].offset;
   P.lfm = (const vp9b_lfm *)(d_packed + h->sec[VP9B_SEC_LFM].offset);
