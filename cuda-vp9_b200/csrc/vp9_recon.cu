@@ -1467,7 +1467,8 @@ __global__ void __launch_bounds__(NW + 64, NW == 128 ? 3 : 2) k_loopfilter(const
   // per-thread vector slots are fixed across superblocks: precompute plane / offsets once.  Slot
   // (row, v) holds columns 8v..8v+7 of the superblock; the v = 0 slot is also the one that loads
   // the look-ahead columns (64.. of the tile = 0..7 of c+1) and moves them to the front.
-  int int_goff[kMaxInt], int_soff[kMaxInt], int_pl[kMaxInt], int_first[kMaxInt];
+  Px *int_gp[kMaxInt];   // global address of the slot in superblock column 0 (advance: sbc * 64 or nC samples)
+  int int_soff[kMaxInt], int_pl[kMaxInt], int_first[kMaxInt];
 #pragma unroll
   for (int k = 0; k < kMaxInt; k++) {
     const int i = tid + k * nworkers;
@@ -1476,18 +1477,19 @@ __global__ void __launch_bounds__(NW + 64, NW == 128 ? 3 : 2) k_loopfilter(const
     if (i < nInt) {
       const Px *g; Px *sm;
       vec_addr(i, false, g, sm, int_pl[k], int_first[k]);
-      int_goff[k] = (int)(g - (const Px *)P.dst[int_pl[k]].ptr);
+      int_gp[k] = (Px *)g;
       int_soff[k] = (int)(sm - tile);
     }
   }
+  auto wptr = [&](int k, int sbc) -> Px * { return int_gp[k] + sbc * (int_pl[k] ? nC : 64); };
   Vec pre[kMaxInt];
   // registers <- interior of superblock sbc (columns 8..63) and the first 8 columns of sbc+1
   auto prefetch = [&](int sbc) {
 #pragma unroll
     for (int k = 0; k < kMaxInt; k++)
       if (int_pl[k] >= 0) {
-        if (!int_first[k]) pre[k] = __ldcg((const Vec *)gptr(int_pl[k], int_goff[k], sbc));
-        else if (sbc + 1 < sb_cols) pre[k] = __ldcg((const Vec *)gptr(int_pl[k], int_goff[k], sbc + 1));
+        if (!int_first[k]) pre[k] = __ldcg((const Vec *)wptr(k, sbc));
+        else if (sbc + 1 < sb_cols) pre[k] = __ldcg((const Vec *)wptr(k, sbc + 1));
       }
   };
   // vertical edge c (0..7) of the superblock described by M at row pointer `row` (sample 0 of
@@ -1551,7 +1553,7 @@ __global__ void __launch_bounds__(NW + 64, NW == 128 ? 3 : 2) k_loopfilter(const
         if (!int_first[k]) smem_put(tile + int_soff[k], pre[k]);
         else {
           if (has_next) smem_put(tile + int_soff[k] + (int_pl[k] ? nC : 64), pre[k]);
-          if (!carry_valid) smem_put(tile + int_soff[k], __ldcg((const Vec *)gptr(int_pl[k], int_goff[k], sbc)));
+          if (!carry_valid) smem_put(tile + int_soff[k], __ldcg((const Vec *)wptr(k, sbc)));
         }
       }
     // ---- prefetch the next step (nobody else touches those samples before this CTA is done with them)
@@ -1564,50 +1566,51 @@ __global__ void __launch_bounds__(NW + 64, NW == 128 ? 3 : 2) k_loopfilter(const
     LFT(3)
     bar_sync(2, n_b2);       // B2: + halo rows
     LFT(4)
-    // ---- horizontal edges of c: thread = sample column
+    // ---- horizontal edges of c: thread = sample column.  The masks are tested at bit (row, column)
+    // directly; only a 16-wide edge needs its whole mask row (pairing)
     if (w0) {
-      const int x = my_idx, c = x >> 3;
-      Px *col = T + x;
-      for (int r = 0; r < nb; r++) {
-        const int mrow = uvsub ? 2 * r : r;
-        if (mi_row + mrow >= P.mi_rows) break;
-        uint32_t row16, row8, row4, row4i;
-        const uint8_t *lfl;
-        int lstep;
-        if (!uvsub) {
-          row16 = (uint32_t)(M.above_y[2] >> (r * 8)) & 0xff;
-          row8 = (uint32_t)(M.above_y[1] >> (r * 8)) & 0xff;
-          row4 = (uint32_t)(M.above_y[0] >> (r * 8)) & 0xff;
-          row4i = (uint32_t)(M.int_4x4_y >> (r * 8)) & 0xff;
-          lfl = &M.lfl_y[r * 8];
-          lstep = 1;
-        } else {
-          row16 = (uint32_t)(M.above_uv[2] >> (r * 4)) & 0xf;
-          row8 = (uint32_t)(M.above_uv[1] >> (r * 4)) & 0xf;
-          row4 = (uint32_t)(M.above_uv[0] >> (r * 4)) & 0xf;
-          row4i = (uint32_t)(M.int_4x4_uv >> (r * 4)) & 0xf;
-          if (mi_row + mrow == P.mi_rows - 1) row4i = 0;  // skip_border_4x4_r
-          lfl = &M.lfl_y[(2 * r) * 8];
-          lstep = 2;
-        }
-        if (mi_row + mrow == 0) row16 = row8 = row4 = 0;
-        if (!(((row16 | row8 | row4 | row4i) >> c) & 1)) continue;
+      const int c = my_idx >> 3;
+      Px *col = T + my_idx;
+      uint64_t a16, a8, a4, ai;
+      int rsh, lstep;
+      if (!uvsub) {
+        a16 = M.above_y[2]; a8 = M.above_y[1]; a4 = M.above_y[0]; ai = M.int_4x4_y;
+        rsh = 3; lstep = 1;
+      } else {
+        a16 = M.above_uv[2]; a8 = M.above_uv[1]; a4 = M.above_uv[0]; ai = M.int_4x4_uv;
+        rsh = 2; lstep = 2;
+      }
+      if (mi_row == 0) {   // no edge on the frame's top row (the inner 4x4 edge stays)
+        const uint64_t keep = ~(uint64_t)((1u << (1 << rsh)) - 1);
+        a16 &= keep; a8 &= keep; a4 &= keep;
+      }
+      // rows of this superblock inside the frame; 4:2:0 drops the inner edge of the last odd row
+      const int rows_left = P.mi_rows - mi_row;
+      const int nrow = uvsub ? min(nb, (rows_left + 1) >> 1) : min(nb, rows_left);
+      if (uvsub && (rows_left & 1) && rows_left < 8) ai &= ~((uint64_t)0xf << (4 * (rows_left >> 1)));  // skip_border_4x4_r
+      for (int r = 0; r < nrow; r++) {
+        const int bit = (r << rsh) + c;
+        const uint32_t k16 = (uint32_t)(a16 >> bit) & 1, k8 = (uint32_t)(a8 >> bit) & 1, k4 = (uint32_t)(a4 >> bit) & 1,
+                       ki = (uint32_t)(ai >> bit) & 1;
+        if (!(k16 | k8 | k4 | ki)) continue;
         Px *s = col + r * 8 * ts;
+        const uint8_t *lfl = &M.lfl_y[(r * lstep) * 8];
         const int lvl = lfl[c * lstep];
-        if ((row16 >> c) & 1) {
+        if (k16) {
           // greedy pairing from the left (vpx_lpf_horizontal_16_dual): the second block of a
-          // pair is filtered with the first block's thresholds
-          int start = c;
-          while (start > 0 && ((row16 >> (start - 1)) & 1)) start--;
-          const int lv = ((c - start) & 1) ? lfl[(c - 1) * lstep] : lvl;
+          // pair is filtered with the first block's thresholds.  run = number of set bits directly
+          // below column c in this mask row
+          const uint32_t row16 = (uint32_t)(a16 >> (r << rsh)) & 0xff;
+          const uint32_t below = ~row16 & ((1u << c) - 1);          // zero bits below c
+          const int run = below ? c - 1 - (31 - __clz(below)) : c;
+          const int lv = (run & 1) ? lfl[(c - 1) * lstep] : lvl;
           lf_px<Px>(s, ts, 16, P.lf_mblim[lv], P.lf_lim[lv], lv >> 4, P.bd);
-        } else if ((row8 >> c) & 1) {
+        } else if (k8) {
           lf_px<Px>(s, ts, 8, P.lf_mblim[lvl], P.lf_lim[lvl], lvl >> 4, P.bd);
-        } else if ((row4 >> c) & 1) {
+        } else if (k4) {
           lf_px<Px>(s, ts, 4, P.lf_mblim[lvl], P.lf_lim[lvl], lvl >> 4, P.bd);
         }
-        if (!((row16 >> c) & 1) && ((row4i >> c) & 1))
-          lf_px<Px>(s + 4 * ts, ts, 4, P.lf_mblim[lvl], P.lf_lim[lvl], lvl >> 4, P.bd);
+        if (!k16 && ki) lf_px<Px>(s + 4 * ts, ts, 4, P.lf_mblim[lvl], P.lf_lim[lvl], lvl >> 4, P.bd);
       }
     }
     LFT(5)
@@ -1622,7 +1625,7 @@ __global__ void __launch_bounds__(NW + 64, NW == 128 ? 3 : 2) k_loopfilter(const
       if (int_pl[k] >= 0) {
         Vec vv;
         smem_get(tile + int_soff[k], vv);
-        __stcg((Vec *)gptr(int_pl[k], int_goff[k], sbc), vv);
+        __stcg((Vec *)wptr(k, sbc), vv);
         if (int_first[k] && has_next) {
           smem_get(tile + int_soff[k] + (int_pl[k] ? nC : 64), vv);
           smem_put(tile + int_soff[k], vv);
