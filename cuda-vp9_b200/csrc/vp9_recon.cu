@@ -1236,18 +1236,19 @@ VP9B_DEV void lf_px(Px *s, int step, int size, int blimit, int limit, int thresh
   const int p3 = s[-4 * step], p2 = s[-3 * step], p1 = s[-2 * step], p0 = s[-step];
   const int q0 = s[0], q1 = s[step], q2 = s[2 * step], q3 = s[3 * step];
   const int lim16 = limit << sh, blim16 = blimit << sh, one = 1 << sh;
-  const bool fm = !(abs(p3 - p2) > lim16 || abs(p2 - p1) > lim16 || abs(p1 - p0) > lim16 || abs(q1 - q0) > lim16 ||
-                    abs(q2 - q1) > lim16 || abs(q3 - q2) > lim16 || abs(p0 - q0) * 2 + abs(p1 - q1) / 2 > blim16);
+  // masks as max chains: no short-circuit branches, |p1-p0| and |q1-q0| shared by all of them
+  const int d10p = abs(p1 - p0), d10q = abs(q1 - q0);
+  const int dmax = max(max(max(abs(p3 - p2), abs(p2 - p1)), max(abs(q2 - q1), abs(q3 - q2))), max(d10p, d10q));
+  const bool fm = dmax <= lim16 && abs(p0 - q0) * 2 + (abs(p1 - q1) >> 1) <= blim16;
   if (!fm) return;  // filter_mask == 0: every variant leaves the samples untouched
   bool flat = false;
   if (size >= 8)
-    flat = !(abs(p1 - p0) > one || abs(q1 - q0) > one || abs(p2 - p0) > one || abs(q2 - q0) > one ||
-             abs(p3 - p0) > one || abs(q3 - q0) > one);
+    flat = max(max(max(d10p, d10q), max(abs(p2 - p0), abs(q2 - q0))), max(abs(p3 - p0), abs(q3 - q0))) <= one;
   if (size == 16 && flat) {
     const int p7 = s[-8 * step], p6 = s[-7 * step], p5 = s[-6 * step], p4 = s[-5 * step];
     const int q4 = s[4 * step], q5 = s[5 * step], q6 = s[6 * step], q7 = s[7 * step];
-    const bool flat2 = !(abs(p4 - p0) > one || abs(q4 - q0) > one || abs(p5 - p0) > one || abs(q5 - q0) > one ||
-                         abs(p6 - p0) > one || abs(q6 - q0) > one || abs(p7 - p0) > one || abs(q7 - q0) > one);
+    const bool flat2 = max(max(max(abs(p4 - p0), abs(q4 - q0)), max(abs(p5 - p0), abs(q5 - q0))),
+                           max(max(abs(p6 - p0), abs(q6 - q0)), max(abs(p7 - p0), abs(q7 - q0)))) <= one;
     if (flat2) {
       // 15-tap [1,1,1,1,1,1,1,2,1,1,1,1,1,1,1] with edge replication, evaluated from prefix
       // sums so that the 14 outputs are independent of each other (short dependency chain)
@@ -1281,7 +1282,7 @@ VP9B_DEV void lf_px(Px *s, int step, int size, int blimit, int limit, int thresh
   const int off = 0x80 << sh;
   const int ps1 = p1 - off, ps0 = p0 - off, qs0 = q0 - off, qs1 = q1 - off;
   const int t16 = thresh << sh;
-  const int hev = (abs(p1 - p0) > t16 || abs(q1 - q0) > t16) ? -1 : 0;
+  const int hev = max(d10p, d10q) > t16 ? -1 : 0;
   int f = sc_clamp(ps1 - qs1, bd) & hev;
   f = sc_clamp(f + 3 * (qs0 - ps0), bd);
   const int f1 = sc_clamp(f + 4, bd) >> 3, f2 = sc_clamp(f + 3, bd) >> 3;
