@@ -1231,7 +1231,8 @@ VP9B_DEV int sc_clamp(int t, int bd) {
 
 // s: pointer to q0 in the tile; step: distance between taps
 template <typename Px>
-VP9B_DEV void lf_px(Px *s, int step, int size, int blimit, int limit, int thresh, int bd) {
+VP9B_DEV void lf_px(Px *s, int step, int size, int blimit, int limit, int thresh, int bd_) {
+  const int bd = sizeof(Px) == 1 ? 8 : bd_;   // 8-bit samples: every shift below folds away
   const int sh = bd - 8;
   const int p3 = s[-4 * step], p2 = s[-3 * step], p1 = s[-2 * step], p0 = s[-step];
   const int q0 = s[0], q1 = s[step], q2 = s[2 * step], q3 = s[3 * step];
