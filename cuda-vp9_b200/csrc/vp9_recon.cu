@@ -414,18 +414,20 @@ VP9B_DEV void inter_pred_u8_body(const FrameParams &P, int plane, int bx_, int b
 
 // All three planes in one launch: a flat grid of CTAs, luma tiles (32x128 samples) first, then
 // the two chroma planes (4:2:0: 32x64-sample tiles of 4x4 units; 4:4:4: same as luma).
-__global__ void __launch_bounds__(128, 8) k_inter_pred_u8(const __grid_constant__ FrameParams P, int ncta_y, int ncta_c,
-                                                       int gx_y, int gx_c) {
-  int b = blockIdx.x, plane = 0, gx = gx_y;
-  if (b >= ncta_y) {
-    b -= ncta_y;
-    plane = 1 + b / ncta_c;
-    b %= ncta_c;
-    gx = gx_c;
+__global__ void __launch_bounds__(128, 8) k_inter_pred_u8(const __grid_constant__ FrameParams P, int gy_y, int gy_c,
+                                                         int gx_c) {
+  // grid = (tiles across the luma plane, luma tile rows + 2 x chroma tile rows): plane and tile come
+  // from blockIdx without divisions; chroma rows use the first gx_c columns only
+  int by = blockIdx.y, plane = 0;
+  if (by >= gy_y) {
+    by -= gy_y;
+    plane = 1;
+    if (by >= gy_c) { by -= gy_c; plane = 2; }
+    if ((int)blockIdx.x >= gx_c) return;
   }
   // one call site per unit height keeps the kernel inside the instruction cache
-  if (plane && P.ss_x) inter_pred_u8_body<4>(P, plane, b % gx, b / gx);
-  else inter_pred_u8_body<8>(P, plane, b % gx, b / gx);
+  if (plane && P.ss_x) inter_pred_u8_body<4>(P, plane, blockIdx.x, by);
+  else inter_pred_u8_body<8>(P, plane, blockIdx.x, by);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -628,17 +630,17 @@ VP9B_DEV void inter_pred_u16_body(const FrameParams &P, int plane, int bx_, int 
   for (int i = 0; i < H; i++) *(uint2 *)(dst + (size_t)i * dstride) = o[i];
 }
 
-__global__ void __launch_bounds__(128, 4) k_inter_pred_u16(const __grid_constant__ FrameParams P, int ncta_y, int ncta_c,
-                                                          int gx_y, int gx_c) {
-  int b = blockIdx.x, plane = 0, gx = gx_y;
-  if (b >= ncta_y) {
-    b -= ncta_y;
-    plane = 1 + b / ncta_c;
-    b %= ncta_c;
-    gx = gx_c;
+__global__ void __launch_bounds__(128, 4) k_inter_pred_u16(const __grid_constant__ FrameParams P, int gy_y, int gy_c,
+                                                          int gx_c) {
+  int by = blockIdx.y, plane = 0;
+  if (by >= gy_y) {
+    by -= gy_y;
+    plane = 1;
+    if (by >= gy_c) { by -= gy_c; plane = 2; }
+    if ((int)blockIdx.x >= gx_c) return;
   }
-  if (plane && P.ss_x) inter_pred_u16_body<4>(P, plane, b % gx, b / gx);
-  else inter_pred_u16_body<8>(P, plane, b % gx, b / gx);
+  if (plane && P.ss_x) inter_pred_u16_body<4>(P, plane, blockIdx.x, by);
+  else inter_pred_u16_body<8>(P, plane, blockIdx.x, by);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1930,9 +1932,9 @@ static int launch_stages(vp9gpu_ctx *ctx, const FrameParams &P, const vp9b_frame
       const int pwc = pwy >> P.ss_x, phc = phy >> P.ss_y;
       const int gx_y = (pwy + 31) / 32, gy_y = (phy + 127) / 128;
       const int gx_c = (pwc + 31) / 32, gy_c = P.ss_x ? (phc + 63) / 64 : (phc + 127) / 128;
-      const int ncta_y = gx_y * gy_y, ncta_c = gx_c * gy_c;
-      if (sizeof(Px) == 1) k_inter_pred_u8<<<ncta_y + 2 * ncta_c, 128, 0, st>>>(P, ncta_y, ncta_c, gx_y, gx_c);
-      else k_inter_pred_u16<<<ncta_y + 2 * ncta_c, 128, 0, st>>>(P, ncta_y, ncta_c, gx_y, gx_c);
+      const dim3 grid(gx_y, gy_y + 2 * gy_c);
+      if (sizeof(Px) == 1) k_inter_pred_u8<<<grid, 128, 0, st>>>(P, gy_y, gy_c, gx_c);
+      else k_inter_pred_u16<<<grid, 128, 0, st>>>(P, gy_y, gy_c, gx_c);
       ctx->launches++;
     }
     if (prof) cudaEventRecord(ctx->prof_ev[2], st);
