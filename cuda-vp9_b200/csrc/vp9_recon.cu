@@ -1516,14 +1516,19 @@ __global__ void __launch_bounds__(NW + 64, NW == 128 ? 3 : 2) k_loopfilter(const
     }
     m16 &= sel_edge; m8 &= sel_edge; m4 &= sel_edge; m4i &= sel_inner;
     uint32_t all = m16 | m8 | m4 | m4i;
+    if (!all) return;
+    // the eight levels of this mask row (and of the first row of the pair) in two loads, so that no
+    // edge of the chain waits for a level byte
+    const int lrow = uvsub ? 2 * r8 : r8, prow = uvsub ? 2 * pr : pr, lsh = uvsub ? 16 : 8;
+    const uint64_t lv_own = *(const uint64_t *)&M.lfl_y[lrow * 8], lv_pair = *(const uint64_t *)&M.lfl_y[prow * 8];
     while (all) {
       const int c = __ffs(all) - 1;
       all &= all - 1;
-      const int lo = uvsub ? M.lfl_y[(2 * r8) * 8 + 2 * c] : M.lfl_y[r8 * 8 + c];
+      const int lo = (int)(lv_own >> (c * lsh)) & 0xff;
       Px *s = row + c * 8;
       if ((m16 >> c) & 1) {
         // dual 16 (both rows of the pair set): both bands use the first band's level
-        const int lv = ((m16n >> c) & 1) ? (uvsub ? M.lfl_y[(2 * pr) * 8 + 2 * c] : M.lfl_y[pr * 8 + c]) : lo;
+        const int lv = ((m16n >> c) & 1) ? ((int)(lv_pair >> (c * lsh)) & 0xff) : lo;
         lf_px<Px>(s, 1, 16, P.lf_mblim[lv], P.lf_lim[lv], lv >> 4, P.bd);
       } else if ((m8 >> c) & 1) {
         lf_px<Px>(s, 1, 8, P.lf_mblim[lo], P.lf_lim[lo], lo >> 4, P.bd);
@@ -1592,6 +1597,11 @@ __global__ void __launch_bounds__(NW + 64, NW == 128 ? 3 : 2) k_loopfilter(const
       const int rows_left = P.mi_rows - mi_row;
       const int nrow = uvsub ? min(nb, (rows_left + 1) >> 1) : min(nb, rows_left);
       if (uvsub && (rows_left & 1) && rows_left < 8) ai &= ~((uint64_t)0xf << (4 * (rows_left >> 1)));  // skip_border_4x4_r
+      // levels of this column for the eight mask rows, gathered up front (independent loads)
+      uint64_t lv_col = 0;
+#pragma unroll
+      for (int r = 0; r < 8; r++)
+        if (r < nrow) lv_col |= (uint64_t)M.lfl_y[(r * lstep) * 8 + c * lstep] << (8 * r);
       for (int r = 0; r < nrow; r++) {
         const int bit = (r << rsh) + c;
         const uint32_t k16 = (uint32_t)(a16 >> bit) & 1, k8 = (uint32_t)(a8 >> bit) & 1, k4 = (uint32_t)(a4 >> bit) & 1,
@@ -1599,7 +1609,7 @@ __global__ void __launch_bounds__(NW + 64, NW == 128 ? 3 : 2) k_loopfilter(const
         if (!(k16 | k8 | k4 | ki)) continue;
         Px *s = col + r * 8 * ts;
         const uint8_t *lfl = &M.lfl_y[(r * lstep) * 8];
-        const int lvl = lfl[c * lstep];
+        const int lvl = (int)(lv_col >> (8 * r)) & 0xff;
         if (k16) {
           // greedy pairing from the left (vpx_lpf_horizontal_16_dual): the second block of a
           // pair is filtered with the first block's thresholds.  run = number of set bits directly
