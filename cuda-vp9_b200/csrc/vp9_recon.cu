@@ -1322,9 +1322,9 @@ VP9B_DEV void bar_sync(int id, int nthreads) {
 }
 
 template <typename Px, int NW>
-__global__ void __launch_bounds__(NW + 64, NW == 128 ? 3 : 2) k_loopfilter(const __grid_constant__ FrameParams P) {
+__global__ void __launch_bounds__(NW + 64 + NW / 2, NW == 128 ? 3 : 2) k_loopfilter(const __grid_constant__ FrameParams P) {
   // One persistent CTA per superblock ROW walks its row left to right: 4 (4:2:0) or 6 (4:4:4)
-  // worker warps filter, a halo warp and a publish warp talk to the neighbouring rows.
+  // worker warps only filter; a halo warp and two mover warps do all the global traffic.
   //
   // libvpx filters superblock by superblock: all vertical edges of c, all horizontal edges of c,
   // then c+1 (vp9_loopfilter.c:1440-1467).  The only operation of c+1 that touches samples of c
@@ -1333,30 +1333,32 @@ __global__ void __launch_bounds__(NW + 64, NW == 128 ? 3 : 2) k_loopfilter(const
   // which is the same order along every sample row and column, and leaves superblock c final at
   // the end of its own step: the row below can start on c one step (not two) behind.
   //
-  //   workers, per superblock c (tile = 64 columns of c + the first 8 of c+1, all planes):
-  //     staged interior -> shared | B1 | vertical edges (thread = sample row) | B2 | horizontal
-  //     edges (thread = sample column) | B3 | left edge of c+1 | B5 | store the 64 columns of c,
-  //     move the 8 look-ahead columns to the front | B6.
-  //     The interior of c+1 is prefetched into registers while c is filtered, and a thread
-  //     stores and re-fills only its own shared-memory slots, so nothing separates two steps.
-  //   halo warp: waits until the row above has published superblock c, loads the 8 rows above
-  //     it into shared memory while the workers are in the vertical pass | B2 | B3 | stores the
-  //     (now filtered) rows back.
-  //   publish warp: B6 (all stores of c issued) -> st.release "c+1 superblocks final".
+  // Two tile buffers (64 columns of c + the first 8 of c+1, all planes) alternate:
+  //   workers, step c on buffer X:   vertical edges (thread = sample row) | B2 | horizontal edges
+  //     (thread = sample column) | B3 | left edge of c+1, copy the 8 look-ahead columns to the
+  //     front of the other buffer Y | B5.  No loads, no stores, three barriers.
+  //   movers, during step c:  store tile c-1 from Y to global and publish it (st.release), then
+  //     fill Y with superblock c+1 (prefetched into registers a step earlier) and prefetch c+2
+  //     | B3 | B5.
+  //   halo warp: waits until the row above has published superblock c, loads the 8 rows above it
+  //     into X while the workers are in the vertical pass | B2 | B3 | stores the filtered rows back.
+  // Only the first horizontal edge of a superblock depends on the row above, and only the halo
+  // warp ever waits for it.
   extern __shared__ __align__(16) unsigned char lf_smem[];
-  Px *tile = (Px *)lf_smem;
   typedef typename LfVec<Px>::T Vec;
   constexpr int nworkers = NW;   // 128: 4:2:0, 192: 4:4:4
+  constexpr int kMovers = NW / 2;   // 64 / 96 threads move the tiles
   const int tid = threadIdx.x;
-  const int n_b2 = nworkers + 32, n_b3 = nworkers + 32, n_b6 = nworkers + 32;
+  constexpr int n_b2 = NW + 32, n_b3 = NW + 32 + kMovers, n_b5 = NW + kMovers, n_b7 = kMovers + 32;
   const int lane = tid & 31;
   constexpr bool sub = NW == 128;  // 4:2:0 (else 4:4:4)
   // stride in samples: (stride bytes / 4) odd -> conflict-free row-per-thread walks
   constexpr int tsY = sizeof(Px) == 1 ? 76 : 74, tsC = sub ? (sizeof(Px) == 1 ? 44 : 42) : tsY;
   constexpr int nC = sub ? 32 : 64;
   constexpr int offU = 72 * tsY, offV = 72 * tsY + (nC + 8) * tsC;
-  // has-work flag per superblock of this row, computed once (the loops below look two ahead)
-  uint8_t *wk = (uint8_t *)(tile + offV + (nC + 8) * tsC) + 16;
+  constexpr int kTileSamples = offV + (nC + 8) * tsC + 8;       // one buffer (all planes), padded
+  Px *const tiles = (Px *)lf_smem;
+  auto buf = [&](int c) -> Px * { return tiles + (c & 1) * kTileSamples; };
   __shared__ int s_row;
   if (threadIdx.x == 0) s_row = (int)(atomicAdd(P.ticket_lf, 1u) - P.ticket_lf_base);
   __syncthreads();
@@ -1371,9 +1373,9 @@ __global__ void __launch_bounds__(NW + 64, NW == 128 ? 3 : 2) k_loopfilter(const
   constexpr int nInt = vY + 2 * vC;
   constexpr int hYv = 8 * 8, hCv = 8 * (nC >> 3);         // top-halo vectors per plane
   constexpr int nHalo = hYv + 2 * hCv;
-  constexpr int kMaxInt = (nInt + NW - 1) / NW, kMaxHalo = (nHalo + 31) / 32;  // slots per worker thread / halo lane
-  auto vec_addr = [&](int i, bool halo, const Px *&g, Px *&sm, int &pl, int &first) {
-    // flat vector index -> global address (superblock column 0), shared address, plane
+  constexpr int kMaxInt = (nInt + kMovers - 1) / kMovers, kMaxHalo = (nHalo + 31) / 32;  // slots per mover thread / halo lane
+  auto vec_addr = [&](int i, bool halo, const Px *&g, int &soff, int &pl, int &first) {
+    // flat vector index -> global address (superblock column 0), offset inside a tile buffer, plane
     int p, r, v;
     const int a = halo ? hYv : vY, bq = halo ? hCv : vC;
     if (i < a) { p = 0; }
@@ -1385,77 +1387,132 @@ __global__ void __launch_bounds__(NW + 64, NW == 128 ? 3 : 2) k_loopfilter(const
     if (halo) r -= 8;
     const int stride = P.dst[p].stride;
     g = (const Px *)P.dst[p].ptr + (ptrdiff_t)(sbr * pn + r) * stride + v * 8;
-    sm = tile + (p == 0 ? 0 : (p == 1 ? offU : offV)) + (8 + r) * pts + v * 8;
+    soff = (p == 0 ? 0 : (p == 1 ? offU : offV)) + (8 + r) * pts + v * 8;
     pl = p;
   };
-  for (int c = tid; c < sb_cols + 2; c += NW + 64) {
-    bool w = false;
-    if (c < sb_cols) {
-      const vp9b_lfm &M = P.lfm[sbr * sb_cols + c];
-      const uint64_t anyY = M.left_y[0] | M.left_y[1] | M.left_y[2] | M.above_y[0] | M.above_y[1] | M.above_y[2] | M.int_4x4_y;
-      const uint32_t anyUV = M.left_uv[0] | M.left_uv[1] | M.left_uv[2] | M.above_uv[0] | M.above_uv[1] | M.above_uv[2] | M.int_4x4_uv;
-      w = (anyY | anyUV) != 0;
-    }
-    wk[c] = w;
-  }
-  __syncthreads();
-  auto has_work = [&](int sbc) -> bool { return wk[sbc] != 0; };   // valid up to sb_cols + 1
-  auto gptr = [&](int pl, int goff, int sbc) -> Px * { return (Px *)P.dst[pl].ptr + goff + sbc * (pl ? nC : 64); };
 
-  if (tid >= nworkers + 32) {
+  if (tid >= nworkers + 32 && tid < nworkers + 64) {
     // ------------------------------------------------------------------ publish warp
-    for (int sbc = 0; sbc < sb_cols; sbc++) {
-      // The workers join this barrier with bar.sync too: the publish warp is normally waiting here
-      // already, so they do not stall, and they can never run a second step into the barrier
-      // while a release is still in flight.
-      bar_sync(6, n_b6);                 // every store of superblock sbc has been issued
-      if (lane == 0) st_release(prog + sbr, base + (uint32_t)(sbc + 1));
+    // waits until the movers have issued every store of a superblock, then releases it to the row
+    // below; the fence latency stays off everybody else's path
+    for (int sbc = 1; sbc <= sb_cols; sbc++) {
+      bar_sync(7, n_b7);
+      if (lane == 0) st_release(prog + sbr, base + (uint32_t)sbc);
     }
+    return;
+  }
+  if (tid >= nworkers + 64) {
+    // ------------------------------------------------------------------ mover warps
+    const int mt = tid - (nworkers + 64);
+    Px *int_gp[kMaxInt];   // global address of the slot in superblock column 0 (advance: sbc * 64 or nC samples)
+    int int_soff[kMaxInt], int_pl[kMaxInt], int_first[kMaxInt];
+#pragma unroll
+    for (int k = 0; k < kMaxInt; k++) {
+      const int i = mt + k * kMovers;
+      int_pl[k] = -1;
+      int_first[k] = 0;
+      if (i < nInt) {
+        const Px *g;
+        vec_addr(i, false, g, int_soff[k], int_pl[k], int_first[k]);
+        int_gp[k] = (Px *)g;
+      }
+    }
+    auto wptr = [&](int k, int sbc) -> Px * { return int_gp[k] + sbc * (int_pl[k] ? nC : 64); };
+    Vec pre[kMaxInt];
+    // registers <- columns 8..63 of superblock sbc and the first 8 columns of sbc+1 (the slot that
+    // holds columns 0..7 fetches the look-ahead columns instead: 0..7 arrive through the carry)
+    auto prefetch = [&](int sbc) {
+#pragma unroll
+      for (int k = 0; k < kMaxInt; k++)
+        if (int_pl[k] >= 0) {
+          if (!int_first[k]) pre[k] = __ldcg((const Vec *)wptr(k, sbc));
+          else if (sbc + 1 < sb_cols) pre[k] = __ldcg((const Vec *)wptr(k, sbc + 1));
+        }
+    };
+    auto fill = [&](int sbc) {      // registers -> tile buffer of superblock sbc
+      Px *t = buf(sbc);
+#pragma unroll
+      for (int k = 0; k < kMaxInt; k++)
+        if (int_pl[k] >= 0) {
+          if (!int_first[k]) smem_put(t + int_soff[k], pre[k]);
+          else if (sbc + 1 < sb_cols) smem_put(t + int_soff[k] + (int_pl[k] ? nC : 64), pre[k]);
+        }
+    };
+    auto store = [&](int sbc) {     // tile buffer of superblock sbc (all 64 columns final) -> global
+      const Px *t = buf(sbc);
+#pragma unroll
+      for (int k = 0; k < kMaxInt; k++)
+        if (int_pl[k] >= 0) {
+          Vec vv;
+          smem_get(t + int_soff[k], vv);
+          __stcg((Vec *)wptr(k, sbc), vv);
+        }
+    };
+    // prologue: superblock 0 completely (its columns 0..7 have no carry), then prefetch 1
+    prefetch(0);
+    {
+      Px *t = buf(0);
+#pragma unroll
+      for (int k = 0; k < kMaxInt; k++)
+        if (int_pl[k] >= 0 && int_first[k]) smem_put(t + int_soff[k], __ldcg((const Vec *)wptr(k, 0)));
+    }
+    fill(0);
+    if (sb_cols > 1) prefetch(1);
+    bar_sync(5, n_b5);                   // "B5(-1)": buffer 0 is ready
+    for (int sbc = 0; sbc < sb_cols; sbc++) {
+      if (sbc >= 1) {
+        store(sbc - 1);
+        bar_sync(7, n_b7);               // every store of superblock sbc-1 has been issued: publish warp's turn
+      }
+      if (sbc + 1 < sb_cols) {
+        fill(sbc + 1);
+        if (sbc + 2 < sb_cols) prefetch(sbc + 2);
+      }
+      bar_sync(3, n_b3);                 // B3: our reads of the other buffer are done (the carry may write it)
+      bar_sync(5, n_b5);                 // B5: buffer of sbc is final, buffer of sbc+1 is filled
+    }
+    store(sb_cols - 1);
+    bar_sync(7, n_b7);
     return;
   }
   if (tid >= nworkers) {
     // ------------------------------------------------------------------ halo warp
-    int h_goff[kMaxHalo], h_soff[kMaxHalo], h_pl[kMaxHalo];
+    int h_soff[kMaxHalo], h_pl[kMaxHalo];
+    Px *h_gp[kMaxHalo];
 #pragma unroll
     for (int k = 0; k < kMaxHalo; k++) {
       const int i = lane + k * 32;
       h_pl[k] = -1;
       if (hy && i < nHalo) {
-        const Px *g; Px *sm; int f;
-        vec_addr(i, true, g, sm, h_pl[k], f);
-        h_goff[k] = (int)(g - (const Px *)P.dst[h_pl[k]].ptr);
-        h_soff[k] = (int)(sm - tile);
+        const Px *g; int f;
+        vec_addr(i, true, g, h_soff[k], h_pl[k], f);
+        h_gp[k] = (Px *)g;
       }
     }
     uint32_t seen = base;
-    bool w0 = has_work(0);
     for (int sbc = 0; sbc < sb_cols; sbc++) {
-      const bool w1 = has_work(sbc + 1);
-      if (w0 | w1) {
-        const bool need_halo = hy && w0;
-        if (need_halo) {
-          const int need = sbc + 1;   // the row above has finished superblock sbc
-          if ((int)(seen - base) < need) {
-            while ((int)((seen = ld_relaxed(prog + sbr - 1)) - base) < need) __nanosleep(20);
-            seen = ld_acquire(prog + sbr - 1);
-          }
-#pragma unroll
-          for (int k = 0; k < kMaxHalo; k++)
-            if (h_pl[k] >= 0) smem_put(tile + h_soff[k], __ldcg((const Vec *)gptr(h_pl[k], h_goff[k], sbc)));
+      Px *t = buf(sbc);
+      if (hy) {
+        const int need = sbc + 1;   // the row above has finished superblock sbc
+        if ((int)(seen - base) < need) {
+          while ((int)((seen = ld_relaxed(prog + sbr - 1)) - base) < need) __nanosleep(20);
+          seen = ld_acquire(prog + sbr - 1);
         }
-        bar_sync(2, n_b2);   // B2: halo rows in place / vertical pass done
-        bar_sync(3, n_b3);   // B3: horizontal pass done
-        if (need_halo) {
 #pragma unroll
-          for (int k = 0; k < kMaxHalo; k++)
-            if (h_pl[k] >= 0) {
-              Vec vv;
-              smem_get(tile + h_soff[k], vv);
-              __stcg((Vec *)gptr(h_pl[k], h_goff[k], sbc), vv);
-            }
-        }
+        for (int k = 0; k < kMaxHalo; k++)
+          if (h_pl[k] >= 0) smem_put(t + h_soff[k], __ldcg((const Vec *)(h_gp[k] + sbc * (h_pl[k] ? nC : 64))));
       }
-      w0 = w1;
+      bar_sync(2, n_b2);   // B2: halo rows in place / vertical pass done
+      bar_sync(3, n_b3);   // B3: horizontal pass done
+      if (hy) {
+#pragma unroll
+        for (int k = 0; k < kMaxHalo; k++)
+          if (h_pl[k] >= 0) {
+            Vec vv;
+            smem_get(t + h_soff[k], vv);
+            __stcg((Vec *)(h_gp[k] + sbc * (h_pl[k] ? nC : 64)), vv);
+          }
+      }
     }
     return;
   }
@@ -1467,35 +1524,7 @@ __global__ void __launch_bounds__(NW + 64, NW == 128 ? 3 : 2) k_loopfilter(const
   else { my_plane = 2; my_idx = tid - 64 - nC; }
   const bool uvsub = my_plane && sub;
   const int n = my_plane ? nC : 64, ts = my_plane ? tsC : tsY, nb = n >> 3;
-  Px *T = tile + (my_plane == 0 ? 0 : (my_plane == 1 ? offU : offV)) + 8 * ts;   // sample (0,0) of superblock c
-  // per-thread vector slots are fixed across superblocks: precompute plane / offsets once.  Slot
-  // (row, v) holds columns 8v..8v+7 of the superblock; the v = 0 slot is also the one that loads
-  // the look-ahead columns (64.. of the tile = 0..7 of c+1) and moves them to the front.
-  Px *int_gp[kMaxInt];   // global address of the slot in superblock column 0 (advance: sbc * 64 or nC samples)
-  int int_soff[kMaxInt], int_pl[kMaxInt], int_first[kMaxInt];
-#pragma unroll
-  for (int k = 0; k < kMaxInt; k++) {
-    const int i = tid + k * nworkers;
-    int_pl[k] = -1;
-    int_first[k] = 0;
-    if (i < nInt) {
-      const Px *g; Px *sm;
-      vec_addr(i, false, g, sm, int_pl[k], int_first[k]);
-      int_gp[k] = (Px *)g;
-      int_soff[k] = (int)(sm - tile);
-    }
-  }
-  auto wptr = [&](int k, int sbc) -> Px * { return int_gp[k] + sbc * (int_pl[k] ? nC : 64); };
-  Vec pre[kMaxInt];
-  // registers <- interior of superblock sbc (columns 8..63) and the first 8 columns of sbc+1
-  auto prefetch = [&](int sbc) {
-#pragma unroll
-    for (int k = 0; k < kMaxInt; k++)
-      if (int_pl[k] >= 0) {
-        if (!int_first[k]) pre[k] = __ldcg((const Vec *)wptr(k, sbc));
-        else if (sbc + 1 < sb_cols) pre[k] = __ldcg((const Vec *)wptr(k, sbc + 1));
-      }
-  };
+  const int toff = (my_plane == 0 ? 0 : (my_plane == 1 ? offU : offV)) + 8 * ts;   // sample (0,0) inside a buffer
   // vertical edge c (0..7) of the superblock described by M at row pointer `row` (sample 0 of
   // that superblock in this thread's row); `edge` selects the 8-aligned edge, `inner` the 4x4 one
   auto v_edges = [&](const vp9b_lfm &M, Px *row, uint32_t sel_edge, uint32_t sel_inner) {
@@ -1540,38 +1569,15 @@ __global__ void __launch_bounds__(NW + 64, NW == 128 ? 3 : 2) k_loopfilter(const
   };
   const bool row_valid = mi_row + (uvsub ? 2 * ((my_idx >> 3) & ~1) : ((my_idx >> 3) & ~1)) < P.mi_rows;
 
-  bool w0 = has_work(0), w1 = has_work(1);
-  bool carry_valid = false;          // tile columns 0..7 hold the (left-edge filtered) start of superblock c
-  if (w0 | w1) prefetch(0);
+  bar_sync(5, n_b5);                     // "B5(-1)": buffer 0 is ready
   for (int sbc = 0; sbc < sb_cols; sbc++) {
-    const bool w2 = has_work(sbc + 2);
     const bool has_next = sbc + 1 < sb_cols;
-    LFT(0)
-    if (!(w0 | w1)) {                // nothing to filter in c, no left edge in c+1
-      bar_sync(6, n_b6);
-      carry_valid = false;
-      if (w1 | w2) prefetch(sbc + 1);
-      w0 = w1; w1 = w2;
-      continue;
-    }
+    Px *T = buf(sbc) + toff;
     const vp9b_lfm &M = P.lfm[sbr * sb_cols + sbc];
-    // ---- (A) staged registers -> shared; columns 0..7 from global only if they were not carried
-#pragma unroll
-    for (int k = 0; k < kMaxInt; k++)
-      if (int_pl[k] >= 0) {
-        if (!int_first[k]) smem_put(tile + int_soff[k], pre[k]);
-        else {
-          if (has_next) smem_put(tile + int_soff[k] + (int_pl[k] ? nC : 64), pre[k]);
-          if (!carry_valid) smem_put(tile + int_soff[k], __ldcg((const Vec *)wptr(k, sbc)));
-        }
-      }
-    // ---- prefetch the next step (nobody else touches those samples before this CTA is done with them)
-    if (w1 | w2) prefetch(sbc + 1);
-    LFT(1)
-    bar_sync(1, nworkers);   // B1 (workers only)
-    LFT(2)
+    constexpr bool w0 = true;
+    LFT(0)
     // ---- vertical edges 1..7 and all inner 4x4 edges of c: thread = sample row
-    if (row_valid && w0) v_edges(M, T + my_idx * ts, 0xfe, 0xff);
+    if (row_valid) v_edges(M, T + my_idx * ts, 0xfe, 0xff);
     LFT(3)
     bar_sync(2, n_b2);       // B2: + halo rows
     LFT(4)
@@ -1630,25 +1636,17 @@ __global__ void __launch_bounds__(NW + 64, NW == 128 ? 3 : 2) k_loopfilter(const
     LFT(5)
     bar_sync(3, n_b3);       // B3
     LFT(6)
-    // ---- left edge of c+1 (reads / writes the last 8 columns of c and the look-ahead columns)
-    if (has_next && w1 && row_valid) v_edges(P.lfm[sbr * sb_cols + sbc + 1], T + my_idx * ts + n, 0x01, 0x00);
-    bar_sync(5, nworkers);   // B5 (workers only)
-    // ---- store the 64 columns of c (all final now); the v = 0 slot then takes the look-ahead columns
-#pragma unroll
-    for (int k = 0; k < kMaxInt; k++)
-      if (int_pl[k] >= 0) {
-        Vec vv;
-        smem_get(tile + int_soff[k], vv);
-        __stcg((Vec *)wptr(k, sbc), vv);
-        if (int_first[k] && has_next) {
-          smem_get(tile + int_soff[k] + (int_pl[k] ? nC : 64), vv);
-          smem_put(tile + int_soff[k], vv);
-        }
-      }
-    bar_sync(6, n_b6);       // the publish warp releases superblock c
-    carry_valid = true;
+    // ---- left edge of c+1 (reads / writes the last 8 columns of c and the look-ahead columns), then
+    // the look-ahead columns move to the front of the next buffer (same thread: no barrier needed)
+    if (has_next) {
+      Px *row = T + my_idx * ts;
+      if (row_valid) v_edges(P.lfm[sbr * sb_cols + sbc + 1], row + n, 0x01, 0x00);
+      Vec vv;
+      smem_get(row + n, vv);
+      smem_put(buf(sbc + 1) + toff + my_idx * ts, vv);
+    }
+    bar_sync(5, n_b5);       // B5: this buffer is final, the next one is filled
     LFT(7)
-    w0 = w1; w1 = w2;
   }
 }
 
@@ -1984,10 +1982,18 @@ static int launch_stages(vp9gpu_ctx *ctx, const FrameParams &P, const vp9b_frame
   if (h->lf_level) {
     const bool sub = P.ss_x != 0;
     const int tsY = sizeof(Px) == 1 ? 76 : 74, tsC = sub ? (sizeof(Px) == 1 ? 44 : 42) : tsY, nC = sub ? 32 : 64;
-    // tiles + per-superblock work flags; threads = worker warps + halo warp + publish warp
-    const size_t smem = sizeof(Px) * (size_t)(72 * tsY + 2 * (nC + 8) * tsC) + 32 + ((P.sb_cols + 2 + 15) & ~15);
-    if (sub) k_loopfilter<Px, 128><<<P.sb_rows, 192, smem, st>>>(P);
-    else k_loopfilter<Px, 192><<<P.sb_rows, 256, smem, st>>>(P);
+    // two tile buffers; threads = worker warps + halo warp + publish warp + mover warps
+    const size_t smem = 2 * sizeof(Px) * (size_t)(72 * tsY + 2 * (nC + 8) * tsC + 8) + 32;
+    if (sub) {
+      k_loopfilter<Px, 128><<<P.sb_rows, 128 + 64 + 64, smem, st>>>(P);
+    } else {
+      static bool attr_set = false;
+      if (!attr_set) {
+        cudaFuncSetAttribute(k_loopfilter<Px, 192>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        attr_set = true;
+      }
+      k_loopfilter<Px, 192><<<P.sb_rows, 192 + 64 + 96, smem, st>>>(P);
+    }
     ctx->ticket_lf_base += (uint32_t)P.sb_rows;
     ctx->launches++;
   }
