@@ -1575,6 +1575,12 @@ __global__ void __launch_bounds__(NW + 64 + NW / 2, NW == 128 ? 3 : 2) k_loopfil
     Px *T = buf(sbc) + toff;
     const vp9b_lfm &M = P.lfm[sbr * sb_cols + sbc];
     constexpr bool w0 = true;
+    // the masks of c+1 are first needed by the left-edge pass at the end of this step: pull them
+    // into L1 now so that pass does not start with an L2 round trip
+    if (has_next && tid < 2) {
+      const char *nx = (const char *)&P.lfm[sbr * sb_cols + sbc + 1] + tid * 128;
+      asm volatile("prefetch.global.L1 [%0];" ::"l"(nx));
+    }
     LFT(0)
     // ---- vertical edges 1..7 and all inner 4x4 edges of c: thread = sample row
     if (row_valid) v_edges(M, T + my_idx * ts, 0xfe, 0xff);
