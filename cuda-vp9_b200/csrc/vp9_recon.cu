@@ -1704,6 +1704,7 @@ struct vp9gpu_ctx {
   MiEntry *d_mi = nullptr;
   uint32_t *d_tickets = nullptr;  // wavefront progress counters
   uint32_t epoch = 0;
+  unsigned attr_done = 0;         // kernels whose dynamic shared-memory limit has been raised on this device
   uint8_t *d_out8 = nullptr;      // staging for 8-bit output of high-bit-depth frames
   uint8_t *d_resid = nullptr;     // residual planes of intra blocks
   size_t resid_bytes = 0;
@@ -1970,10 +1971,11 @@ static int launch_stages(vp9gpu_ctx *ctx, const FrameParams &P, const vp9b_frame
                              h->sec[VP9B_SEC_TXB_INTRA_V].count;
     if (n_intra) {
       const size_t ismem = IntraTileGeom<Px>::kWarpBytes * kWaveWarps;
-      static bool attr_set = false;
-      if (!attr_set) {
-        cudaFuncSetAttribute(k_intra<Px, PT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ismem);
-        attr_set = true;
+      // opt-in shared memory size: per device, so remembered per context (one context = one device)
+      const unsigned abit = sizeof(Px) == 1 ? 1u : 2u;
+      if (!(ctx->attr_done & abit)) {
+        CK(cudaFuncSetAttribute(k_intra<Px, PT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ismem));
+        ctx->attr_done |= abit;
       }
       const int rblocks = std::min((int)((n_intra + kResWarps - 1) / kResWarps), ctx->num_sms * 8);
       k_intra_residual<Px, PT><<<rblocks, kResWarps * 32, 0, st>>>(P);
@@ -1993,10 +1995,10 @@ static int launch_stages(vp9gpu_ctx *ctx, const FrameParams &P, const vp9b_frame
     if (sub) {
       k_loopfilter<Px, 128><<<P.sb_rows, 128 + 64 + 64, smem, st>>>(P);
     } else {
-      static bool attr_set = false;
-      if (!attr_set) {
-        cudaFuncSetAttribute(k_loopfilter<Px, 192>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        attr_set = true;
+      const unsigned abit = sizeof(Px) == 1 ? 4u : 8u;
+      if (!(ctx->attr_done & abit)) {
+        CK(cudaFuncSetAttribute(k_loopfilter<Px, 192>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        ctx->attr_done |= abit;
       }
       k_loopfilter<Px, 192><<<P.sb_rows, 192 + 64 + 96, smem, st>>>(P);
     }
