@@ -26,14 +26,16 @@ gpu.sync()
 buf = (C.c_ulonglong * 512)()
 gpu.L.vp9gpu_debug_read(buf)
 t00 = buf[0]
+# stamps written by thread 0 of rows 2 and 3 (LFT(k) in k_loopfilter): 0 step start, 3 vertical pass done,
+# 4 past B2 (halo rows in place), 5 horizontal pass done, 6 past B3, 7 past B5 (left edge of c+1 + carry done)
 for row in range(2):
     prev = None
-    print("row %d:  sb  start(ns)  A  B1  V  B2  H  B3  F | step  gap" % (row + 2))
+    print("row %d:  sb  start(ns) |  V  B2wait  H  B3wait  left+carry+B5 | step  gap" % (row + 2))
     for sb in range(32):
         t = [buf[(row * 32 + sb) * 8 + k] for k in range(8)]
         if t[0] == 0:
             continue
-        print("  %2d %8d | %5d %5d %5d %5d %5d %5d %5d | %6d %s" % (
-            sb, t[0] - t00, t[1] - t[0], t[2] - t[1], t[3] - t[2], t[4] - t[3], t[5] - t[4], t[6] - t[5], t[7] - t[6],
-            t[7] - t[0], (t[0] - prev) if prev else "-"))
+        print("  %2d %8d | %5d %5d %5d %5d %5d | %6d %s" % (
+            sb, t[0] - t00, t[3] - t[0], t[4] - t[3], t[5] - t[4], t[6] - t[5], t[7] - t[6], t[7] - t[0],
+            (t[0] - prev) if prev else "-"))
         prev = t[7]
