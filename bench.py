@@ -202,14 +202,27 @@ def run_ours(args, rank, world, local):
     streams = [torch.cuda.ExternalStream(c.stream()) for c in ctxs]
     master = torch.cuda.Stream()
 
-    batches = [ctxs[ci].make_batch([(dptr[ci][f], hdrs[f]) for f in range(n_coded)]) for ci in range(S)]
+    K = max(1, min(args.batch, 4))
+    if K == 1:
+        batches = [ctxs[ci].make_batch([(dptr[ci][f], hdrs[f]) for f in range(n_coded)]) for ci in range(S)]
+        n_workers = S
 
-    def submit_all(ci):
-        ctxs[ci].submit_batch(batches[ci])      # one C-ABI call queues the whole clip pass
+        def submit_all(ci):
+            ctxs[ci].submit_batch(batches[ci])      # one C-ABI call queues the whole clip pass
+    else:
+        # K streams share each launch (the hardware has 32 work queues): groups of K contexts
+        groups = [list(range(g, min(g + K, S))) for g in range(0, S, K)]
+        packs = [[vb.GpuRecon.make_multi([ctxs[ci] for ci in grp], [(dptr[ci][f], hdrs[f]) for ci in grp])
+                  for f in range(n_coded)] for grp in groups]
+        n_workers = len(groups)
+
+        def submit_all(gi):
+            for pk in packs[gi]:
+                vb.GpuRecon.submit_multi(pk)
 
     def replay_step(threads=True):
         if threads and S > 1:
-            th = [threading.Thread(target=submit_all, args=(i,)) for i in range(S)]
+            th = [threading.Thread(target=submit_all, args=(i,)) for i in range(n_workers)]
             for t in th:
                 t.start()
             for t in th:
@@ -371,7 +384,7 @@ def run_ours(args, rank, world, local):
            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
            "vs_baseline": None, "dtype": "u8" if bps == 1 else "u16", "data": "synthetic",
            "config": {"workload": workload_name(args, w, h), "streams_per_gpu": S, "coded_frames": n_coded,
-                      "shown_frames": shown, "parallelism": "independent streams, %d per GPU, no collective" % S,
+                      "shown_frames": shown, "parallelism": "independent streams, %d per GPU, %d per kernel launch, no collective" % (S, K),
                       "l2": "working set %d MB per GPU (> 126 MB L2): %d streams x (frame pool + packed buffers)" %
                             (S * (12 * frame_bytes(hdrs[0]) + sum(len(p) for p in packed)) >> 20, S),
                       "host_parse_fps_1thread": shown / parse_s,
@@ -430,6 +443,7 @@ def main():
     ap.add_argument("--clip", default="1440p", choices=sorted(CLIPS))
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--stop-stage", type=int, default=0, help=argparse.SUPPRESS)
+    ap.add_argument("--batch", type=int, default=1, help="streams per kernel launch (1..4)")
     args = ap.parse_args()
     rank, world, local = dist_setup(args)
     if args.impl == "reference":

@@ -102,6 +102,8 @@ def lib_gpu():
         L.vp9gpu_free_packed.argtypes = [vp, vp]
         L.vp9gpu_sync.argtypes = [vp]
         L.vp9gpu_frame_submit_device_n.argtypes = [vp, C.POINTER(C.c_void_p), C.POINTER(C.POINTER(FrameHdr)), C.c_int]
+        L.vp9gpu_frame_submit_device_multi.argtypes = [C.POINTER(vp), C.POINTER(C.c_void_p),
+                                                        C.POINTER(C.POINTER(FrameHdr)), C.c_int]
         L.vp9gpu_get_frame.argtypes = [vp, C.c_int, vp, vp, vp, C.c_int, C.c_int]
         L.vp9gpu_get_frame_async.argtypes = [vp, C.c_int, vp, vp, vp, C.c_int, C.c_int]
         L.vp9gpu_get_frame_8bit_async.argtypes = [vp, C.c_int, vp, vp, vp, C.c_int, C.c_int]
@@ -226,6 +228,22 @@ class GpuRecon:
 
     def submit_device(self, d_packed, hdr):
         self._chk(self.L.vp9gpu_frame_submit_device(self.ctx, d_packed, C.byref(hdr)))
+
+    @staticmethod
+    def make_multi(ctxs, frames):
+        """One frame of each context in `ctxs` -> opaque argument pack for submit_multi.
+        frames: [(device pointer, FrameHdr)], same order as ctxs."""
+        n = len(ctxs)
+        cs = (C.c_void_p * n)(*[c.ctx for c in ctxs])
+        ptrs = (C.c_void_p * n)(*[d.value if isinstance(d, C.c_void_p) else d for d, _ in frames])
+        hdrs = (C.POINTER(FrameHdr) * n)(*[C.pointer(h) for _, h in frames])
+        return (cs, ptrs, hdrs, n, frames, ctxs)
+
+    @staticmethod
+    def submit_multi(pack):
+        """Frames of several contexts through one launch per stage (vp9gpu_frame_submit_device_multi)."""
+        lead = pack[5][0]
+        lead._chk(lead.L.vp9gpu_frame_submit_device_multi(pack[0], pack[1], pack[2], pack[3]))
 
     def make_batch(self, frames):
         """frames: [(device pointer, FrameHdr)] -> opaque batch for submit_batch (one C call per pass)."""

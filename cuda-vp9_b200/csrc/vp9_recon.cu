@@ -85,6 +85,17 @@ struct FrameParams {
   uint32_t *ticket_lf, *ticket_intra;
   uint32_t ticket_lf_base, ticket_intra_base;
   uint8_t lf_lim[64], lf_mblim[64];
+  // which stages this frame takes part in, and its own motion-compensation grid (a launch covers a
+  // batch of frames of different contexts; its grid is the maximum over the batch)
+  int do_inter, do_res, do_intra, do_lf;
+  int gy_y, gy_c, gx_c;
+};
+
+// Frames of up to kMaxBatch different contexts that go through one launch per stage: the hardware
+// has 32 work queues, so more than 32 concurrent streams need several frames per launch.
+constexpr int kMaxBatch = 4;
+struct FrameBatch {
+  FrameParams f[kMaxBatch];
 };
 
 __device__ __constant__ uint8_t d_bw8[13] = { 1, 1, 1, 1, 1, 2, 2, 2, 4, 4, 4, 8, 8 };
@@ -94,8 +105,12 @@ VP9B_DEV int clampi(int v, int lo, int hi) { return min(max(v, lo), hi); }
 
 // ------------------------------------------------------------------------------------------
 // stage 0: block list -> dense mi map
-__global__ void k_expand_blocks(const vp9b_block *__restrict__ blocks, int n, MiEntry *__restrict__ mi, int mi_cols,
-                                int mi_rows) {
+__global__ void k_expand_blocks(const __grid_constant__ FrameBatch B) {
+  const FrameParams &P = B.f[blockIdx.z];
+  if (!P.do_inter) return;
+  const vp9b_block *__restrict__ blocks = P.blocks;
+  MiEntry *__restrict__ mi = P.mi;
+  const int n = P.n_blocks, mi_cols = P.mi_cols, mi_rows = P.mi_rows;
   // 8 threads per block: thread l fills row l of the block's footprint in the 8x8 map
   const int t = blockIdx.x * blockDim.x + threadIdx.x, i = t >> 3, l = t & 7;
   if (i >= n) return;
@@ -414,8 +429,10 @@ VP9B_DEV void inter_pred_u8_body(const FrameParams &P, int plane, int bx_, int b
 
 // All three planes in one launch: a flat grid of CTAs, luma tiles (32x128 samples) first, then
 // the two chroma planes (4:2:0: 32x64-sample tiles of 4x4 units; 4:4:4: same as luma).
-__global__ void __launch_bounds__(128, 8) k_inter_pred_u8(const __grid_constant__ FrameParams P, int gy_y, int gy_c,
-                                                         int gx_c) {
+__global__ void __launch_bounds__(128, 8) k_inter_pred_u8(const __grid_constant__ FrameBatch B) {
+  const FrameParams &P = B.f[blockIdx.z];
+  if (!P.do_inter) return;
+  const int gy_y = P.gy_y, gy_c = P.gy_c, gx_c = P.gx_c;
   // grid = (tiles across the luma plane, luma tile rows + 2 x chroma tile rows): plane and tile come
   // from blockIdx without divisions; chroma rows use the first gx_c columns only
   int by = blockIdx.y, plane = 0;
@@ -630,8 +647,10 @@ VP9B_DEV void inter_pred_u16_body(const FrameParams &P, int plane, int bx_, int 
   for (int i = 0; i < H; i++) *(uint2 *)(dst + (size_t)i * dstride) = o[i];
 }
 
-__global__ void __launch_bounds__(128, 4) k_inter_pred_u16(const __grid_constant__ FrameParams P, int gy_y, int gy_c,
-                                                          int gx_c) {
+__global__ void __launch_bounds__(128, 4) k_inter_pred_u16(const __grid_constant__ FrameBatch B) {
+  const FrameParams &P = B.f[blockIdx.z];
+  if (!P.do_inter) return;
+  const int gy_y = P.gy_y, gy_c = P.gy_c, gx_c = P.gx_c;
   int by = blockIdx.y, plane = 0;
   if (by >= gy_y) {
     by -= gy_y;
@@ -847,7 +866,9 @@ VP9B_DEV void group_itx_add(int *tbuf, const FrameParams &P, int first, int coun
 
 constexpr int kResWarps = 4;
 template <typename Px, typename PT>
-__global__ void __launch_bounds__(kResWarps * 32) k_residual(const __grid_constant__ FrameParams P) {
+__global__ void __launch_bounds__(kResWarps * 32) k_residual(const __grid_constant__ FrameBatch B) {
+  const FrameParams &P = B.f[blockIdx.z];
+  if (!P.do_res) return;
   __shared__ int tbuf[kResWarps][32 * 33];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nwarps = gridDim.x * kResWarps;
@@ -872,7 +893,9 @@ __global__ void __launch_bounds__(kResWarps * 32) k_residual(const __grid_consta
 // so it is taken off the intra wavefront's dependency chain and computed here, one warp per block,
 // into a residual plane; the wavefront (k_intra) then only predicts and adds.
 template <typename Px, typename PT>
-__global__ void __launch_bounds__(kResWarps * 32) k_intra_residual(const __grid_constant__ FrameParams P) {
+__global__ void __launch_bounds__(kResWarps * 32) k_intra_residual(const __grid_constant__ FrameBatch B) {
+  const FrameParams &P = B.f[blockIdx.z];
+  if (!P.do_intra) return;
   __shared__ int tbuf[kResWarps][32 * 33];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nwarps = gridDim.x * kResWarps;
@@ -1088,7 +1111,9 @@ template <typename Px> struct IntraTileGeom {
 };
 
 template <typename Px, typename PT>
-__global__ void __launch_bounds__(kWaveWarps * 32) k_intra(const __grid_constant__ FrameParams P) {
+__global__ void __launch_bounds__(kWaveWarps * 32) k_intra(const __grid_constant__ FrameBatch B) {
+  const FrameParams &P = B.f[blockIdx.z];
+  if (!P.do_intra) return;
   extern __shared__ __align__(16) unsigned char intra_smem[];
   typedef IntraTileGeom<Px> G;
   typedef typename LfVec<Px>::T Vec;  // 8 samples
@@ -1322,7 +1347,9 @@ VP9B_DEV void bar_sync(int id, int nthreads) {
 }
 
 template <typename Px, int NW>
-__global__ void __launch_bounds__(NW + 64 + NW / 2, NW == 128 ? 3 : 2) k_loopfilter(const __grid_constant__ FrameParams P) {
+__global__ void __launch_bounds__(NW + 64 + NW / 2, NW == 128 ? 3 : 2) k_loopfilter(const __grid_constant__ FrameBatch B) {
+  const FrameParams &P = B.f[blockIdx.z];
+  if (!P.do_lf) return;
   // One persistent CTA per superblock ROW walks its row left to right: 4 (4:2:0) or 6 (4:4:4)
   // worker warps only filter; a halo warp and two mover warps do all the global traffic.
   //
@@ -1363,6 +1390,7 @@ __global__ void __launch_bounds__(NW + 64 + NW / 2, NW == 128 ? 3 : 2) k_loopfil
   if (threadIdx.x == 0) s_row = (int)(atomicAdd(P.ticket_lf, 1u) - P.ticket_lf_base);
   __syncthreads();
   const int sbr = s_row, sb_cols = P.sb_cols;
+  if (sbr >= P.sb_rows) return;   // the launch is as tall as the tallest frame of the batch
   const int mi_row = sbr * 8;
   const int hy = sbr > 0 ? 8 : 0;
   uint32_t *prog = P.prog_lf;  // [sb_rows] prog_base + number of leading superblocks that are final
@@ -1704,6 +1732,7 @@ struct vp9gpu_ctx {
   MiEntry *d_mi = nullptr;
   uint32_t *d_tickets = nullptr;  // wavefront progress counters
   uint32_t epoch = 0;
+  cudaEvent_t join_ev = nullptr;  // joins this context's stream with a batch leader's (submit_device_multi)
   unsigned attr_done = 0;         // kernels whose dynamic shared-memory limit has been raised on this device
   uint8_t *d_out8 = nullptr;      // staging for 8-bit output of high-bit-depth frames
   uint8_t *d_resid = nullptr;     // residual planes of intra blocks
@@ -1729,6 +1758,15 @@ struct vp9gpu_ctx {
     cudaError_t e_ = (call);                                                           \
     if (e_ != cudaSuccess) {                                                           \
       ctx->err = std::string(#call) + ": " + cudaGetErrorString(e_);                   \
+      return VP9B_ERR_CUDA;                                                            \
+    }                                                                                  \
+  } while (0)
+
+#define CK2(c, call)                                                                   \
+  do {                                                                                 \
+    cudaError_t e_ = (call);                                                           \
+    if (e_ != cudaSuccess) {                                                           \
+      (c)->err = std::string(#call) + ": " + cudaGetErrorString(e_);                  \
       return VP9B_ERR_CUDA;                                                            \
     }                                                                                  \
   } while (0)
@@ -1786,6 +1824,7 @@ extern "C" void vp9gpu_destroy(vp9gpu_ctx *ctx) {
   for (int i = 0; i < 6; i++) cudaEventDestroy(ctx->prof_ev[i]);
   if (ctx->tickets_ready)
     for (int i = 0; i < vp9gpu_ctx::kTickets; i++) cudaEventDestroy(ctx->ticket_ev[i]);
+  if (ctx->join_ev) cudaEventDestroy(ctx->join_ev);
   cudaFree(ctx->d_mi);
   cudaFree(ctx->d_out8);
   cudaFree(ctx->d_resid);
@@ -1930,79 +1969,97 @@ static int setup_workspace(vp9gpu_ctx *ctx, const vp9b_frame_hdr *h) {
   return 0;
 }
 
+// One launch per stage for a batch of n prepared frames (one per context, all of the same sample
+// type and chroma format) on the stream of the first context.  Grids are the maximum over the
+// batch; a frame that does not take part in a stage has its flag cleared and its CTAs return.
 template <typename Px, typename PT>
-static int launch_stages(vp9gpu_ctx *ctx, const FrameParams &P, const vp9b_frame_hdr *h) {
+static int launch_batch(vp9gpu_ctx *const *ctxs, FrameBatch &B, int n) {
+  vp9gpu_ctx *ctx = ctxs[0];
   cudaStream_t st = ctx->stream;
   const int stop = ctx->stop_stage;
-  const bool prof = ctx->profiling;
-  if (prof) cudaEventRecord(ctx->prof_ev[0], st);
-  if (!h->intra_only) {
-    if (P.n_blocks) {
-      k_expand_blocks<<<(P.n_blocks * 8 + 127) / 128, 128, 0, st>>>(P.blocks, P.n_blocks, P.mi, P.mi_cols, P.mi_rows);
-      ctx->launches++;
-    }
-    if (prof) cudaEventRecord(ctx->prof_ev[1], st);
-    {
+  const bool prof = ctx->profiling && n == 1;
+  int g_expand = 0, g_mcx = 0, g_mcy = 0, g_res = 0, g_ires = 0, g_intra = 0, g_lf = 0;
+  for (int i = 0; i < n; i++) {
+    FrameParams &P = B.f[i];
+    if (P.do_inter) {
+      g_expand = std::max(g_expand, (P.n_blocks * 8 + 127) / 128);
       const int pwy = P.mi_cols * 8, phy = P.mi_rows * 8;
       const int pwc = pwy >> P.ss_x, phc = phy >> P.ss_y;
-      const int gx_y = (pwy + 31) / 32, gy_y = (phy + 127) / 128;
-      const int gx_c = (pwc + 31) / 32, gy_c = P.ss_x ? (phc + 63) / 64 : (phc + 127) / 128;
-      const dim3 grid(gx_y, gy_y + 2 * gy_c);
-      if (sizeof(Px) == 1) k_inter_pred_u8<<<grid, 128, 0, st>>>(P, gy_y, gy_c, gx_c);
-      else k_inter_pred_u16<<<grid, 128, 0, st>>>(P, gy_y, gy_c, gx_c);
-      ctx->launches++;
+      P.gy_y = (phy + 127) / 128;
+      P.gx_c = (pwc + 31) / 32;
+      P.gy_c = P.ss_x ? (phc + 63) / 64 : (phc + 127) / 128;
+      g_mcx = std::max(g_mcx, (pwy + 31) / 32);
+      g_mcy = std::max(g_mcy, P.gy_y + 2 * P.gy_c);
     }
-    if (prof) cudaEventRecord(ctx->prof_ev[2], st);
-    if (stop != 1 && P.n_txb_inter) {
+    P.do_res = P.do_inter && stop != 1 && P.n_txb_inter > 0;
+    if (P.do_res) {
       const int tasks = ((P.n_txb_size[0] + 7) >> 3) + ((P.n_txb_size[1] + 3) >> 2) + ((P.n_txb_size[2] + 1) >> 1) + P.n_txb_size[3];
-      const int blocks = std::min((tasks + kResWarps - 1) / kResWarps, ctx->num_sms * 8);
-      k_residual<Px, PT><<<blocks, kResWarps * 32, 0, st>>>(P);
-      ctx->launches++;
+      g_res = std::max(g_res, std::min((tasks + kResWarps - 1) / kResWarps, ctx->num_sms * 8));
     }
-  } else if (prof) {
-    cudaEventRecord(ctx->prof_ev[1], st);
-    cudaEventRecord(ctx->prof_ev[2], st);
+    const int n_intra = P.n_txb_intra[0] + P.n_txb_intra[1] + P.n_txb_intra[2];
+    P.do_intra = stop != 1 && stop != 2 && n_intra > 0;
+    if (P.do_intra) {
+      g_ires = std::max(g_ires, std::min((n_intra + kResWarps - 1) / kResWarps, ctx->num_sms * 8));
+      g_intra = std::max(g_intra, (3 * P.sb_rows + kWaveWarps - 1) / kWaveWarps);
+    }
+    P.do_lf = P.do_lf && stop == 0;
+    if (P.do_lf) g_lf = std::max(g_lf, P.sb_rows);
+  }
+  // tickets: every participating frame's counter advances by the number of CTAs launched for it
+  for (int i = 0; i < n; i++) {
+    FrameParams &P = B.f[i];
+    P.ticket_intra_base = ctxs[i]->ticket_intra_base;
+    P.ticket_lf_base = ctxs[i]->ticket_lf_base;
+    if (P.do_intra) ctxs[i]->ticket_intra_base += (uint32_t)g_intra;
+    if (P.do_lf) ctxs[i]->ticket_lf_base += (uint32_t)g_lf;
+  }
+  if (prof) cudaEventRecord(ctx->prof_ev[0], st);
+  if (g_expand) {
+    k_expand_blocks<<<dim3(g_expand, 1, n), 128, 0, st>>>(B);
+    ctx->launches++;
+  }
+  if (prof) cudaEventRecord(ctx->prof_ev[1], st);
+  if (g_mcx) {
+    const dim3 grid(g_mcx, g_mcy, n);
+    if (sizeof(Px) == 1) k_inter_pred_u8<<<grid, 128, 0, st>>>(B);
+    else k_inter_pred_u16<<<grid, 128, 0, st>>>(B);
+    ctx->launches++;
+  }
+  if (prof) cudaEventRecord(ctx->prof_ev[2], st);
+  if (g_res) {
+    k_residual<Px, PT><<<dim3(g_res, 1, n), kResWarps * 32, 0, st>>>(B);
+    ctx->launches++;
   }
   if (prof) cudaEventRecord(ctx->prof_ev[3], st);
-  if (stop == 1 || stop == 2) return 0;
-  const int wave_blocks = (3 * P.sb_rows + kWaveWarps - 1) / kWaveWarps;
-  {
-    const uint32_t n_intra = h->sec[VP9B_SEC_TXB_INTRA_Y].count + h->sec[VP9B_SEC_TXB_INTRA_U].count +
-                             h->sec[VP9B_SEC_TXB_INTRA_V].count;
-    if (n_intra) {
-      const size_t ismem = IntraTileGeom<Px>::kWarpBytes * kWaveWarps;
-      // opt-in shared memory size: per device, so remembered per context (one context = one device)
-      const unsigned abit = sizeof(Px) == 1 ? 1u : 2u;
-      if (!(ctx->attr_done & abit)) {
-        CK(cudaFuncSetAttribute(k_intra<Px, PT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ismem));
-        ctx->attr_done |= abit;
-      }
-      const int rblocks = std::min((int)((n_intra + kResWarps - 1) / kResWarps), ctx->num_sms * 8);
-      k_intra_residual<Px, PT><<<rblocks, kResWarps * 32, 0, st>>>(P);
-      ctx->launches++;
-      k_intra<Px, PT><<<wave_blocks, kWaveWarps * 32, ismem, st>>>(P);
-      ctx->ticket_intra_base += (uint32_t)wave_blocks;
-      ctx->launches++;
+  if (g_intra) {
+    const size_t ismem = IntraTileGeom<Px>::kWarpBytes * kWaveWarps;
+    // opt-in shared memory size: per device, so remembered per context (one context = one device)
+    const unsigned abit = sizeof(Px) == 1 ? 1u : 2u;
+    if (!(ctx->attr_done & abit)) {
+      CK(cudaFuncSetAttribute(k_intra<Px, PT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ismem));
+      ctx->attr_done |= abit;
     }
+    k_intra_residual<Px, PT><<<dim3(g_ires, 1, n), kResWarps * 32, 0, st>>>(B);
+    ctx->launches++;
+    k_intra<Px, PT><<<dim3(g_intra, 1, n), kWaveWarps * 32, ismem, st>>>(B);
+    ctx->launches++;
   }
   if (prof) cudaEventRecord(ctx->prof_ev[4], st);
-  if (stop == 3) return 0;
-  if (h->lf_level) {
-    const bool sub = P.ss_x != 0;
+  if (g_lf) {
+    const bool sub = B.f[0].ss_x != 0;
     const int tsY = sizeof(Px) == 1 ? 76 : 74, tsC = sub ? (sizeof(Px) == 1 ? 44 : 42) : tsY, nC = sub ? 32 : 64;
     // two tile buffers; threads = worker warps + halo warp + publish warp + mover warps
     const size_t smem = 2 * sizeof(Px) * (size_t)(72 * tsY + 2 * (nC + 8) * tsC + 8) + 32;
     if (sub) {
-      k_loopfilter<Px, 128><<<P.sb_rows, 128 + 64 + 64, smem, st>>>(P);
+      k_loopfilter<Px, 128><<<dim3(g_lf, 1, n), 128 + 64 + 64, smem, st>>>(B);
     } else {
       const unsigned abit = sizeof(Px) == 1 ? 4u : 8u;
       if (!(ctx->attr_done & abit)) {
         CK(cudaFuncSetAttribute(k_loopfilter<Px, 192>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         ctx->attr_done |= abit;
       }
-      k_loopfilter<Px, 192><<<P.sb_rows, 192 + 64 + 96, smem, st>>>(P);
+      k_loopfilter<Px, 192><<<dim3(g_lf, 1, n), 192 + 64 + 96, smem, st>>>(B);
     }
-    ctx->ticket_lf_base += (uint32_t)P.sb_rows;
     ctx->launches++;
   }
   if (prof) {
@@ -2014,10 +2071,12 @@ static int launch_stages(vp9gpu_ctx *ctx, const FrameParams &P, const vp9b_frame
       ctx->stage_ms[i] += ms;
     }
   }
+  CK(cudaGetLastError());
   return 0;
 }
 
-static int submit_device(vp9gpu_ctx *ctx, const uint8_t *d_packed, const vp9b_frame_hdr *h) {
+// Validate one packed frame, make sure its context has the memory it needs and fill its FrameParams.
+static int prepare_frame(vp9gpu_ctx *ctx, const uint8_t *d_packed, const vp9b_frame_hdr *h, FrameParams &P) {
   if (h->magic != VP9B_MAGIC) { ctx->err = "bad packed buffer magic"; return VP9B_ERR_INVALID; }
   if (h->dst_slot < 0 || h->dst_slot >= VP9B_NUM_SLOTS) { ctx->err = "bad dst slot"; return VP9B_ERR_INVALID; }
   if (!((h->ss_x == 1 && h->ss_y == 1) || (h->ss_x == 0 && h->ss_y == 0))) {
@@ -2061,7 +2120,6 @@ static int submit_device(vp9gpu_ctx *ctx, const uint8_t *d_packed, const vp9b_fr
   if (e) return e;
   e = setup_workspace(ctx, h);
   if (e) return e;
-  FrameParams P;
   memset(&P, 0, sizeof(P));
   const DevFrame &D = ctx->slot[h->dst_slot];
   for (int p = 0; p < 3; p++) P.dst[p] = D.pl[p];
@@ -2135,14 +2193,64 @@ static int submit_device(vp9gpu_ctx *ctx, const uint8_t *d_packed, const vp9b_fr
   P.prog_base = (ctx->epoch & 0xfffff) << 11;
   P.ticket_lf = ctx->d_tickets + 4096;
   P.ticket_intra = ctx->d_tickets + 4097;
-  P.ticket_lf_base = ctx->ticket_lf_base;
-  P.ticket_intra_base = ctx->ticket_intra_base;
   memcpy(P.lf_lim, h->lf_lim, 64);
   memcpy(P.lf_mblim, h->lf_mblim, 64);
-  if (h->bit_depth == 8) e = launch_stages<uint8_t, int>(ctx, P, h);
-  else e = launch_stages<uint16_t, long long>(ctx, P, h);
+  P.do_inter = !h->intra_only;
+  P.do_lf = h->lf_level != 0;
+  return 0;
+}
+
+static int submit_device(vp9gpu_ctx *ctx, const uint8_t *d_packed, const vp9b_frame_hdr *h) {
+  FrameBatch B;
+  int e = prepare_frame(ctx, d_packed, h, B.f[0]);
   if (e) return e;
-  CK(cudaGetLastError());
+  vp9gpu_ctx *one[1] = { ctx };
+  if (h->bit_depth == 8) return launch_batch<uint8_t, int>(one, B, 1);
+  return launch_batch<uint16_t, long long>(one, B, 1);
+}
+
+// Frames of n different contexts through one launch per stage.  They run on the stream of the first
+// context; the other contexts' streams are joined before and after, so their earlier and later
+// work stays ordered.  Frames that cannot share a launch (other sample type / chroma format) are
+// submitted one by one.
+extern "C" int vp9gpu_frame_submit_device_multi(vp9gpu_ctx *const *ctxs, const void *const *d_packed,
+                                                const vp9b_frame_hdr *const *hdr, int n) {
+  if (!ctxs || !d_packed || !hdr || n <= 0) return VP9B_ERR_INVALID;
+  for (int i = 0; i < n; i++)
+    if (!ctxs[i] || !d_packed[i] || !hdr[i]) return VP9B_ERR_INVALID;
+  bool same = n <= kMaxBatch;
+  for (int i = 1; i < n && same; i++) {
+    same = (hdr[i]->bit_depth > 8) == (hdr[0]->bit_depth > 8) && hdr[i]->ss_x == hdr[0]->ss_x && hdr[i]->ss_y == hdr[0]->ss_y &&
+           ctxs[i]->device == ctxs[0]->device;
+    for (int j = 0; j < i; j++) same = same && ctxs[i] != ctxs[j];
+  }
+  if (!same || n == 1) {
+    for (int i = 0; i < n; i++) {
+      const int e = submit_device(ctxs[i], (const uint8_t *)d_packed[i], hdr[i]);
+      if (e) return e;
+    }
+    return 0;
+  }
+  vp9gpu_ctx *lead = ctxs[0];
+  FrameBatch B;
+  for (int i = 0; i < n; i++) {
+    const int e = prepare_frame(ctxs[i], (const uint8_t *)d_packed[i], hdr[i], B.f[i]);
+    if (e) { lead->err = ctxs[i]->err; return e; }
+  }
+  CK2(lead, cudaSetDevice(lead->device));
+  for (int i = 1; i < n; i++) {   // join: the lead stream continues after everything queued on the others
+    if (!ctxs[i]->join_ev) CK2(lead, cudaEventCreateWithFlags(&ctxs[i]->join_ev, cudaEventDisableTiming));
+    CK2(lead, cudaEventRecord(ctxs[i]->join_ev, ctxs[i]->stream));
+    CK2(lead, cudaStreamWaitEvent(lead->stream, ctxs[i]->join_ev, 0));
+  }
+  int e;
+  if (hdr[0]->bit_depth == 8) e = launch_batch<uint8_t, int>(ctxs, B, n);
+  else e = launch_batch<uint16_t, long long>(ctxs, B, n);
+  if (e) return e;
+  for (int i = 1; i < n; i++) {   // fork: later work on the other streams waits for this batch
+    CK2(lead, cudaEventRecord(ctxs[i]->join_ev, lead->stream));
+    CK2(lead, cudaStreamWaitEvent(ctxs[i]->stream, ctxs[i]->join_ev, 0));
+  }
   return 0;
 }
 

@@ -151,6 +151,13 @@ int vp9gpu_frame_submit_device(vp9gpu_ctx *ctx, const void *d_packed, const vp9b
  * front ends that queue a whole GOP): stops at the first error. */
 int vp9gpu_frame_submit_device_n(vp9gpu_ctx *ctx, const void *const *d_packed,
                                  const vp9b_frame_hdr *const *hdr, int n);
+/* One frame of each of n DIFFERENT contexts (same device) through one kernel launch per stage: the
+ * hardware has 32 work queues, so serving more than 32 concurrent streams per GPU means batching
+ * several streams per launch.  Up to 4 frames of the same sample type (8-bit / high bit depth) and
+ * chroma format share the launches (others are submitted one by one); they run on the stream of
+ * ctxs[0], the other contexts' streams are joined before and after.  Frame sizes may differ. */
+int vp9gpu_frame_submit_device_multi(vp9gpu_ctx *const *ctxs, const void *const *d_packed,
+                                     const vp9b_frame_hdr *const *hdr, int n);
 /* Upload a packed buffer to a ctx-owned device allocation for later submit_device calls. */
 int vp9gpu_upload_packed(vp9gpu_ctx *ctx, const void *packed, size_t bytes, void **d_packed);
 int vp9gpu_free_packed(vp9gpu_ctx *ctx, void *d_packed);
