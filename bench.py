@@ -443,7 +443,7 @@ def main():
     ap.add_argument("--clip", default="1440p", choices=sorted(CLIPS))
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--stop-stage", type=int, default=0, help=argparse.SUPPRESS)
-    ap.add_argument("--batch", type=int, default=1, help="streams per kernel launch (1..4)")
+    ap.add_argument("--batch", type=int, default=2, help="streams per kernel launch (1..4)")
     args = ap.parse_args()
     rank, world, local = dist_setup(args)
     if args.impl == "reference":
