@@ -1140,6 +1140,9 @@ __global__ void __launch_bounds__(kWaveWarps * 32) k_intra(const __grid_constant
   Px *T0 = tile + TS + M;  // sample (0,0) of the superblock; row -1 / column -1 hold the neighbours
   bool left_in_smem = false;
   int published = 0;   // superblocks of this row already released to the row below
+  constexpr int kPer = 64 * 8 / 32;
+  Vec tmp[kPer];       // staged tile interior (also the prefetch of the next non-empty superblock)
+  int pf_sbc = -1;
   // Superblocks without intra blocks are final after the inter stages: walk only the non-empty
   // ones (32 ranges at a time, one per lane) and release everything skipped in one store.
   for (int c0 = 0; c0 < P.sb_cols; c0 += 32) {
@@ -1162,20 +1165,19 @@ __global__ void __launch_bounds__(kWaveWarps * 32) k_intra(const __grid_constant
     Px *g = gplane + (size_t)(sbr * n) * stride + sbc * n;
     // interior rows can be fetched before the dependency wait (nobody else writes them)
     const int vpr = n >> 3, vsh = n == 64 ? 3 : 2, nvec = n * vpr;
-    {
-      // all loads of the tile are issued before the first one is consumed (one L2 round trip)
-      constexpr int kPer = 64 * 8 / 32;
-      Vec tmp[kPer];
+    // all loads of the tile are issued before the first one is consumed (one L2 round trip); they
+    // were already issued at the end of the previous superblock when that one ran in this loop
+    if (pf_sbc != sbc) {
 #pragma unroll
       for (int k = 0; k < kPer; k++) {
         const int i = lane + 32 * k;
         if (i < nvec) tmp[k] = __ldcg((const Vec *)(g + (size_t)(i >> vsh) * stride + (i & (vpr - 1)) * 8));
       }
+    }
 #pragma unroll
-      for (int k = 0; k < kPer; k++) {
-        const int i = lane + 32 * k;
-        if (i < nvec) *(Vec *)(T0 + (i >> vsh) * TS + (i & (vpr - 1)) * 8) = tmp[k];
-      }
+    for (int k = 0; k < kPer; k++) {
+      const int i = lane + 32 * k;
+      if (i < nvec) *(Vec *)(T0 + (i >> vsh) * TS + (i & (vpr - 1)) * 8) = tmp[k];
     }
     if (sbc > 0 && !left_in_smem)
       for (int r = lane; r < n; r += 32) T0[r * TS - 1] = __ldcg((const Px *)(g + (size_t)r * stride - 1));
@@ -1228,6 +1230,17 @@ __global__ void __launch_bounds__(kWaveWarps * 32) k_intra(const __grid_constant
     __syncwarp();
     if (lane == 0) st_release(prog + sbr, P.prog_base + (uint32_t)(sbc + 1));
     published = sbc + 1;
+    // prefetch the interior of the next non-empty superblock of this chunk: its loads fly while the
+    // rest of this tile is written back
+    if (todo) {
+      pf_sbc = c0 + __ffs(todo) - 1;
+      const Px *gn = gplane + (size_t)(sbr * n) * stride + pf_sbc * n;
+#pragma unroll
+      for (int k = 0; k < kPer; k++) {
+        const int i = lane + 32 * k;
+        if (i < nvec) tmp[k] = __ldcg((const Vec *)(gn + (size_t)(i >> vsh) * stride + (i & (vpr - 1)) * 8));
+      }
+    }
     // the rest of the tile (read again only by the next launch) and the next left neighbour column
 #pragma unroll 4
     for (int i = lane; i < nvec - vpr; i += 32)
