@@ -225,3 +225,22 @@ def test_gpu_batched_contexts_stay_bit_exact(names):
     got = _decode_lockstep(names)
     for i, nme in enumerate(names):
         assert got[nme + str(i)] == golden_md5(nme), nme
+
+
+@pytest.mark.gpu
+def test_decoder_survives_corrupt_chunks():
+    """A corrupt chunk is reported as an error (vpx_codec_decode returns VPX_CODEC_CORRUPT_FRAME,
+    vpxdec.c:896-901) and the decoder keeps working when the stream restarts at a key frame."""
+    _, _, chunks = vb.ivf_read(clip_path("odd_rt"))
+    d = vb.Decoder(0)
+    for bad in (b"\x00" * 40, chunks[1][: len(chunks[1]) // 3], bytes(reversed(chunks[0]))):
+        with pytest.raises(vb.VP9BError):
+            d.decode(bad)
+    got = []
+    for ch in chunks:                      # restart at the key frame
+        d.decode(ch)
+        planes = d.get_frame()
+        if planes is not None:
+            got.append(vb.md5_planes(planes))
+    assert got == golden_md5("odd_rt")
+    d.close()
