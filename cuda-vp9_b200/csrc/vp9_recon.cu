@@ -21,6 +21,7 @@
 #include "vp9_b200.h"
 #include "vp9_tables.h"
 #include "vp9_txfm.cuh"
+#include "vp9_lf_sb.cuh"
 
 namespace vp9b {
 
@@ -83,6 +84,8 @@ struct FrameParams {
   // unit that waits for a lower-numbered one can only be running if that one was started before
   // it -- forward progress does not depend on the order in which the hardware dispatches CTAs.
   uint32_t *ticket_lf, *ticket_intra;
+  uint32_t *lf_flags;           // [2 * superblocks] loop-filter data-flow flags (k_lf_sb)
+  uint32_t lf_epoch;            // value a flag takes when set in this frame
   uint32_t ticket_lf_base, ticket_intra_base;
   uint8_t lf_lim[64], lf_mblim[64];
   // which stages this frame takes part in, and its own motion-compensation grid (a launch covers a
@@ -1255,446 +1258,105 @@ __global__ void __launch_bounds__(kWaveWarps * 32) k_intra(const __grid_constant
 }
 
 // ------------------------------------------------------------------------------------------
-// stage 4: loop filter.  One CTA per superblock (all planes), wavefront order 2*row+col: a
-// superblock depends on its left and above-right neighbours -- the lag libvpx's own row-MT
-// filter uses (vp9_thread_common.c:38-87) -- because libvpx filters superblock by superblock,
-// vertical edges then horizontal edges (vp9_loopfilter.c:1440-1467).  The CTA stages the
-// 64x64 luma tile and the chroma tiles (+8 samples halo left/top) in shared memory, filters
-// all vertical edges (thread = sample row) then all horizontal edges (thread = sample column)
-// in vp9_filter_block_plane_ss00/ss11 order (vp9_loopfilter.c:1241-1422) and writes the tiles
-// back with 8/16-byte vectors.  The tile interior is prefetched before the dependency wait.
-// Filter arithmetic: vpx_dsp/loopfilter.c:18-357 (8-bit) == :360-743 evaluated at bd.
-VP9B_DEV int sc_clamp(int t, int bd) {
-  const int lim = 128 << (bd - 8);
-  return clampi(t, -lim, lim - 1);
-}
-
-// s: pointer to q0 in the tile; step: distance between taps
-template <typename Px>
-VP9B_DEV void lf_px(Px *s, int step, int size, int blimit, int limit, int thresh, int bd_) {
-  const int bd = sizeof(Px) == 1 ? 8 : bd_;   // 8-bit samples: every shift below folds away
-  const int sh = bd - 8;
-  const int p3 = s[-4 * step], p2 = s[-3 * step], p1 = s[-2 * step], p0 = s[-step];
-  const int q0 = s[0], q1 = s[step], q2 = s[2 * step], q3 = s[3 * step];
-  const int lim16 = limit << sh, blim16 = blimit << sh, one = 1 << sh;
-  // masks as max chains: no short-circuit branches, |p1-p0| and |q1-q0| shared by all of them
-  const int d10p = abs(p1 - p0), d10q = abs(q1 - q0);
-  const int dmax = max(max(max(abs(p3 - p2), abs(p2 - p1)), max(abs(q2 - q1), abs(q3 - q2))), max(d10p, d10q));
-  const bool fm = dmax <= lim16 && abs(p0 - q0) * 2 + (abs(p1 - q1) >> 1) <= blim16;
-  if (!fm) return;  // filter_mask == 0: every variant leaves the samples untouched
-  bool flat = false;
-  if (size >= 8)
-    flat = max(max(max(d10p, d10q), max(abs(p2 - p0), abs(q2 - q0))), max(abs(p3 - p0), abs(q3 - q0))) <= one;
-  if (size == 16 && flat) {
-    const int p7 = s[-8 * step], p6 = s[-7 * step], p5 = s[-6 * step], p4 = s[-5 * step];
-    const int q4 = s[4 * step], q5 = s[5 * step], q6 = s[6 * step], q7 = s[7 * step];
-    const bool flat2 = max(max(max(abs(p4 - p0), abs(q4 - q0)), max(abs(p5 - p0), abs(q5 - q0))),
-                           max(max(abs(p6 - p0), abs(q6 - q0)), max(abs(p7 - p0), abs(q7 - q0)))) <= one;
-    if (flat2) {
-      // 15-tap [1,1,1,1,1,1,1,2,1,1,1,1,1,1,1] with edge replication, evaluated from prefix
-      // sums so that the 14 outputs are independent of each other (short dependency chain)
-      const int v[16] = { p7, p6, p5, p4, p3, p2, p1, p0, q0, q1, q2, q3, q4, q5, q6, q7 };
-      int S[17];
-      S[0] = 0;
-#pragma unroll
-      for (int i = 0; i < 16; i++) S[i + 1] = S[i] + v[i];
-#pragma unroll
-      for (int k = 1; k <= 14; k++) {
-        const int lo = k - 7 > 0 ? k - 7 : 0, hi = k + 7 < 15 ? k + 7 : 15;
-        const int box = S[hi + 1] - S[lo] + (7 - k > 0 ? (7 - k) * p7 : 0) + (k - 8 > 0 ? (k - 8) * q7 : 0);
-        s[(k - 8) * step] = (Px)((box + v[k] + 8) >> 4);
-      }
-      const int sp = 0, sq = 0;
-      (void)sp;
-      (void)sq;
-      return;
-    }
-  }
-  if (flat) {
-    s[-3 * step] = (Px)((p3 + p3 + p3 + 2 * p2 + p1 + p0 + q0 + 4) >> 3);
-    s[-2 * step] = (Px)((p3 + p3 + p2 + 2 * p1 + p0 + q0 + q1 + 4) >> 3);
-    s[-1 * step] = (Px)((p3 + p2 + p1 + 2 * p0 + q0 + q1 + q2 + 4) >> 3);
-    s[0] = (Px)((p2 + p1 + p0 + 2 * q0 + q1 + q2 + q3 + 4) >> 3);
-    s[1 * step] = (Px)((p1 + p0 + q0 + 2 * q1 + q2 + q3 + q3 + 4) >> 3);
-    s[2 * step] = (Px)((p0 + q0 + q1 + 2 * q2 + q3 + q3 + q3 + 4) >> 3);
-    return;
-  }
-  // filter4 (mask is all ones here)
-  const int off = 0x80 << sh;
-  const int ps1 = p1 - off, ps0 = p0 - off, qs0 = q0 - off, qs1 = q1 - off;
-  const int t16 = thresh << sh;
-  const int hev = max(d10p, d10q) > t16 ? -1 : 0;
-  int f = sc_clamp(ps1 - qs1, bd) & hev;
-  f = sc_clamp(f + 3 * (qs0 - ps0), bd);
-  const int f1 = sc_clamp(f + 4, bd) >> 3, f2 = sc_clamp(f + 3, bd) >> 3;
-  s[0] = (Px)(sc_clamp(qs0 - f1, bd) + off);
-  s[-step] = (Px)(sc_clamp(ps0 + f2, bd) + off);
-  f = ((f1 + 1) >> 1) & ~hev;
-  s[step] = (Px)(sc_clamp(qs1 - f, bd) + off);
-  s[-2 * step] = (Px)(sc_clamp(ps1 + f, bd) + off);
-}
-
-
-// geometry of one plane's tile in shared memory
-struct LfPlane {
-  int n;        // tile size in samples (64 or 32)
-  int ts;       // row stride in samples
-  int off;      // offset (samples) of the tile in the shared array
-};
-
-// optional phase timing of one loop-filter row (compile with -DVP9B_LF_TIMING; tools read it back
-// through vp9gpu_debug_read)
-#ifdef VP9B_LF_TIMING
-__device__ unsigned long long d_lf_dbg[64 * 8];
-VP9B_DEV unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
-#define LFT(k) if (tid == 0 && (sbr == 2 || sbr == 3) && sbc < 32) d_lf_dbg[((sbr - 2) * 32 + sbc) * 8 + (k)] = gtime();
-#else
-#define LFT(k)
-#endif
-// Named barriers go through the compiler intrinsic, not inline PTX: bar.sync is warp-aligned, and
-// only the intrinsic tells the compiler that the warp has to reconverge before it (the filter
-// passes in front of these barriers diverge on the sample data; an opaque asm barrier hung there).
-VP9B_DEV void bar_sync(int id, int nthreads) {
-  __syncwarp();
-  __barrier_sync_count((unsigned)id, (unsigned)nthreads);
-}
-
-template <typename Px, int NW>
-__global__ void __launch_bounds__(NW + 64 + NW / 2, NW == 128 ? 3 : 2) k_loopfilter(const __grid_constant__ FrameBatch B) {
+// stage 4: loop filter -- one CTA per superblock, ordered by data flow (vp9_lf_sb.cuh has the
+// design and the per-thread phase functions; this is the CTA-level schedule and the flag protocol).
+// Flags per superblock t = sbr * sb_cols + sbc, value = the frame's epoch once set:
+//   F_edge = flags[2t]    last block column + the look-ahead columns (left edge of c+1 applied) are
+//                         in global memory
+//   F_done = flags[2t+1]  everything of the superblock is
+// Producer: all threads store (st.cg), block barrier, one thread fence + st.release.gpu.
+// Consumer: one thread polls (relaxed, then one ld.acquire.gpu), block barrier, ld.cg loads.
+template <typename Px, bool SUB>
+__global__ void __launch_bounds__(LfGeom<Px, SUB>::NT) k_lf_sb(const __grid_constant__ FrameBatch B) {
   const FrameParams &P = B.f[blockIdx.z];
   if (!P.do_lf) return;
-  // One persistent CTA per superblock ROW walks its row left to right: 4 (4:2:0) or 6 (4:4:4)
-  // worker warps only filter; a halo warp and two mover warps do all the global traffic.
-  //
-  // libvpx filters superblock by superblock: all vertical edges of c, all horizontal edges of c,
-  // then c+1 (vp9_loopfilter.c:1440-1467).  The only operation of c+1 that touches samples of c
-  // is its left-most vertical edge, so each step here runs
-  //     vertical edges 1..7 of c  ->  horizontal edges of c  ->  left edge of c+1
-  // which is the same order along every sample row and column, and leaves superblock c final at
-  // the end of its own step: the row below can start on c one step (not two) behind.
-  //
-  // Two tile buffers (64 columns of c + the first 8 of c+1, all planes) alternate:
-  //   workers, step c on buffer X:   vertical edges (thread = sample row) | B2 | horizontal edges
-  //     (thread = sample column) | B3 | left edge of c+1, copy the 8 look-ahead columns to the
-  //     front of the other buffer Y | B5.  No loads, no stores, three barriers.
-  //   movers, during step c:  store tile c-1 from Y to global and publish it (st.release), then
-  //     fill Y with superblock c+1 (prefetched into registers a step earlier) and prefetch c+2
-  //     | B3 | B5.
-  //   halo warp: waits until the row above has published superblock c, loads the 8 rows above it
-  //     into X while the workers are in the vertical pass | B2 | B3 | stores the filtered rows back.
-  // Only the first horizontal edge of a superblock depends on the row above, and only the halo
-  // warp ever waits for it.
+  typedef LfGeom<Px, SUB> G;
   extern __shared__ __align__(16) unsigned char lf_smem[];
-  typedef typename LfVec<Px>::T Vec;
-  constexpr int nworkers = NW;   // 128: 4:2:0, 192: 4:4:4
-  constexpr int kMovers = NW / 2;   // 64 / 96 threads move the tiles
+  __shared__ vp9b_lfm s_M[2];
+  __shared__ uint16_t s_dset[24];
+  __shared__ int s_t;
   const int tid = threadIdx.x;
-  constexpr int n_b2 = NW + 32, n_b3 = NW + 32 + kMovers, n_b5 = NW + kMovers, n_b7 = kMovers + 32;
-  const int lane = tid & 31;
-  constexpr bool sub = NW == 128;  // 4:2:0 (else 4:4:4)
-  // stride in samples: (stride bytes / 4) odd -> conflict-free row-per-thread walks
-  constexpr int tsY = sizeof(Px) == 1 ? 76 : 74, tsC = sub ? (sizeof(Px) == 1 ? 44 : 42) : tsY;
-  constexpr int nC = sub ? 32 : 64;
-  constexpr int offU = 72 * tsY, offV = 72 * tsY + (nC + 8) * tsC;
-  constexpr int kTileSamples = offV + (nC + 8) * tsC + 8;       // one buffer (all planes), padded
-  Px *const tiles = (Px *)lf_smem;
-  auto buf = [&](int c) -> Px * { return tiles + (c & 1) * kTileSamples; };
-  __shared__ int s_row;
-  if (threadIdx.x == 0) s_row = (int)(atomicAdd(P.ticket_lf, 1u) - P.ticket_lf_base);
+  if (tid == 0) s_t = (int)(atomicAdd(P.ticket_lf, 1u) - P.ticket_lf_base);
   __syncthreads();
-  const int sbr = s_row, sb_cols = P.sb_cols;
-  if (sbr >= P.sb_rows) return;   // the launch is as tall as the tallest frame of the batch
-  const int mi_row = sbr * 8;
-  const int hy = sbr > 0 ? 8 : 0;
-  uint32_t *prog = P.prog_lf;  // [sb_rows] prog_base + number of leading superblocks that are final
-  const uint32_t base = P.prog_base;
-
-  // vectors of 8 samples, flattened over the three planes:  interior rows / top-halo rows
-  constexpr int vY = 64 * 8, vC = nC * (nC >> 3);         // interior vectors per plane
-  constexpr int nInt = vY + 2 * vC;
-  constexpr int hYv = 8 * 8, hCv = 8 * (nC >> 3);         // top-halo vectors per plane
-  constexpr int nHalo = hYv + 2 * hCv;
-  constexpr int kMaxInt = (nInt + kMovers - 1) / kMovers, kMaxHalo = (nHalo + 31) / 32;  // slots per mover thread / halo lane
-  auto vec_addr = [&](int i, bool halo, const Px *&g, int &soff, int &pl, int &first) {
-    // flat vector index -> global address (superblock column 0), offset inside a tile buffer, plane
-    int p, r, v;
-    const int a = halo ? hYv : vY, bq = halo ? hCv : vC;
-    if (i < a) { p = 0; }
-    else if (i < a + bq) { p = 1; i -= a; }
-    else { p = 2; i -= a + bq; }
-    const int pn = p ? nC : 64, pts = p ? tsC : tsY, vpr = pn >> 3;
-    r = i / vpr; v = i % vpr;
-    first = v == 0;
-    if (halo) r -= 8;
-    const int stride = P.dst[p].stride;
-    g = (const Px *)P.dst[p].ptr + (ptrdiff_t)(sbr * pn + r) * stride + v * 8;
-    soff = (p == 0 ? 0 : (p == 1 ? offU : offV)) + (8 + r) * pts + v * 8;
-    pl = p;
+  const int t = s_t;
+  if (t >= P.sb_cols * P.sb_rows) return;   // the launch is as large as the largest frame of the batch
+  LfCtx<Px, SUB> C;
+  C.sbr = t / P.sb_cols;
+  C.sbc = t - C.sbr * P.sb_cols;
+  C.sb_cols = P.sb_cols; C.mi_rows = P.mi_rows; C.bd = P.bd;
+  C.has_next = C.sbc + 1 < P.sb_cols;
+  C.has_top = C.sbr > 0;
+  C.tile = (Px *)lf_smem;
+  C.dset = s_dset;
+  C.M = &s_M[0];
+  C.Mn = &s_M[1];
+  C.lf_lim = P.lf_lim;
+  C.lf_mblim = P.lf_mblim;
+#pragma unroll
+  for (int p = 0; p < 3; p++) {
+    const int n = p ? G::nC : 64;
+    C.stride[p] = P.dst[p].stride;
+    C.g[p] = (Px *)P.dst[p].ptr + (size_t)(C.sbr * n) * P.dst[p].stride + C.sbc * n;
+  }
+  uint32_t *const flags = P.lf_flags;
+  const uint32_t epoch = P.lf_epoch;
+  auto wait_flag = [&](int tt, int which) {
+    const uint32_t *f = flags + 2 * tt + which;
+    while (ld_relaxed(f) != epoch) __nanosleep(40);
+    (void)ld_acquire(f);
   };
-
-  if (tid >= nworkers + 32 && tid < nworkers + 64) {
-    // ------------------------------------------------------------------ publish warp
-    // waits until the movers have issued every store of a superblock, then releases it to the row
-    // below; the fence latency stays off everybody else's path
-    for (int sbc = 1; sbc <= sb_cols; sbc++) {
-      bar_sync(7, n_b7);
-      if (lane == 0) st_release(prog + sbr, base + (uint32_t)sbc);
-    }
-    return;
-  }
-  if (tid >= nworkers + 64) {
-    // ------------------------------------------------------------------ mover warps
-    const int mt = tid - (nworkers + 64);
-    Px *int_gp[kMaxInt];   // global address of the slot in superblock column 0 (advance: sbc * 64 or nC samples)
-    int int_soff[kMaxInt], int_pl[kMaxInt], int_first[kMaxInt];
-#pragma unroll
-    for (int k = 0; k < kMaxInt; k++) {
-      const int i = mt + k * kMovers;
-      int_pl[k] = -1;
-      int_first[k] = 0;
-      if (i < nInt) {
-        const Px *g;
-        vec_addr(i, false, g, int_soff[k], int_pl[k], int_first[k]);
-        int_gp[k] = (Px *)g;
-      }
-    }
-    auto wptr = [&](int k, int sbc) -> Px * { return int_gp[k] + sbc * (int_pl[k] ? nC : 64); };
-    Vec pre[kMaxInt];
-    // registers <- columns 8..63 of superblock sbc and the first 8 columns of sbc+1 (the slot that
-    // holds columns 0..7 fetches the look-ahead columns instead: 0..7 arrive through the carry)
-    auto prefetch = [&](int sbc) {
-#pragma unroll
-      for (int k = 0; k < kMaxInt; k++)
-        if (int_pl[k] >= 0) {
-          if (!int_first[k]) pre[k] = __ldcg((const Vec *)wptr(k, sbc));
-          else if (sbc + 1 < sb_cols) pre[k] = __ldcg((const Vec *)wptr(k, sbc + 1));
-        }
-    };
-    auto fill = [&](int sbc) {      // registers -> tile buffer of superblock sbc
-      Px *t = buf(sbc);
-#pragma unroll
-      for (int k = 0; k < kMaxInt; k++)
-        if (int_pl[k] >= 0) {
-          if (!int_first[k]) smem_put(t + int_soff[k], pre[k]);
-          else if (sbc + 1 < sb_cols) smem_put(t + int_soff[k] + (int_pl[k] ? nC : 64), pre[k]);
-        }
-    };
-    auto store = [&](int sbc) {     // tile buffer of superblock sbc (all 64 columns final) -> global
-      const Px *t = buf(sbc);
-#pragma unroll
-      for (int k = 0; k < kMaxInt; k++)
-        if (int_pl[k] >= 0) {
-          Vec vv;
-          smem_get(t + int_soff[k], vv);
-          __stcg((Vec *)wptr(k, sbc), vv);
-        }
-    };
-    // prologue: superblock 0 completely (its columns 0..7 have no carry), then prefetch 1
-    prefetch(0);
-    {
-      Px *t = buf(0);
-#pragma unroll
-      for (int k = 0; k < kMaxInt; k++)
-        if (int_pl[k] >= 0 && int_first[k]) smem_put(t + int_soff[k], __ldcg((const Vec *)wptr(k, 0)));
-    }
-    fill(0);
-    if (sb_cols > 1) prefetch(1);
-    bar_sync(5, n_b5);                   // "B5(-1)": buffer 0 is ready
-    for (int sbc = 0; sbc < sb_cols; sbc++) {
-      if (sbc >= 1) {
-        store(sbc - 1);
-        bar_sync(7, n_b7);               // every store of superblock sbc-1 has been issued: publish warp's turn
-      }
-      if (sbc + 1 < sb_cols) {
-        fill(sbc + 1);
-        if (sbc + 2 < sb_cols) prefetch(sbc + 2);
-      }
-      bar_sync(3, n_b3);                 // B3: our reads of the other buffer are done (the carry may write it)
-      bar_sync(5, n_b5);                 // B5: buffer of sbc is final, buffer of sbc+1 is filled
-    }
-    store(sb_cols - 1);
-    bar_sync(7, n_b7);
-    return;
-  }
-  if (tid >= nworkers) {
-    // ------------------------------------------------------------------ halo warp
-    int h_soff[kMaxHalo], h_pl[kMaxHalo];
-    Px *h_gp[kMaxHalo];
-#pragma unroll
-    for (int k = 0; k < kMaxHalo; k++) {
-      const int i = lane + k * 32;
-      h_pl[k] = -1;
-      if (hy && i < nHalo) {
-        const Px *g; int f;
-        vec_addr(i, true, g, h_soff[k], h_pl[k], f);
-        h_gp[k] = (Px *)g;
-      }
-    }
-    uint32_t seen = base;
-    for (int sbc = 0; sbc < sb_cols; sbc++) {
-      Px *t = buf(sbc);
-      if (hy) {
-        const int need = sbc + 1;   // the row above has finished superblock sbc
-        if ((int)(seen - base) < need) {
-          while ((int)((seen = ld_relaxed(prog + sbr - 1)) - base) < need) __nanosleep(20);
-          seen = ld_acquire(prog + sbr - 1);
-        }
-#pragma unroll
-        for (int k = 0; k < kMaxHalo; k++)
-          if (h_pl[k] >= 0) smem_put(t + h_soff[k], __ldcg((const Vec *)(h_gp[k] + sbc * (h_pl[k] ? nC : 64))));
-      }
-      bar_sync(2, n_b2);   // B2: halo rows in place / vertical pass done
-      bar_sync(3, n_b3);   // B3: horizontal pass done
-      if (hy) {
-#pragma unroll
-        for (int k = 0; k < kMaxHalo; k++)
-          if (h_pl[k] >= 0) {
-            Vec vv;
-            smem_get(t + h_soff[k], vv);
-            __stcg((Vec *)(h_gp[k] + sbc * (h_pl[k] ? nC : 64)), vv);
-          }
-      }
-    }
-    return;
-  }
-
-  // -------------------------------------------------------------------- worker warps
-  int my_plane, my_idx;
-  if (tid < 64) { my_plane = 0; my_idx = tid; }
-  else if (tid < 64 + nC) { my_plane = 1; my_idx = tid - 64; }
-  else { my_plane = 2; my_idx = tid - 64 - nC; }
-  const bool uvsub = my_plane && sub;
-  const int n = my_plane ? nC : 64, ts = my_plane ? tsC : tsY, nb = n >> 3;
-  const int toff = (my_plane == 0 ? 0 : (my_plane == 1 ? offU : offV)) + 8 * ts;   // sample (0,0) inside a buffer
-  // vertical edge c (0..7) of the superblock described by M at row pointer `row` (sample 0 of
-  // that superblock in this thread's row); `edge` selects the 8-aligned edge, `inner` the 4x4 one
-  auto v_edges = [&](const vp9b_lfm &M, Px *row, uint32_t sel_edge, uint32_t sel_inner) {
-    const int y = my_idx, r8 = y >> 3, pr = r8 & ~1;
-    uint32_t m16, m16n, m8, m4, m4i;
-    if (!uvsub) {
-      m16 = (uint32_t)(M.left_y[2] >> (r8 * 8)) & 0xff;
-      m16n = (uint32_t)(M.left_y[2] >> (pr * 8)) & (uint32_t)(M.left_y[2] >> (pr * 8 + 8)) & 0xff;
-      m8 = (uint32_t)(M.left_y[1] >> (r8 * 8)) & 0xff;
-      m4 = (uint32_t)(M.left_y[0] >> (r8 * 8)) & 0xff;
-      m4i = (uint32_t)(M.int_4x4_y >> (r8 * 8)) & 0xff;
-    } else {
-      m16 = (uint32_t)(M.left_uv[2] >> (r8 * 4)) & 0xf;
-      m16n = (uint32_t)(M.left_uv[2] >> (pr * 4)) & (uint32_t)(M.left_uv[2] >> (pr * 4 + 4)) & 0xf;
-      m8 = (uint32_t)(M.left_uv[1] >> (r8 * 4)) & 0xf;
-      m4 = (uint32_t)(M.left_uv[0] >> (r8 * 4)) & 0xf;
-      m4i = (uint32_t)(M.int_4x4_uv >> (r8 * 4)) & 0xf;
-    }
-    m16 &= sel_edge; m8 &= sel_edge; m4 &= sel_edge; m4i &= sel_inner;
-    uint32_t all = m16 | m8 | m4 | m4i;
-    if (!all) return;
-    // the eight levels of this mask row (and of the first row of the pair) in two loads, so that no
-    // edge of the chain waits for a level byte
-    const int lrow = uvsub ? 2 * r8 : r8, prow = uvsub ? 2 * pr : pr, lsh = uvsub ? 16 : 8;
-    const uint64_t lv_own = *(const uint64_t *)&M.lfl_y[lrow * 8], lv_pair = *(const uint64_t *)&M.lfl_y[prow * 8];
-    while (all) {
-      const int c = __ffs(all) - 1;
-      all &= all - 1;
-      const int lo = (int)(lv_own >> (c * lsh)) & 0xff;
-      Px *s = row + c * 8;
-      if ((m16 >> c) & 1) {
-        // dual 16 (both rows of the pair set): both bands use the first band's level
-        const int lv = ((m16n >> c) & 1) ? ((int)(lv_pair >> (c * lsh)) & 0xff) : lo;
-        lf_px<Px>(s, 1, 16, P.lf_mblim[lv], P.lf_lim[lv], lv >> 4, P.bd);
-      } else if ((m8 >> c) & 1) {
-        lf_px<Px>(s, 1, 8, P.lf_mblim[lo], P.lf_lim[lo], lo >> 4, P.bd);
-      } else if ((m4 >> c) & 1) {
-        lf_px<Px>(s, 1, 4, P.lf_mblim[lo], P.lf_lim[lo], lo >> 4, P.bd);
-      }
-      if ((m4i >> c) & 1) lf_px<Px>(s + 4, 1, 4, P.lf_mblim[lo], P.lf_lim[lo], lo >> 4, P.bd);
+  auto publish = [&](int which) {   // every thread's stores are issued; make them visible, then set the flag
+    __syncthreads();
+    if (tid == 0) {
+      __threadfence();
+      st_release(flags + 2 * t + which, epoch);
     }
   };
-  const bool row_valid = mi_row + (uvsub ? 2 * ((my_idx >> 3) & ~1) : ((my_idx >> 3) & ~1)) < P.mi_rows;
-
-  bar_sync(5, n_b5);                     // "B5(-1)": buffer 0 is ready
-  for (int sbc = 0; sbc < sb_cols; sbc++) {
-    const bool has_next = sbc + 1 < sb_cols;
-    Px *T = buf(sbc) + toff;
-    const vp9b_lfm &M = P.lfm[sbr * sb_cols + sbc];
-    constexpr bool w0 = true;
-    // the masks of c+1 are first needed by the left-edge pass at the end of this step: pull them
-    // into L1 now so that pass does not start with an L2 round trip
-    if (has_next && tid < 2) {
-      const char *nx = (const char *)&P.lfm[sbr * sb_cols + sbc + 1] + tid * 128;
-      asm volatile("prefetch.global.L1 [%0];" ::"l"(nx));
-    }
-    LFT(0)
-    // ---- vertical edges 1..7 and all inner 4x4 edges of c: thread = sample row
-    if (row_valid) v_edges(M, T + my_idx * ts, 0xfe, 0xff);
-    LFT(3)
-    bar_sync(2, n_b2);       // B2: + halo rows
-    LFT(4)
-    // ---- horizontal edges of c: thread = sample column.  The masks are tested at bit (row, column)
-    // directly; only a 16-wide edge needs its whole mask row (pairing)
-    if (w0) {
-      const int c = my_idx >> 3;
-      Px *col = T + my_idx;
-      uint64_t a16, a8, a4, ai;
-      int rsh, lstep;
-      if (!uvsub) {
-        a16 = M.above_y[2]; a8 = M.above_y[1]; a4 = M.above_y[0]; ai = M.int_4x4_y;
-        rsh = 3; lstep = 1;
-      } else {
-        a16 = M.above_uv[2]; a8 = M.above_uv[1]; a4 = M.above_uv[0]; ai = M.int_4x4_uv;
-        rsh = 2; lstep = 2;
-      }
-      if (mi_row == 0) {   // no edge on the frame's top row (the inner 4x4 edge stays)
-        const uint64_t keep = ~(uint64_t)((1u << (1 << rsh)) - 1);
-        a16 &= keep; a8 &= keep; a4 &= keep;
-      }
-      // rows of this superblock inside the frame; 4:2:0 drops the inner edge of the last odd row
-      const int rows_left = P.mi_rows - mi_row;
-      const int nrow = uvsub ? min(nb, (rows_left + 1) >> 1) : min(nb, rows_left);
-      if (uvsub && (rows_left & 1) && rows_left < 8) ai &= ~((uint64_t)0xf << (4 * (rows_left >> 1)));  // skip_border_4x4_r
-      // levels of this column for the eight mask rows, gathered up front (independent loads)
-      uint64_t lv_col = 0;
-#pragma unroll
-      for (int r = 0; r < 8; r++)
-        if (r < nrow) lv_col |= (uint64_t)M.lfl_y[(r * lstep) * 8 + c * lstep] << (8 * r);
-      for (int r = 0; r < nrow; r++) {
-        const int bit = (r << rsh) + c;
-        const uint32_t k16 = (uint32_t)(a16 >> bit) & 1, k8 = (uint32_t)(a8 >> bit) & 1, k4 = (uint32_t)(a4 >> bit) & 1,
-                       ki = (uint32_t)(ai >> bit) & 1;
-        if (!(k16 | k8 | k4 | ki)) continue;
-        Px *s = col + r * 8 * ts;
-        const uint8_t *lfl = &M.lfl_y[(r * lstep) * 8];
-        const int lvl = (int)(lv_col >> (8 * r)) & 0xff;
-        if (k16) {
-          // greedy pairing from the left (vpx_lpf_horizontal_16_dual): the second block of a
-          // pair is filtered with the first block's thresholds.  run = number of set bits directly
-          // below column c in this mask row
-          const uint32_t row16 = (uint32_t)(a16 >> (r << rsh)) & 0xff;
-          const uint32_t below = ~row16 & ((1u << c) - 1);          // zero bits below c
-          const int run = below ? c - 1 - (31 - __clz(below)) : c;
-          const int lv = (run & 1) ? lfl[(c - 1) * lstep] : lvl;
-          lf_px<Px>(s, ts, 16, P.lf_mblim[lv], P.lf_lim[lv], lv >> 4, P.bd);
-        } else if (k8) {
-          lf_px<Px>(s, ts, 8, P.lf_mblim[lvl], P.lf_lim[lvl], lvl >> 4, P.bd);
-        } else if (k4) {
-          lf_px<Px>(s, ts, 4, P.lf_mblim[lvl], P.lf_lim[lvl], lvl >> 4, P.bd);
-        }
-        if (!k16 && ki) lf_px<Px>(s + 4 * ts, ts, 4, P.lf_mblim[lvl], P.lf_lim[lvl], lvl >> 4, P.bd);
-      }
-    }
-    LFT(5)
-    bar_sync(3, n_b3);       // B3
-    LFT(6)
-    // ---- left edge of c+1 (reads / writes the last 8 columns of c and the look-ahead columns), then
-    // the look-ahead columns move to the front of the next buffer (same thread: no barrier needed)
-    if (has_next) {
-      Px *row = T + my_idx * ts;
-      if (row_valid) v_edges(P.lfm[sbr * sb_cols + sbc + 1], row + n, 0x01, 0x00);
-      Vec vv;
-      smem_get(row + n, vv);
-      smem_put(buf(sbc + 1) + toff + my_idx * ts, vv);
-    }
-    bar_sync(5, n_b5);       // B5: this buffer is final, the next one is filled
-    LFT(7)
+  // masks of this superblock and the next one (40 words each)
+  if (tid < 80) {
+    const int which = tid >= 40;
+    const uint32_t *src = (const uint32_t *)&P.lfm[t + ((which && C.has_next) ? 1 : 0)];
+    ((uint32_t *)s_M)[tid] = __ldg(src + (which ? tid - 40 : tid));
   }
+  lf_phase_load_interior(C, tid);
+  __syncthreads();
+  const bool chain = __syncthreads_or(lf_phase_dsets(C, tid)) != 0;
+  lf_phase_vertical(C, tid, false);                    // A
+  if (chain && C.sbc > 0) {                            // D before H7: the row serialises through F_edge
+    if (tid == 0) wait_flag(t - 1, 0);
+    __syncthreads();
+    lf_phase_merge_left(C, tid);
+    lf_phase_vertical(C, tid, true);
+  }
+  if (C.has_top) {
+    if (tid == 0) wait_flag(t - P.sb_cols, 0);
+    __syncthreads();
+    lf_phase_load_top(C, tid, 0);
+  }
+  __syncthreads();
+  lf_phase_horizontal(C, tid, 0);                      // H7
+  __syncthreads();
+  if (C.has_next) {
+    lf_phase_next_left_edge(C, tid);                   // E
+    __syncthreads();
+  }
+  lf_phase_store(C, tid, 0);
+  publish(0);
+  if (tid == 0) {
+    if (!chain && C.sbc > 0) wait_flag(t - 1, 0);
+    if (C.has_top) wait_flag(t - P.sb_cols, 1);
+  }
+  __syncthreads();
+  if (!chain && C.sbc > 0) {                           // D
+    lf_phase_merge_left(C, tid);
+    lf_phase_vertical(C, tid, true);
+  }
+  lf_phase_load_top(C, tid, 1);
+  __syncthreads();
+  lf_phase_horizontal(C, tid, 1);                      // H
+  __syncthreads();
+  lf_phase_store(C, tid, 1);
+  publish(1);
 }
 
 // output path: 16-bit samples -> 8 bits (truncating shift, highbd_img_downshift in tools_common.c)
@@ -1744,6 +1406,7 @@ struct vp9gpu_ctx {
   int ws_sb_cols = 0, ws_sb_rows = 0, ws_mi_cols = 0, ws_mi_rows = 0;
   MiEntry *d_mi = nullptr;
   uint32_t *d_tickets = nullptr;  // wavefront progress counters
+  uint32_t *d_lf_flags = nullptr; // loop-filter data-flow flags, 2 per superblock
   uint32_t epoch = 0;
   cudaEvent_t join_ev = nullptr;  // joins this context's stream with a batch leader's (submit_device_multi)
   unsigned attr_done = 0;         // kernels whose dynamic shared-memory limit has been raised on this device
@@ -1842,6 +1505,7 @@ extern "C" void vp9gpu_destroy(vp9gpu_ctx *ctx) {
   cudaFree(ctx->d_out8);
   cudaFree(ctx->d_resid);
   cudaFree(ctx->d_tickets);
+  cudaFree(ctx->d_lf_flags);
   cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -1971,6 +1635,10 @@ static int setup_workspace(vp9gpu_ctx *ctx, const vp9b_frame_hdr *h) {
     ctx->d_mi = nullptr;
     CK(cudaMalloc(&ctx->d_mi, sizeof(MiEntry) * (size_t)h->mi_cols * h->mi_rows));
     CK(cudaMemsetAsync(ctx->d_mi, 0, sizeof(MiEntry) * (size_t)h->mi_cols * h->mi_rows, ctx->stream));
+    cudaFree(ctx->d_lf_flags);
+    ctx->d_lf_flags = nullptr;
+    CK(cudaMalloc(&ctx->d_lf_flags, sizeof(uint32_t) * 2 * (size_t)h->sb_cols * h->sb_rows));
+    CK(cudaMemsetAsync(ctx->d_lf_flags, 0, sizeof(uint32_t) * 2 * (size_t)h->sb_cols * h->sb_rows, ctx->stream));
     if (!ctx->d_tickets) {
       CK(cudaMalloc(&ctx->d_tickets, sizeof(uint32_t) * (4096 + 64)));
       CK(cudaMemsetAsync(ctx->d_tickets, 0, sizeof(uint32_t) * (4096 + 64), ctx->stream));
@@ -2016,7 +1684,7 @@ static int launch_batch(vp9gpu_ctx *const *ctxs, FrameBatch &B, int n) {
       g_intra = std::max(g_intra, (3 * P.sb_rows + kWaveWarps - 1) / kWaveWarps);
     }
     P.do_lf = P.do_lf && stop == 0;
-    if (P.do_lf) g_lf = std::max(g_lf, P.sb_rows);
+    if (P.do_lf) g_lf = std::max(g_lf, P.sb_rows * P.sb_cols);
   }
   // tickets: every participating frame's counter advances by the number of CTAs launched for it
   for (int i = 0; i < n; i++) {
@@ -2059,20 +1727,9 @@ static int launch_batch(vp9gpu_ctx *const *ctxs, FrameBatch &B, int n) {
   }
   if (prof) cudaEventRecord(ctx->prof_ev[4], st);
   if (g_lf) {
-    const bool sub = B.f[0].ss_x != 0;
-    const int tsY = sizeof(Px) == 1 ? 76 : 74, tsC = sub ? (sizeof(Px) == 1 ? 44 : 42) : tsY, nC = sub ? 32 : 64;
-    // two tile buffers; threads = worker warps + halo warp + publish warp + mover warps
-    const size_t smem = 2 * sizeof(Px) * (size_t)(72 * tsY + 2 * (nC + 8) * tsC + 8) + 32;
-    if (sub) {
-      k_loopfilter<Px, 128><<<dim3(g_lf, 1, n), 128 + 64 + 64, smem, st>>>(B);
-    } else {
-      const unsigned abit = sizeof(Px) == 1 ? 4u : 8u;
-      if (!(ctx->attr_done & abit)) {
-        CK(cudaFuncSetAttribute(k_loopfilter<Px, 192>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        ctx->attr_done |= abit;
-      }
-      k_loopfilter<Px, 192><<<dim3(g_lf, 1, n), 192 + 64 + 96, smem, st>>>(B);
-    }
+    // one CTA per superblock of the largest frame in the batch; threads = sample rows of the three planes
+    if (B.f[0].ss_x) k_lf_sb<Px, true><<<dim3(g_lf, 1, n), LfGeom<Px, true>::NT, LfGeom<Px, true>::kTileBytes, st>>>(B);
+    else k_lf_sb<Px, false><<<dim3(g_lf, 1, n), LfGeom<Px, false>::NT, LfGeom<Px, false>::kTileBytes, st>>>(B);
     ctx->launches++;
   }
   if (prof) {
@@ -2199,12 +1856,14 @@ static int prepare_frame(vp9gpu_ctx *ctx, const uint8_t *d_packed, const vp9b_fr
   // progress counters: [0, 3*1024) intra (plane, row), [3072, 4096) loop filter.  Values are
   // prog_base + count with prog_base advancing by 2048 per frame; cleared only when it wraps.
   if (h->sb_rows > 1024 || h->sb_cols >= 2048) { ctx->err = "frame too large"; return VP9B_ERR_UNSUP; }
-  ctx->epoch++;
+  if (++ctx->epoch == 0) ctx->epoch = 1;
   if ((ctx->epoch & 0xfffff) == 0) CK(cudaMemsetAsync(ctx->d_tickets, 0, sizeof(uint32_t) * 4096, ctx->stream));
   P.prog_intra = ctx->d_tickets;
   P.prog_lf = ctx->d_tickets + 3072;
   P.prog_base = (ctx->epoch & 0xfffff) << 11;
   P.ticket_lf = ctx->d_tickets + 4096;
+  P.lf_flags = ctx->d_lf_flags;
+  P.lf_epoch = ctx->epoch;   // never 0: the flags start out as 0
   P.ticket_intra = ctx->d_tickets + 4097;
   memcpy(P.lf_lim, h->lf_lim, 64);
   memcpy(P.lf_mblim, h->lf_mblim, 64);

@@ -1073,3 +1073,12 @@ void vp9ref_lpf_edge8(uint16_t *s, int pitch, int vertical, int size, int blimit
     else lf_edge_px(s + i, pitch, size, blimit, limit, thresh, bd);
   }
 }
+
+/* Test hook: the raw sample array of a plane (aligned size + padding), for stage-level checks
+ * that need the samples between the crop size and the aligned size. */
+uint16_t *vp9ref_plane(vp9ref_ctx *c, int slot, int plane, int *stride, int *rows) {
+  if (!c || slot < 0 || slot >= VP9B_NUM_SLOTS || plane < 0 || plane > 2 || !c->slot[slot].valid) return NULL;
+  *stride = c->slot[slot].stride[plane];
+  *rows = c->slot[slot].alloc_h[plane];
+  return c->slot[slot].plane[plane];
+}
