@@ -1,7 +1,9 @@
 // C ABI, host-only part: parser + superframe splitter (include/vp9_b200.h section 2).
 #include <string.h>
 
+#include <exception>
 #include <new>
+#include <string>
 
 #include "vp9_b200.h"
 #include "vp9_parser.h"
@@ -17,7 +19,10 @@ vp9b_parser *vp9b_parser_create(void) { return new (std::nothrow) vp9b_parser();
 
 void vp9b_parser_destroy(vp9b_parser *p) { delete p; }
 
-const char *vp9b_parser_last_error(vp9b_parser *p) { return p ? p->impl.error().c_str() : "null parser"; }
+const char *vp9b_parser_last_error(vp9b_parser *p) {
+  if (!p) return "null parser";
+  return p->err.empty() ? p->impl.error().c_str() : p->err.c_str();
+}
 
 int vp9b_parser_parse(vp9b_parser *p, const uint8_t *data, size_t size, const void **packed,
                       size_t *bytes, int *show_slot) {
@@ -25,7 +30,17 @@ int vp9b_parser_parse(vp9b_parser *p, const uint8_t *data, size_t size, const vo
   *packed = nullptr;
   *bytes = 0;
   *show_slot = -1;
-  const int e = p->impl.parse(data, size);
+  p->err.clear();
+  int e;
+  try {   // nothing may propagate through the C ABI (a hostile header can still ask for a lot of memory)
+    e = p->impl.parse(data, size);
+  } catch (const std::bad_alloc &) {
+    p->err = "out of memory";
+    return VP9B_ERR_MEM;
+  } catch (const std::exception &ex) {
+    p->err = ex.what();
+    return VP9B_ERR_INVALID;
+  }
   if (e) return e;
   *packed = p->impl.packed();
   *bytes = p->impl.packed_bytes();

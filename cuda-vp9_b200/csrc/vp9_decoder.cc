@@ -29,6 +29,7 @@ vp9b_decoder *vp9b_decoder_create(int device) {
     delete d;
     return nullptr;
   }
+  vp9gpu_set_validation(d->gpu, 0);   // packed buffers come from vp9b_parser_* of this library
   return d;
 }
 

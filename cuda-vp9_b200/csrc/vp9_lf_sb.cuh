@@ -1,4 +1,4 @@
-// Loop filter, one CTA per 64x64 superblock, ordered by data flow instead of by a row walk.
+// Loop filter: one persistent CTA per superblock COLUMN, superblocks ordered by data flow.
 //
 // libvpx filters superblock by superblock in raster order: all vertical edges of a superblock,
 // then all its horizontal edges (vp9_loopfilter.c:1440-1467, vp9_filter_block_plane_ss00/ss11
@@ -10,28 +10,31 @@
 //   * vertical before horizontal wherever they overlap -- EXCEPT that the horizontal edges of the
 //     last 8 columns of superblock c run before the left-most vertical edge of c+1 (which reaches
 //     8 samples back into c).
-// A CTA therefore owns superblock (r, c) plus 8 look-ahead columns of (r, c+1) and runs
+// The horizontal edges chain down the frame (the top edge of every superblock needs the final
+// bottom rows of the one above), so a worker owns a whole superblock column and keeps those 8 rows
+// in shared memory from one superblock to the next: no global round trip on the long dependency.
+// For superblock (r, c) -- tile = 64x64 (+ chroma) plus 8 look-ahead columns of (r, c+1) -- it runs
 //   A   every vertical edge of c that does not (transitively) overlap the left edge of c
-//       [that left edge was applied by CTA (r, c-1) on its look-ahead columns]
-//   H7  horizontal edges of the last block column of c        (needs the 8 rows above: F_edge(r-1,c))
+//       [that left edge is applied by worker c-1 on its look-ahead columns]
+//   H7  horizontal edges of the last block column of c
 //   E   the left vertical edge of c+1 on the look-ahead columns
 //       -> store last block column + look-ahead, release F_edge(r, c)
 //   D   after F_edge(r, c-1): take over the samples the left edge changed, then the vertical edges
 //       that depend on them (rarely any: an 8/16-wide edge every 8+ samples does not chain)
-//   H   horizontal edges of the other block columns          (needs the 8 rows above: F_done(r-1,c))
-//       -> store, release F_done(r, c)
-// If the dependent set D reaches the last block column ("chain"), D runs before H7 and the
-// superblocks of that row serialise through F_edge; otherwise nothing in a row waits for its left
-// neighbour until its own edge work is published, and the only long dependency is one hop per
-// superblock row.  CTAs take their superblock from a ticket counter in raster order, so a CTA only
-// ever waits for CTAs that started before it.
+//   H   horizontal edges of the other block columns -> store
+// and carries the bottom 8 rows over as the next superblock's top rows.  The next superblock's
+// samples are fetched while the current one is filtered.  If the dependent set D reaches the last
+// block column ("chain"), D runs before H7 and the workers of that row serialise through F_edge;
+// otherwise a worker publishes its edge before it looks at its left neighbour, and the columns
+// advance side by side.  Workers take their column from a ticket counter, so a worker only ever
+// waits for one that started before it.
 //
 // Filter arithmetic: vpx_dsp/loopfilter.c:18-357 (8-bit) == :360-743 evaluated at bd; selection
 // and level quirks: filter_selectively_vert_row2 / _horiz (vp9_loopfilter.c:297-650).
 //
 // The per-thread functions are compiled for the device and, with VP9B_EMUL, for the host: the CPU
-// emulation in tests/emul runs the same phase functions thread by thread in an adversarial
-// schedule and is compared with the oracle (no GPU needed to validate the decomposition).
+// emulation in tests/emul runs the same phase functions thread by thread in adversarial but legal
+// schedules and is compared with the oracle (no GPU needed to validate the decomposition).
 #pragma once
 #include <stdint.h>
 
@@ -155,7 +158,10 @@ template <typename Px, bool SUB> struct LfGeom {
   static constexpr int pitchC = SUB ? (sizeof(Px) == 1 ? 44 : 42) : pitchY;
   static constexpr int offU = 72 * pitchY, offV = offU + (nC + 8) * pitchC;
   static constexpr int kTileSamples = offV + (nC + 8) * pitchC + 8;
-  static constexpr size_t kTileBytes = (size_t)kTileSamples * sizeof(Px);
+  static constexpr size_t kTileBytes = (((size_t)kTileSamples * sizeof(Px)) + 15) & ~(size_t)15;
+  static constexpr int kInterior = 64 * 8 + 2 * nC * (nC >> 3);       // 8-sample vectors of the three planes' interiors
+  static constexpr int kPre = kInterior / NT + 1;                       // per thread: interior slots + one look-ahead vector
+  static_assert(kInterior % NT == 0, "interior vectors must divide evenly over the threads");
 };
 
 // everything one CTA needs to know about its superblock
@@ -274,96 +280,152 @@ LF_HD bool lf_row_valid(bool uvsub, int y, int mi_row, int mi_rows) {
   return mi_row + (uvsub ? 2 * pr : pr) < mi_rows;
 }
 
-// Horizontal edges of sample column x (0..n-1) of one plane: block rows top to bottom
-// (filter_selectively_horiz, vp9_loopfilter.c:453-650: priority 16 > 8 > 4, inner edge unless 16;
-// a run of 16-wide edges is paired greedily from the left and the second block of a pair is
-// filtered with the first block's thresholds).  col = sample (0, x) in the tile, ts = row pitch.
-template <typename Px>
-LF_HD void lf_h_col(const vp9b_lfm &M, bool uvsub, int x, Px *col, int ts, int mi_row, int mi_rows, int nb,
-                    const uint8_t *lf_lim, const uint8_t *lf_mblim, int bd) {
-  const int c = x >> 3;
-  uint64_t a16, a8, a4, ai;
-  int rsh, lstep;
+// Horizontal edges (filter_selectively_horiz, vp9_loopfilter.c:453-650: priority 16 > 8 > 4, inner
+// edge unless 16; a run of 16-wide edges is paired greedily from the left and the second block of a
+// pair is filtered with the first block's thresholds).
+struct LfHMasks {
+  uint64_t a16, a8, a4, ai;   // above masks of the plane, frame-edge rules applied
+  int rsh, lstep, nrow;       // log2(block columns per mask row), level step, block rows inside the frame
+};
+LF_HD LfHMasks lf_h_masks(const vp9b_lfm &M, bool uvsub, int mi_row, int mi_rows, int nb) {
+  LfHMasks H;
   if (!uvsub) {
-    a16 = M.above_y[2]; a8 = M.above_y[1]; a4 = M.above_y[0]; ai = M.int_4x4_y;
-    rsh = 3; lstep = 1;
+    H.a16 = M.above_y[2]; H.a8 = M.above_y[1]; H.a4 = M.above_y[0]; H.ai = M.int_4x4_y;
+    H.rsh = 3; H.lstep = 1;
   } else {
-    a16 = M.above_uv[2]; a8 = M.above_uv[1]; a4 = M.above_uv[0]; ai = M.int_4x4_uv;
-    rsh = 2; lstep = 2;
+    H.a16 = M.above_uv[2]; H.a8 = M.above_uv[1]; H.a4 = M.above_uv[0]; H.ai = M.int_4x4_uv;
+    H.rsh = 2; H.lstep = 2;
   }
   if (mi_row == 0) {   // no edge on the frame's top row (the inner 4x4 edge stays)
-    const uint64_t keep = ~(uint64_t)((1u << (1 << rsh)) - 1);
-    a16 &= keep; a8 &= keep; a4 &= keep;
+    const uint64_t keep = ~(uint64_t)((1u << (1 << H.rsh)) - 1);
+    H.a16 &= keep; H.a8 &= keep; H.a4 &= keep;
   }
   // rows of this superblock inside the frame; 4:2:0 drops the inner edge of the last odd row
   const int rows_left = mi_rows - mi_row;
-  const int nrow = uvsub ? min(nb, (rows_left + 1) >> 1) : min(nb, rows_left);
-  if (uvsub && (rows_left & 1) && rows_left < 8) ai &= ~((uint64_t)0xf << (4 * (rows_left >> 1)));  // skip_border_4x4_r
-  for (int r = 0; r < nrow; r++) {
-    const int bit = (r << rsh) + c;
-    const uint32_t k16 = (uint32_t)(a16 >> bit) & 1, k8 = (uint32_t)(a8 >> bit) & 1, k4 = (uint32_t)(a4 >> bit) & 1,
-                   ki = (uint32_t)(ai >> bit) & 1;
-    if (!(k16 | k8 | k4 | ki)) continue;
-    Px *s = col + r * 8 * ts;
-    const uint8_t *lfl = &M.lfl_y[(r * lstep) * 8];
-    const int lvl = lfl[c * lstep];
-    if (k16) {
-      const uint32_t row16 = (uint32_t)(a16 >> (r << rsh)) & 0xff;
-      const uint32_t below = ~row16 & ((1u << c) - 1);          // zero bits below c
-      const int run = below ? c - 1 - (31 - lf_clz(below)) : c;
-      const int lv = (run & 1) ? lfl[(c - 1) * lstep] : lvl;
-      lf_px<Px>(s, ts, 16, lf_mblim[lv], lf_lim[lv], lv >> 4, bd);
-    } else if (k8) {
-      lf_px<Px>(s, ts, 8, lf_mblim[lvl], lf_lim[lvl], lvl >> 4, bd);
-    } else if (k4) {
-      lf_px<Px>(s, ts, 4, lf_mblim[lvl], lf_lim[lvl], lvl >> 4, bd);
-    }
-    if (!k16 && ki) lf_px<Px>(s + 4 * ts, ts, 4, lf_mblim[lvl], lf_lim[lvl], lvl >> 4, bd);
+  H.nrow = uvsub ? min(nb, (rows_left + 1) >> 1) : min(nb, rows_left);
+  if (uvsub && (rows_left & 1) && rows_left < 8) H.ai &= ~((uint64_t)0xf << (4 * (rows_left >> 1)));  // skip_border_4x4_r
+  return H;
+}
+// the edges of block row r in sample column x (block column c = x >> 3); col = sample (0, x)
+template <typename Px>
+LF_HD void lf_h_unit(const LfHMasks &H, const vp9b_lfm &M, int x, int r, Px *col, int ts, const uint8_t *lf_lim,
+                     const uint8_t *lf_mblim, int bd) {
+  const int c = x >> 3, bit = (r << H.rsh) + c;
+  const uint32_t k16 = (uint32_t)(H.a16 >> bit) & 1, k8 = (uint32_t)(H.a8 >> bit) & 1, k4 = (uint32_t)(H.a4 >> bit) & 1,
+                 ki = (uint32_t)(H.ai >> bit) & 1;
+  if (!(k16 | k8 | k4 | ki)) return;
+  Px *s = col + r * 8 * ts;
+  const uint8_t *lfl = &M.lfl_y[(r * H.lstep) * 8];
+  const int lvl = lfl[c * H.lstep];
+  if (k16) {
+    const uint32_t row16 = (uint32_t)(H.a16 >> (r << H.rsh)) & 0xff;
+    const uint32_t below = ~row16 & ((1u << c) - 1);          // zero bits below c
+    const int run = below ? c - 1 - (31 - lf_clz(below)) : c;
+    const int lv = (run & 1) ? lfl[(c - 1) * H.lstep] : lvl;
+    lf_px<Px>(s, ts, 16, lf_mblim[lv], lf_lim[lv], lv >> 4, bd);
+  } else if (k8) {
+    lf_px<Px>(s, ts, 8, lf_mblim[lvl], lf_lim[lvl], lvl >> 4, bd);
+  } else if (k4) {
+    lf_px<Px>(s, ts, 4, lf_mblim[lvl], lf_lim[lvl], lvl >> 4, bd);
+  }
+  if (!k16 && ki) lf_px<Px>(s + 4 * ts, ts, 4, lf_mblim[lvl], lf_lim[lvl], lvl >> 4, bd);
+}
+// one thread walks a whole sample column: only the block rows that have an edge are visited
+template <typename Px>
+LF_HD void lf_h_col(const vp9b_lfm &M, bool uvsub, int x, Px *col, int ts, int mi_row, int mi_rows, int nb,
+                    const uint8_t *lf_lim, const uint8_t *lf_mblim, int bd) {
+  const LfHMasks H = lf_h_masks(M, uvsub, mi_row, mi_rows, nb);
+  const int c = x >> 3;
+  const uint64_t colsel = uvsub ? 0x1111ull : 0x0101010101010101ull;
+  uint64_t todo = ((H.a16 | H.a8 | H.a4 | H.ai) >> c) & colsel;
+  if (H.nrow < nb) todo &= ((uint64_t)1 << (H.nrow << H.rsh)) - 1;
+  while (todo) {
+    const int bit0 = (todo & 0xffffffffu) ? lf_ffs((uint32_t)todo) - 1 : 32 + lf_ffs((uint32_t)(todo >> 32)) - 1;
+    todo &= todo - 1;
+    lf_h_unit<Px>(H, M, x, bit0 >> H.rsh, col, ts, lf_lim, lf_mblim, bd);
   }
 }
-
 // ------------------------------------------------------------------------------------------
 // phase functions: each is called by every thread of the CTA (tid = 0..NT-1) between barriers
 
-// dependent sets of all bands; returns this thread's contribution to "the set reaches the last
-// block column" (chain)
+// Dependent sets of one superblock: unit u = 0 .. 8 + 2 * nbC - 1 is a (plane, band); writes
+// dset[plane * 8 + band] and returns whether the set reaches the last block column (chain).
 template <typename Px, bool SUB>
-LF_HD bool lf_phase_dsets(LfCtx<Px, SUB> &C, int tid) {
+LF_HD bool lf_plan_unit(const vp9b_lfm &M, bool has_left, int u, uint16_t *dset) {
   constexpr int nbC = LfGeom<Px, SUB>::nC >> 3;
-  // thread -> (plane, band): 8 luma bands, nbC bands for each chroma plane
   int plane, band;
-  if (tid < 8) { plane = 0; band = tid; }
-  else if (tid < 8 + nbC) { plane = 1; band = tid - 8; }
-  else if (tid < 8 + 2 * nbC) { plane = 2; band = tid - 8 - nbC; }
-  else return false;
+  if (u < 8) { plane = 0; band = u; }
+  else if (u < 8 + nbC) { plane = 1; band = u - 8; }
+  else { plane = 2; band = u - 8 - nbC; }
   const bool uvsub = plane && SUB;
   const int nb = plane ? nbC : 8;
   uint32_t m16, m8, m4, m4i;
-  lf_band_masks_v(*C.M, uvsub, band, m16, m8, m4, m4i);
-  const uint32_t d = lf_dependent_set(m16, m8, m4, m4i, nb, C.sbc > 0);
-  C.dset[plane * 8 + band] = (uint16_t)d;
+  lf_band_masks_v(M, uvsub, band, m16, m8, m4, m4i);
+  const uint32_t d = lf_dependent_set(m16, m8, m4, m4i, nb, has_left);
+  dset[plane * 8 + band] = (uint16_t)d;
   return (d >> (2 * nb - 2)) != 0;
 }
+template <typename Px, bool SUB> struct LfPlanUnits { static constexpr int value = 8 + 2 * (LfGeom<Px, SUB>::nC >> 3); };
 
-// interior rows 0..n-1, columns 0..n-1 (+ the look-ahead columns): nobody writes them before this
-// CTA is done, except the left edge of this superblock (merged later)
+// Fetch of a superblock's interior (rows 0..n-1, columns 0..n-1, + the look-ahead columns) into
+// registers, and its later commit to a tile buffer: issued one superblock ahead so that the loads
+// fly while the current superblock is filtered.  Nobody else writes these samples before this
+// worker is done with them, except the left edge of the superblock (merged later).
+// g[p] = global address of sample (0,0) of that superblock.
 template <typename Px, bool SUB>
-LF_HD void lf_phase_load_interior(const LfCtx<Px, SUB> &C, int tid) {
+LF_HD void lf_phase_prefetch(Px *const g[3], const int stride[3], bool has_next, int tid,
+                             typename LfVecT<Px>::T (&pre)[LfGeom<Px, SUB>::kPre]) {
   typedef LfGeom<Px, SUB> G;
   typedef typename LfVecT<Px>::T Vec;
   constexpr int vY = 64 * 8, vC = G::nC * (G::nC >> 3);
-  for (int i = tid; i < vY + 2 * vC; i += G::NT) {
-    int p = 0, k = i;
-    if (k >= vY) { k -= vY; p = 1; if (k >= vC) { k -= vC; p = 2; } }
+#pragma unroll
+  for (int k = 0; k < G::kPre - 1; k++) {
+    int p = 0, i = tid + k * G::NT;
+    if (i >= vY) { i -= vY; p = 1; if (i >= vC) { i -= vC; p = 2; } }
     const int lg = (p && SUB) ? 2 : 3;                 // log2(vectors per row)
-    const int r = k >> lg, v = k & ((1 << lg) - 1);
-    lf_smem_put(lf_tile_at(C, p, r, v * 8), lf_ldg<Vec>(C.g[p] + (size_t)r * C.stride[p] + v * 8));
+    const int r = i >> lg, v = i & ((1 << lg) - 1);
+    pre[k] = lf_ldg<Vec>(g[p] + (size_t)r * stride[p] + v * 8);
+  }
+  if (has_next) {
+    int p, r;
+    lf_role<Px, SUB>(tid, p, r);
+    pre[G::kPre - 1] = lf_ldg<Vec>(g[p] + (size_t)r * stride[p] + (p ? G::nC : 64));
+  }
+}
+template <typename Px, bool SUB>
+LF_HD void lf_phase_commit(const LfCtx<Px, SUB> &C, int tid, const typename LfVecT<Px>::T (&pre)[LfGeom<Px, SUB>::kPre]) {
+  typedef LfGeom<Px, SUB> G;
+  constexpr int vY = 64 * 8, vC = G::nC * (G::nC >> 3);
+#pragma unroll
+  for (int k = 0; k < G::kPre - 1; k++) {
+    int p = 0, i = tid + k * G::NT;
+    if (i >= vY) { i -= vY; p = 1; if (i >= vC) { i -= vC; p = 2; } }
+    const int lg = (p && SUB) ? 2 : 3;
+    lf_smem_put(lf_tile_at(C, p, i >> lg, (i & ((1 << lg) - 1)) * 8), pre[k]);
   }
   if (C.has_next) {
     int p, r;
     lf_role<Px, SUB>(tid, p, r);
-    const int n = p ? G::nC : 64;
-    lf_smem_put(lf_tile_at(C, p, r, n), lf_ldg<Vec>(C.g[p] + (size_t)r * C.stride[p] + n));
+    lf_smem_put(lf_tile_at(C, p, r, p ? G::nC : 64), pre[G::kPre - 1]);
+  }
+}
+
+// bottom 8 rows of the finished superblock -> top rows (-8..-1) of the next one's tile buffer
+template <typename Px, bool SUB>
+LF_HD void lf_phase_carry(const LfCtx<Px, SUB> &C, Px *next_tile, int tid) {
+  typedef LfGeom<Px, SUB> G;
+  typedef typename LfVecT<Px>::T Vec;
+  constexpr int hY = 8 * 8, hC = 8 * (G::nC >> 3);    // vectors per plane
+  LfCtx<Px, SUB> N = C;
+  N.tile = next_tile;
+  for (int i = tid; i < hY + 2 * hC; i += G::NT) {
+    int p = 0, k = i;
+    if (k >= hY) { k -= hY; p = 1; if (k >= hC) { k -= hC; p = 2; } }
+    const int lg = (p && SUB) ? 2 : 3;
+    const int r = k >> lg, v = k & ((1 << lg) - 1), n = p ? G::nC : 64;
+    Vec t;
+    lf_smem_get(lf_tile_at(C, p, n - 8 + r, v * 8), t);
+    lf_smem_put(lf_tile_at(N, p, r - 8, v * 8), t);
   }
 }
 
@@ -414,26 +476,7 @@ LF_HD void lf_phase_merge_left(const LfCtx<Px, SUB> &C, int tid) {
   for (int i = 0; i < reach; i++) t[i] = tmp[i];
 }
 
-// the 8 rows above the superblock: part 0 = last block column (final after F_edge(r-1, c)),
-// part 1 = the other block columns (final after F_done(r-1, c))
-template <typename Px, bool SUB>
-LF_HD void lf_phase_load_top(const LfCtx<Px, SUB> &C, int tid, int part) {
-  typedef LfGeom<Px, SUB> G;
-  typedef typename LfVecT<Px>::T Vec;
-  if (!C.has_top) return;
-  constexpr int hY = 8 * 8, hC = 8 * (G::nC >> 3);    // vectors per plane
-  for (int i = tid; i < hY + 2 * hC; i += G::NT) {
-    int p = 0, k = i;
-    if (k >= hY) { k -= hY; p = 1; if (k >= hC) { k -= hC; p = 2; } }
-    const int lg = (p && SUB) ? 2 : 3;
-    const int r = (k >> lg) - 8, v = k & ((1 << lg) - 1);
-    const bool last = v == (1 << lg) - 1;
-    if (last != (part == 0)) continue;
-    lf_smem_put(lf_tile_at(C, p, r, v * 8), lf_ldg<Vec>(C.g[p] + (ptrdiff_t)r * C.stride[p] + v * 8));
-  }
-}
-
-// horizontal edges: part 0 = last block column, part 1 = the others
+// horizontal edges, one thread per sample column: part 0 = last block column, part 1 = the others
 template <typename Px, bool SUB>
 LF_HD void lf_phase_horizontal(const LfCtx<Px, SUB> &C, int tid, int part) {
   typedef LfGeom<Px, SUB> G;
@@ -441,49 +484,53 @@ LF_HD void lf_phase_horizontal(const LfCtx<Px, SUB> &C, int tid, int part) {
   lf_role<Px, SUB>(tid, p, x);
   const bool uvsub = p && SUB;
   const int n = p ? G::nC : 64, nb = n >> 3;
-  const bool last = (x >> 3) == nb - 1;
-  if (last != (part == 0)) return;
+  if (((x >> 3) == nb - 1) != (part == 0)) return;
   lf_h_col<Px>(*C.M, uvsub, x, lf_tile_at(C, p, 0, x), p ? G::pitchC : G::pitchY, C.sbr * 8, C.mi_rows, nb, C.lf_lim,
                C.lf_mblim, C.bd);
 }
 
-// stores: part 0 = last block column (rows -8..n-1) + look-ahead columns (rows 0..n-1);
-// part 1 = block columns 0..nb-2 (rows -8..n-1)
+// stores of rows r0 .. n-1-keep (r0 = -8 with rows above, else 0; keep = 8 while the bottom rows
+// still wait for the next superblock's top edge, 0 in the last superblock row):
+// part 0 = last block column, plus the look-ahead columns (all rows 0..n-1: the left edge of c+1 is
+// done with them); part 1 = block columns 0..nb-2.  A thread owns one 8-sample column of a plane
+// and walks down the rows with a fixed step.
 template <typename Px, bool SUB>
-LF_HD void lf_phase_store(const LfCtx<Px, SUB> &C, int tid, int part) {
+LF_HD void lf_store_plane(const LfCtx<Px, SUB> &C, int plane, int lg, int idx, int nthreads, int part, int keep) {
   typedef LfGeom<Px, SUB> G;
   typedef typename LfVecT<Px>::T Vec;
-  const int r0 = C.has_top ? -8 : 0;
-  if (part == 0) {
-    const int rows = 64 - r0, rowsC = G::nC - r0;
-    for (int i = tid; i < rows + 2 * rowsC; i += G::NT) {
-      int p = 0, k = i;
-      if (k >= rows) { k -= rows; p = 1; if (k >= rowsC) { k -= rowsC; p = 2; } }
-      const int r = k + r0, x = (p ? G::nC : 64) - 8;
-      Vec v;
-      lf_smem_get(lf_tile_at(C, p, r, x), v);
-      lf_stg<Vec>(C.g[p] + (ptrdiff_t)r * C.stride[p] + x, v);
-    }
-    if (C.has_next) {
-      int p, r;
-      lf_role<Px, SUB>(tid, p, r);
-      const int n = p ? G::nC : 64;
-      Vec v;
-      lf_smem_get(lf_tile_at(C, p, r, n), v);
-      lf_stg<Vec>(C.g[p] + (size_t)r * C.stride[p] + n, v);
-    }
+  const int n = plane ? G::nC : 64, vpr = 1 << lg;        // vectors per row
+  const int v = idx & (vpr - 1), step = nthreads >> lg;
+  if ((v == vpr - 1) != (part == 0)) return;
+  const int pitch = plane ? G::pitchC : G::pitchY, stride = C.stride[plane];
+  int r = (C.has_top ? -8 : 0) + (idx >> lg);
+  const Px *t = lf_tile_at(C, plane, r, v * 8);
+  Px *g = C.g[plane] + (ptrdiff_t)r * stride + v * 8;
+  for (; r < n - keep; r += step, t += step * pitch, g += (ptrdiff_t)step * stride) {
+    Vec val;
+    lf_smem_get(t, val);
+    lf_stg<Vec>(g, val);
+  }
+}
+template <typename Px, bool SUB>
+LF_HD void lf_phase_store(const LfCtx<Px, SUB> &C, int tid, int part, int keep) {
+  typedef LfGeom<Px, SUB> G;
+  typedef typename LfVecT<Px>::T Vec;
+  if (SUB) {
+    lf_store_plane<Px, SUB>(C, 0, 3, tid, G::NT, part, keep);
+    // the two chroma planes share the threads: 64 threads each, 4 vectors per row
+    lf_store_plane<Px, SUB>(C, 1 + (tid >> 6), 2, tid & 63, 64, part, keep);
   } else {
-    constexpr int wY = 7, wC = (G::nC >> 3) - 1;     // vectors per row
-    const int nY = (64 - r0) * wY, nCv = (G::nC - r0) * wC;
-    for (int i = tid; i < nY + 2 * nCv; i += G::NT) {
-      int p = 0, k = i;
-      if (k >= nY) { k -= nY; p = 1; if (k >= nCv) { k -= nCv; p = 2; } }
-      const int w = p ? wC : wY;
-      const int r = k / w + r0, x = (k % w) * 8;
-      Vec v;
-      lf_smem_get(lf_tile_at(C, p, r, x), v);
-      lf_stg<Vec>(C.g[p] + (ptrdiff_t)r * C.stride[p] + x, v);
-    }
+    int p, i;
+    lf_role<Px, SUB>(tid, p, i);
+    lf_store_plane<Px, SUB>(C, p, 3, i, 64, part, keep);
+  }
+  if (part == 0 && C.has_next) {
+    int p, r;
+    lf_role<Px, SUB>(tid, p, r);
+    const int n = p ? G::nC : 64;
+    Vec v;
+    lf_smem_get(lf_tile_at(C, p, r, n), v);
+    lf_stg<Vec>(C.g[p] + (size_t)r * C.stride[p] + n, v);
   }
 }
 

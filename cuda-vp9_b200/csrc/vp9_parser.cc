@@ -12,6 +12,13 @@
 #include "vp9_tables.h"
 
 namespace vp9b {
+// Largest frame dimension accepted from a header (role of libvpx's DECODE_WIDTH_LIMIT /
+// DECODE_HEIGHT_LIMIT, vp9_decodeframe.c:1705-1711): the header is untrusted and every per-frame
+// table is sized from it before any tile data has been validated.  16384 covers 16K video; the
+// GPU side has the same limit (vp9gpu_frame_submit).
+constexpr int kMaxFrameDim = 16384;
+}  // namespace vp9b
+namespace vp9b {
 
 namespace {
 
@@ -308,6 +315,7 @@ int Parser::read_uncompressed_header(const uint8_t *data, size_t size, size_t *h
     w = rb.lit(16) + 1;
     h = rb.lit(16) + 1;
     if (rb.bit()) rb.lit(32);  // render size
+    if (w > kMaxFrameDim || h > kMaxFrameDim) return fail(VP9B_ERR_UNSUP, "frame larger than the decoder limit");
     setup_frame_size(w, h);
   } else {
     intra_only_ = show_frame_ ? 0 : rb.bit();
@@ -325,6 +333,7 @@ int Parser::read_uncompressed_header(const uint8_t *data, size_t size, size_t *h
       w = rb.lit(16) + 1;
       h = rb.lit(16) + 1;
       if (rb.bit()) rb.lit(32);
+      if (w > kMaxFrameDim || h > kMaxFrameDim) return fail(VP9B_ERR_UNSUP, "frame larger than the decoder limit");
       setup_frame_size(w, h);
     } else {
       refresh_frame_flags_ = rb.lit(8);
@@ -359,6 +368,7 @@ int Parser::read_uncompressed_header(const uint8_t *data, size_t size, size_t *h
           return fail(VP9B_ERR_CORRUPT, "reference frame has incompatible colour format");
       }
       if (!any_valid) return fail(VP9B_ERR_CORRUPT, "referenced frame has invalid size");
+      if (w > kMaxFrameDim || h > kMaxFrameDim) return fail(VP9B_ERR_UNSUP, "frame larger than the decoder limit");
       setup_frame_size(w, h);
       if (rb.bit()) rb.lit(32);  // render size
       allow_hp_ = rb.bit();

@@ -84,7 +84,7 @@ struct FrameParams {
   // unit that waits for a lower-numbered one can only be running if that one was started before
   // it -- forward progress does not depend on the order in which the hardware dispatches CTAs.
   uint32_t *ticket_lf, *ticket_intra;
-  uint32_t *lf_flags;           // [2 * superblocks] loop-filter data-flow flags (k_lf_sb)
+  uint32_t *lf_flags;           // [superblocks] loop-filter data-flow flags F_edge (k_lf_sb)
   uint32_t lf_epoch;            // value a flag takes when set in this frame
   uint32_t ticket_lf_base, ticket_intra_base;
   uint8_t lf_lim[64], lf_mblim[64];
@@ -1257,106 +1257,163 @@ __global__ void __launch_bounds__(kWaveWarps * 32) k_intra(const __grid_constant
   if (published < P.sb_cols && lane == 0) st_release(prog + sbr, P.prog_base + (uint32_t)P.sb_cols);
 }
 
+// optional phase timing of two loop-filter workers (compile with -DVP9B_LF_TIMING; tools/lf_phases.py
+// reads the stamps back through vp9gpu_debug_read)
+#ifdef VP9B_LF_TIMING
+__device__ unsigned long long d_lf_dbg[2 * 32 * 16];
+VP9B_DEV unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+#define LFT(k) if (tid == 0 && (sbc == 4 || sbc == 5) && r < 32) d_lf_dbg[((sbc - 4) * 32 + r) * 16 + (k)] = gtime();
+#else
+#define LFT(k)
+#endif
+
 // ------------------------------------------------------------------------------------------
-// stage 4: loop filter -- one CTA per superblock, ordered by data flow (vp9_lf_sb.cuh has the
-// design and the per-thread phase functions; this is the CTA-level schedule and the flag protocol).
-// Flags per superblock t = sbr * sb_cols + sbc, value = the frame's epoch once set:
-//   F_edge = flags[2t]    last block column + the look-ahead columns (left edge of c+1 applied) are
-//                         in global memory
-//   F_done = flags[2t+1]  everything of the superblock is
+// stage 4: loop filter -- one persistent CTA per superblock column (vp9_lf_sb.cuh has the design
+// and the per-thread phase functions; this is the CTA-level schedule and the flag protocol).
+// F_edge(r, c) = flags[r * sb_cols + c], value = the frame's epoch once set: the last block column
+// of (r, c) and the look-ahead columns (left edge of c+1 applied) are in global memory.
 // Producer: all threads store (st.cg), block barrier, one thread fence + st.release.gpu.
-// Consumer: one thread polls (relaxed, then one ld.acquire.gpu), block barrier, ld.cg loads.
+// Consumer (worker c+1): one thread polls (relaxed, then one ld.acquire.gpu), block barrier, ld.cg.
 template <typename Px, bool SUB>
-__global__ void __launch_bounds__(LfGeom<Px, SUB>::NT) k_lf_sb(const __grid_constant__ FrameBatch B) {
+__global__ void __launch_bounds__(LfGeom<Px, SUB>::NT, SUB ? 6 : 3) k_lf_sb(const __grid_constant__ FrameBatch B) {
   const FrameParams &P = B.f[blockIdx.z];
   if (!P.do_lf) return;
   typedef LfGeom<Px, SUB> G;
-  extern __shared__ __align__(16) unsigned char lf_smem[];
-  __shared__ vp9b_lfm s_M[2];
-  __shared__ uint16_t s_dset[24];
+  typedef typename LfVecT<Px>::T Vec;
+  extern __shared__ __align__(16) unsigned char lf_smem[];   // two tile buffers
+  __shared__ vp9b_lfm s_M[2][2];                             // [row parity][this superblock, next in the row]
   __shared__ int s_t;
   const int tid = threadIdx.x;
   if (tid == 0) s_t = (int)(atomicAdd(P.ticket_lf, 1u) - P.ticket_lf_base);
   __syncthreads();
-  const int t = s_t;
-  if (t >= P.sb_cols * P.sb_rows) return;   // the launch is as large as the largest frame of the batch
+  const int sbc = s_t, sb_cols = P.sb_cols, sb_rows = P.sb_rows;
+  if (sbc >= sb_cols) return;   // the launch is as wide as the widest frame of the batch
   LfCtx<Px, SUB> C;
-  C.sbr = t / P.sb_cols;
-  C.sbc = t - C.sbr * P.sb_cols;
-  C.sb_cols = P.sb_cols; C.mi_rows = P.mi_rows; C.bd = P.bd;
-  C.has_next = C.sbc + 1 < P.sb_cols;
-  C.has_top = C.sbr > 0;
-  C.tile = (Px *)lf_smem;
-  C.dset = s_dset;
-  C.M = &s_M[0];
-  C.Mn = &s_M[1];
+  C.sbc = sbc;
+  C.sb_cols = sb_cols; C.mi_rows = P.mi_rows; C.bd = P.bd;
+  C.has_next = sbc + 1 < sb_cols;
   C.lf_lim = P.lf_lim;
   C.lf_mblim = P.lf_mblim;
+  Px *base[3];
 #pragma unroll
   for (int p = 0; p < 3; p++) {
-    const int n = p ? G::nC : 64;
     C.stride[p] = P.dst[p].stride;
-    C.g[p] = (Px *)P.dst[p].ptr + (size_t)(C.sbr * n) * P.dst[p].stride + C.sbc * n;
+    base[p] = (Px *)P.dst[p].ptr + sbc * (p ? G::nC : 64);
   }
   uint32_t *const flags = P.lf_flags;
   const uint32_t epoch = P.lf_epoch;
-  auto wait_flag = [&](int tt, int which) {
-    const uint32_t *f = flags + 2 * tt + which;
-    while (ld_relaxed(f) != epoch) __nanosleep(40);
-    (void)ld_acquire(f);
+  auto wait_left = [&](int r) {     // F_edge(r, sbc - 1)
+    const uint32_t *f = flags + r * sb_cols + sbc - 1;
+    while (ld_acquire(f) != epoch) __nanosleep(32);
   };
-  auto publish = [&](int which) {   // every thread's stores are issued; make them visible, then set the flag
-    __syncthreads();
-    if (tid == 0) {
-      __threadfence();
-      st_release(flags + 2 * t + which, epoch);
+  // masks of (r, sbc) and (r, sbc + 1), 40 words each: fetched into a register one superblock ahead
+  // (like the samples) and written to shared memory at the end of the iteration
+  uint32_t mask_word = 0;
+  auto fetch_masks = [&](int r) {
+    if (tid < 80) {
+      const int which = tid >= 40;
+      const uint32_t *src = (const uint32_t *)&P.lfm[r * sb_cols + sbc + ((which && C.has_next) ? 1 : 0)];
+      mask_word = __ldg(src + (which ? tid - 40 : tid));
     }
   };
-  // masks of this superblock and the next one (40 words each)
-  if (tid < 80) {
-    const int which = tid >= 40;
-    const uint32_t *src = (const uint32_t *)&P.lfm[t + ((which && C.has_next) ? 1 : 0)];
-    ((uint32_t *)s_M)[tid] = __ldg(src + (which ? tid - 40 : tid));
-  }
-  lf_phase_load_interior(C, tid);
+  auto commit_masks = [&](int r) {
+    if (tid < 80) ((uint32_t *)&s_M[r & 1][0])[tid] = mask_word;
+  };
+  auto row_ptrs = [&](int r, Px *g[3]) {
+#pragma unroll
+    for (int p = 0; p < 3; p++) g[p] = base[p] + (size_t)(r * (p ? G::nC : 64)) * C.stride[p];
+  };
+  // Plan of the whole column, computed once by all threads while the first tile is on its way:
+  // per superblock the dependent sets (24 x u16) and the chain flag.  (One superblock's plan is
+  // ~400 dependent instructions on one warp: far too long for the per-superblock critical path.)
+  uint16_t *const plan = (uint16_t *)(lf_smem + 2 * G::kTileBytes);   // [sb_rows][24]
+  uint8_t *const plan_chain = (uint8_t *)(plan + (size_t)sb_rows * 24);  // [sb_rows]
+  for (int i = tid; i < sb_rows; i += G::NT) plan_chain[i] = 0;
   __syncthreads();
-  const bool chain = __syncthreads_or(lf_phase_dsets(C, tid)) != 0;
-  lf_phase_vertical(C, tid, false);                    // A
-  if (chain && C.sbc > 0) {                            // D before H7: the row serialises through F_edge
-    if (tid == 0) wait_flag(t - 1, 0);
+  {
+    constexpr int U = LfPlanUnits<Px, SUB>::value;
+    for (int i = tid; i < sb_rows * U; i += G::NT) {
+      const int r = i / U, u = i - r * U;
+      if (lf_plan_unit<Px, SUB>(P.lfm[r * sb_cols + sbc], sbc > 0, u, plan + r * 24)) plan_chain[r] = 1;
+    }
+  }
+  Vec pre[G::kPre];
+  // prologue: first superblock of the column
+  fetch_masks(0);
+  commit_masks(0);
+  row_ptrs(0, C.g);
+  C.tile = (Px *)lf_smem;
+  lf_phase_prefetch<Px, SUB>(C.g, C.stride, C.has_next, tid, pre);
+  lf_phase_commit<Px, SUB>(C, tid, pre);
+  for (int r = 0; r < sb_rows; r++) {
+    const bool next_row = r + 1 < sb_rows;
+    const int keep = next_row ? 8 : 0;
+    Px *const cur = (Px *)(lf_smem + (size_t)(r & 1) * G::kTileBytes), *const nxt = (Px *)(lf_smem + (size_t)((r + 1) & 1) * G::kTileBytes);
+    C.tile = cur;
+    C.sbr = r;
+    C.has_top = r > 0;
+    C.M = &s_M[r & 1][0];
+    C.Mn = &s_M[r & 1][1];
+    row_ptrs(r, C.g);
+    __syncthreads();                 // tile + masks of this row are in shared memory
+    LFT(0)
+    if (next_row) {                  // the next superblock's samples and masks fly while this one is filtered
+      Px *g[3];
+      row_ptrs(r + 1, g);
+      lf_phase_prefetch<Px, SUB>(g, C.stride, C.has_next, tid, pre);
+      fetch_masks(r + 1);
+    }
+    C.dset = plan + r * 24;
+    const bool chain = plan_chain[r] != 0;
+    LFT(1)
+    lf_phase_vertical(C, tid, false);                    // A
+    LFT(2)
+    if (chain && sbc > 0) {                              // D before H7: this row serialises through F_edge
+      if (tid == 0) wait_left(r);
+      __syncthreads();
+      lf_phase_merge_left(C, tid);
+      lf_phase_vertical(C, tid, true);
+    }
     __syncthreads();
-    lf_phase_merge_left(C, tid);
-    lf_phase_vertical(C, tid, true);
-  }
-  if (C.has_top) {
-    if (tid == 0) wait_flag(t - P.sb_cols, 0);
+    LFT(3)
+    lf_phase_horizontal(C, tid, 0);                      // H7
     __syncthreads();
-    lf_phase_load_top(C, tid, 0);
-  }
-  __syncthreads();
-  lf_phase_horizontal(C, tid, 0);                      // H7
-  __syncthreads();
-  if (C.has_next) {
-    lf_phase_next_left_edge(C, tid);                   // E
+    LFT(4)
+    if (C.has_next) {
+      lf_phase_next_left_edge(C, tid);                   // E
+      __syncthreads();
+    }
+    LFT(5)
+    lf_phase_store(C, tid, 0, keep);
+    LFT(6)
+    if (C.has_next) {                                    // publish F_edge(r, sbc)
+      __syncthreads();
+      if (tid == 0) st_release(flags + r * sb_cols + sbc, epoch);
+    }
+    LFT(7)
+    if (!chain && sbc > 0) {                             // D
+      if (tid == 0) wait_left(r);
+      __syncthreads();
+      LFT(8)
+      lf_phase_merge_left(C, tid);
+      lf_phase_vertical(C, tid, true);
+    }
     __syncthreads();
+    LFT(9)
+    lf_phase_horizontal(C, tid, 1);                      // H
+    __syncthreads();
+    LFT(10)
+    lf_phase_store(C, tid, 1, keep);
+    LFT(11)
+    if (next_row) {
+      lf_phase_carry(C, nxt, tid);
+      LfCtx<Px, SUB> N = C;
+      N.tile = nxt;
+      lf_phase_commit<Px, SUB>(N, tid, pre);
+      commit_masks(r + 1);
+    }
+    LFT(12)
   }
-  lf_phase_store(C, tid, 0);
-  publish(0);
-  if (tid == 0) {
-    if (!chain && C.sbc > 0) wait_flag(t - 1, 0);
-    if (C.has_top) wait_flag(t - P.sb_cols, 1);
-  }
-  __syncthreads();
-  if (!chain && C.sbc > 0) {                           // D
-    lf_phase_merge_left(C, tid);
-    lf_phase_vertical(C, tid, true);
-  }
-  lf_phase_load_top(C, tid, 1);
-  __syncthreads();
-  lf_phase_horizontal(C, tid, 1);                      // H
-  __syncthreads();
-  lf_phase_store(C, tid, 1);
-  publish(1);
 }
 
 // output path: 16-bit samples -> 8 bits (truncating shift, highbd_img_downshift in tools_common.c)
@@ -1421,6 +1478,7 @@ struct vp9gpu_ctx {
   bool tickets_ready = false;
   uint64_t next_ticket = 1;
   int stop_stage = 0;
+  bool validate = true;           // record-level validation of host packed buffers (vp9gpu_set_validation)
   uint64_t launches = 0;
   int num_sms = 148;
   bool profiling = false;
@@ -1518,6 +1576,11 @@ extern "C" int vp9gpu_set_stop_stage(vp9gpu_ctx *ctx, int stage) {
   ctx->stop_stage = stage;
   return 0;
 }
+extern "C" int vp9gpu_set_validation(vp9gpu_ctx *ctx, int enable) {
+  if (!ctx) return VP9B_ERR_INVALID;
+  ctx->validate = enable != 0;
+  return 0;
+}
 extern "C" int vp9gpu_set_profiling(vp9gpu_ctx *ctx, int enable) {
   if (!ctx) return VP9B_ERR_INVALID;
   ctx->profiling = enable != 0;
@@ -1530,7 +1593,7 @@ extern "C" int vp9gpu_get_stage_ms(vp9gpu_ctx *ctx, float ms[8], int reset) {
   return 0;
 }
 #ifdef VP9B_LF_TIMING
-extern "C" int vp9gpu_debug_read(unsigned long long *out) { return (int)cudaMemcpyFromSymbol(out, vp9b::d_lf_dbg, sizeof(unsigned long long) * 512); }
+extern "C" int vp9gpu_debug_read(unsigned long long *out) { return (int)cudaMemcpyFromSymbol(out, vp9b::d_lf_dbg, sizeof(unsigned long long) * 1024); }
 #endif
 extern "C" int vp9gpu_get_frame_8bit_async(vp9gpu_ctx *ctx, int slot, uint8_t *y, uint8_t *u, uint8_t *v, int y_stride,
                                            int uv_stride) {
@@ -1684,7 +1747,7 @@ static int launch_batch(vp9gpu_ctx *const *ctxs, FrameBatch &B, int n) {
       g_intra = std::max(g_intra, (3 * P.sb_rows + kWaveWarps - 1) / kWaveWarps);
     }
     P.do_lf = P.do_lf && stop == 0;
-    if (P.do_lf) g_lf = std::max(g_lf, P.sb_rows * P.sb_cols);
+    if (P.do_lf) g_lf = std::max(g_lf, P.sb_cols);
   }
   // tickets: every participating frame's counter advances by the number of CTAs launched for it
   for (int i = 0; i < n; i++) {
@@ -1727,9 +1790,22 @@ static int launch_batch(vp9gpu_ctx *const *ctxs, FrameBatch &B, int n) {
   }
   if (prof) cudaEventRecord(ctx->prof_ev[4], st);
   if (g_lf) {
-    // one CTA per superblock of the largest frame in the batch; threads = sample rows of the three planes
-    if (B.f[0].ss_x) k_lf_sb<Px, true><<<dim3(g_lf, 1, n), LfGeom<Px, true>::NT, LfGeom<Px, true>::kTileBytes, st>>>(B);
-    else k_lf_sb<Px, false><<<dim3(g_lf, 1, n), LfGeom<Px, false>::NT, LfGeom<Px, false>::kTileBytes, st>>>(B);
+    // one persistent CTA per superblock column of the widest frame in the batch; threads = sample rows of the three planes
+    int max_rows = 0;
+    for (int i = 0; i < n; i++) max_rows = std::max(max_rows, B.f[i].sb_rows);
+    const size_t plan_bytes = ((size_t)max_rows * 49 + 15) & ~(size_t)15;   // per superblock: 24 dependent sets + chain flag
+    // opt-in shared-memory limit, once per device and kernel variant: two tiles + the plan of the tallest frame (16384 / 64 rows)
+    const bool sub = B.f[0].ss_x != 0;
+    const size_t tiles = 2 * (sub ? LfGeom<Px, true>::kTileBytes : LfGeom<Px, false>::kTileBytes);
+    const unsigned abit = (sizeof(Px) == 1 ? 4u : 8u) << (sub ? 2 : 0);
+    if (!(ctx->attr_done & abit)) {
+      const int lim = (int)(tiles + 256 * 49 + 16);
+      if (sub) CK(cudaFuncSetAttribute(k_lf_sb<Px, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+      else CK(cudaFuncSetAttribute(k_lf_sb<Px, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+      ctx->attr_done |= abit;
+    }
+    if (sub) k_lf_sb<Px, true><<<dim3(g_lf, 1, n), LfGeom<Px, true>::NT, tiles + plan_bytes, st>>>(B);
+    else k_lf_sb<Px, false><<<dim3(g_lf, 1, n), LfGeom<Px, false>::NT, tiles + plan_bytes, st>>>(B);
     ctx->launches++;
   }
   if (prof) {
@@ -1745,8 +1821,8 @@ static int launch_batch(vp9gpu_ctx *const *ctxs, FrameBatch &B, int n) {
   return 0;
 }
 
-// Validate one packed frame, make sure its context has the memory it needs and fill its FrameParams.
-static int prepare_frame(vp9gpu_ctx *ctx, const uint8_t *d_packed, const vp9b_frame_hdr *h, FrameParams &P) {
+// Header of a packed buffer: magic, slots, sampling, section bounds, geometry.
+static int check_header(vp9gpu_ctx *ctx, const vp9b_frame_hdr *h) {
   if (h->magic != VP9B_MAGIC) { ctx->err = "bad packed buffer magic"; return VP9B_ERR_INVALID; }
   if (h->dst_slot < 0 || h->dst_slot >= VP9B_NUM_SLOTS) { ctx->err = "bad dst slot"; return VP9B_ERR_INVALID; }
   if (!((h->ss_x == 1 && h->ss_y == 1) || (h->ss_x == 0 && h->ss_y == 0))) {
@@ -1774,6 +1850,84 @@ static int prepare_frame(vp9gpu_ctx *ctx, const uint8_t *d_packed, const vp9b_fr
       ctx->err = "packed buffer: inconsistent frame geometry";
       return VP9B_ERR_INVALID;
     }
+  }
+  return 0;
+}
+
+// Record-level validation of a packed buffer that lives in host memory.  The header checks are in
+// prepare_frame(); this pass makes sure that no record can make a kernel index outside the frame,
+// the coefficient stream, the sub-8x8 MV table or a shared-memory tile.  It runs for every buffer
+// that enters through vp9gpu_frame_submit / vp9gpu_upload_packed (a host-side packer is a foreign
+// producer); the whole-decoder layer, whose buffers come from vp9b_parser_* in this library, turns
+// it off (vp9gpu_set_validation).
+static int validate_records(const uint8_t *p, const vp9b_frame_hdr *h, std::string &err) {
+  auto bad = [&](const char *m) { err = m; return VP9B_ERR_INVALID; };
+  const uint32_t n_submv = h->sec[VP9B_SEC_SUBMV].count, n_coef = h->sec[VP9B_SEC_COEF].count;
+  const vp9b_block *blk = (const vp9b_block *)(p + h->sec[VP9B_SEC_BLOCKS].offset);
+  for (uint32_t i = 0; i < h->sec[VP9B_SEC_BLOCKS].count; i++) {
+    const vp9b_block &b = blk[i];
+    if (b.bsize > 12 || b.mi_col >= h->mi_cols || b.mi_row >= h->mi_rows || b.ref0 > 3 || b.ref1 > 3 || b.filter > 3)
+      return bad("packed buffer: block record out of range");
+    if (b.ref0 && h->intra_only) return bad("packed buffer: inter block in an intra-only frame");
+    if (b.ref1 && !b.ref0) return bad("packed buffer: second reference without a first");
+    if (b.ref0 && b.bsize < 3) {
+      uint32_t idx;
+      memcpy(&idx, &b.mv[0][0], 4);
+      if (idx >= n_submv) return bad("packed buffer: sub-8x8 motion vector index out of range");
+    }
+  }
+  const uint32_t nsb = h->sb_cols * h->sb_rows;
+  auto check_txb = [&](const vp9b_txb &t, int want_plane, bool intra) -> bool {
+    const int tx = t.tx & 3, plane = (t.tx >> 4) & 3, bs4 = 1 << tx;
+    if (plane > 2 || (want_plane >= 0 && plane != want_plane)) return false;
+    if (t.eob > (16u << (2 * tx)) || (uint64_t)t.coef_off + t.eob > n_coef) return false;
+    if (h->lossless && tx != 0) return false;
+    // a transform block may hang over the aligned frame edge into the 64-sample padding
+    const uint32_t pw4 = ((h->mi_cols * 8) >> (plane ? h->ss_x : 0)) / 4 + 16, ph4 = ((h->mi_rows * 8) >> (plane ? h->ss_y : 0)) / 4 + 16;
+    if ((uint32_t)t.x4 + bs4 > pw4 || (uint32_t)t.y4 + bs4 > ph4) return false;
+    if (intra && (t.aux & 15) > 9) return false;
+    return true;
+  };
+  const vp9b_txb *ti = (const vp9b_txb *)(p + h->sec[VP9B_SEC_TXB_INTER].offset);
+  uint32_t first = 0;
+  for (int sz = 0; sz < 4; sz++) {     // the list is grouped by transform size: a warp relies on it
+    for (uint32_t i = first; i < first + h->n_txb_inter_size[sz] && i < h->sec[VP9B_SEC_TXB_INTER].count; i++)
+      if ((ti[i].tx & 3) != sz || !check_txb(ti[i], -1, false) || !ti[i].eob) return bad("packed buffer: inter transform record out of range");
+    first += h->n_txb_inter_size[sz];
+  }
+  const vp9b_sbrange *rg = (const vp9b_sbrange *)(p + h->sec[VP9B_SEC_SB_INTRA].offset);
+  for (int pl = 0; pl < 3; pl++) {
+    const vp9b_txb *t = (const vp9b_txb *)(p + h->sec[VP9B_SEC_TXB_INTRA_Y + pl].offset);
+    const uint32_t cnt = h->sec[VP9B_SEC_TXB_INTRA_Y + pl].count;
+    const int n4 = (pl && h->ss_x) ? 8 : 16;       // superblock size in 4-sample units
+    for (uint32_t sb = 0; sb < nsb; sb++) {
+      const vp9b_sbrange &r = rg[(size_t)pl * nsb + sb];
+      if ((uint64_t)r.start + r.count > cnt) return bad("packed buffer: intra range out of bounds");
+      const uint32_t sbr = sb / h->sb_cols, sbc = sb % h->sb_cols;
+      for (uint32_t i = r.start; i < r.start + r.count; i++) {
+        const int bs4 = 1 << (t[i].tx & 3);
+        // the wavefront kernel reconstructs a superblock inside a shared-memory tile: every record of
+        // the range has to lie inside that superblock
+        if (!check_txb(t[i], pl, true) || t[i].x4 < sbc * n4 || t[i].x4 + bs4 > (sbc + 1) * n4 || t[i].y4 < sbr * n4 ||
+            t[i].y4 + bs4 > (sbr + 1) * n4)
+          return bad("packed buffer: intra transform record out of range");
+      }
+    }
+  }
+  if (h->lf_level) {
+    const vp9b_lfm *m = (const vp9b_lfm *)(p + h->sec[VP9B_SEC_LFM].offset);
+    for (uint32_t sb = 0; sb < nsb; sb++)
+      for (int i = 0; i < 64; i++)
+        if (m[sb].lfl_y[i] > 63) return bad("packed buffer: loop-filter level out of range");
+  }
+  return 0;
+}
+
+// Validate one packed frame, make sure its context has the memory it needs and fill its FrameParams.
+static int prepare_frame(vp9gpu_ctx *ctx, const uint8_t *d_packed, const vp9b_frame_hdr *h, FrameParams &P) {
+  {
+    const int he = check_header(ctx, h);
+    if (he) return he;
   }
   CK(cudaSetDevice(ctx->device));
   int e = 0;
@@ -1803,6 +1957,16 @@ static int prepare_frame(vp9gpu_ctx *ctx, const uint8_t *d_packed, const vp9b_fr
       const DevFrame &F = ctx->slot[rd.slot];
       if (F.bd != h->bit_depth || F.ss_x != h->ss_x || F.ss_y != h->ss_y) {
         ctx->err = "reference format mismatch";
+        return VP9B_ERR_INVALID;
+      }
+      // the clamp extent of motion compensation must be the slot's real size, and a frame cannot
+      // predict from the buffer it is being written to
+      if (rd.width != F.width || rd.height != F.height || rd.slot == h->dst_slot) {
+        ctx->err = "reference descriptor does not match its frame slot";
+        return VP9B_ERR_INVALID;
+      }
+      if (rd.x_scale_fp >= 0 && (rd.x_step_q4 < 1 || rd.x_step_q4 > 80 || rd.y_step_q4 < 1 || rd.y_step_q4 > 80)) {
+        ctx->err = "reference scale out of range";
         return VP9B_ERR_INVALID;
       }
       for (int p = 0; p < 3; p++) {
@@ -1855,7 +2019,7 @@ static int prepare_frame(vp9gpu_ctx *ctx, const uint8_t *d_packed, const vp9b_fr
   P.mi = ctx->d_mi;
   // progress counters: [0, 3*1024) intra (plane, row), [3072, 4096) loop filter.  Values are
   // prog_base + count with prog_base advancing by 2048 per frame; cleared only when it wraps.
-  if (h->sb_rows > 1024 || h->sb_cols >= 2048) { ctx->err = "frame too large"; return VP9B_ERR_UNSUP; }
+  if (h->width > 16384 || h->height > 16384) { ctx->err = "frame too large"; return VP9B_ERR_UNSUP; }
   if (++ctx->epoch == 0) ctx->epoch = 1;
   if ((ctx->epoch & 0xfffff) == 0) CK(cudaMemsetAsync(ctx->d_tickets, 0, sizeof(uint32_t) * 4096, ctx->stream));
   P.prog_intra = ctx->d_tickets;
@@ -1946,6 +2110,11 @@ extern "C" int vp9gpu_frame_submit(vp9gpu_ctx *ctx, const void *packed, size_t b
   if (!ctx || !packed || bytes < sizeof(vp9b_frame_hdr)) return VP9B_ERR_INVALID;
   const vp9b_frame_hdr *h = (const vp9b_frame_hdr *)packed;
   if (h->magic != VP9B_MAGIC || h->total_bytes > bytes) { ctx->err = "corrupt packed buffer"; return VP9B_ERR_INVALID; }
+  if (ctx->validate) {
+    int e = check_header(ctx, h);
+    if (!e) e = validate_records((const uint8_t *)packed, h, ctx->err);
+    if (e) return e;
+  }
   CK(cudaSetDevice(ctx->device));
   const int k = ctx->ring_pos;
   ctx->ring_pos = (k + 1) % vp9gpu_ctx::kRing;
@@ -1972,7 +2141,14 @@ extern "C" int vp9gpu_frame_submit(vp9gpu_ctx *ctx, const void *packed, size_t b
 }
 
 extern "C" int vp9gpu_upload_packed(vp9gpu_ctx *ctx, const void *packed, size_t bytes, void **d_packed) {
-  if (!ctx || !packed || !d_packed) return VP9B_ERR_INVALID;
+  if (!ctx || !packed || !d_packed || bytes < sizeof(vp9b_frame_hdr)) return VP9B_ERR_INVALID;
+  if (ctx->validate) {
+    const vp9b_frame_hdr *h = (const vp9b_frame_hdr *)packed;
+    if (h->magic != VP9B_MAGIC || h->total_bytes > bytes) { ctx->err = "corrupt packed buffer"; return VP9B_ERR_INVALID; }
+    int e = check_header(ctx, h);
+    if (!e) e = validate_records((const uint8_t *)packed, h, ctx->err);
+    if (e) return e;
+  }
   CK(cudaSetDevice(ctx->device));
   CK(cudaMalloc(d_packed, bytes));
   CK(cudaMemcpy(*d_packed, packed, bytes, cudaMemcpyHostToDevice));

@@ -190,6 +190,11 @@ void vp9gpu_free_host(void *p);
 int vp9gpu_set_frame(vp9gpu_ctx *ctx, int slot, uint32_t width, uint32_t height, int bit_depth,
                      int ss_x, int ss_y, const uint8_t *y, const uint8_t *u, const uint8_t *v,
                      int y_stride, int uv_stride);
+/* Record-level validation of packed buffers handed over in host memory (vp9gpu_frame_submit,
+ * vp9gpu_upload_packed): every block / transform / range record is checked against the frame
+ * geometry and the section sizes before anything reaches a kernel.  On by default -- a host-side
+ * packer is a foreign producer; vp9b_decoder_* turns it off for buffers of its own parser. */
+int vp9gpu_set_validation(vp9gpu_ctx *ctx, int enable);
 /* Debug/test hook: stop after a stage (0 = all; 1 inter pred; 2 + inter residual; 3 + intra;
  * 4 + loop filter). */
 int vp9gpu_set_stop_stage(vp9gpu_ctx *ctx, int stage);
@@ -201,6 +206,38 @@ uint64_t vp9gpu_launch_count(vp9gpu_ctx *ctx);
  * 0 upload/expand, 1 inter pred, 2 inter residual, 3 intra, 4 loop filter. */
 int vp9gpu_set_profiling(vp9gpu_ctx *ctx, int enable);
 int vp9gpu_get_stage_ms(vp9gpu_ctx *ctx, float ms[8], int reset);
+
+/* ------------------------------------------------------------------ 1b. frame packer ------- */
+/* Builds the packed buffer record by record, for a host decoder that keeps its own bitstream parser
+ * (libvpx: called from decode_block(); integration/libvpx/vp9_b200_shim.inc is that binding).  Role
+ * of createBuffers / createBuffersTr (vpx-master/inter_cuda_kernel.cu:897-1028,
+ * intra_cuda_kernel.cu:1252-1304) without any libvpx type crossing the boundary. */
+typedef struct vp9b_packer vp9b_packer;
+
+vp9b_packer *vp9b_packer_create(void);
+void vp9b_packer_destroy(vp9b_packer *p);
+const char *vp9b_packer_last_error(vp9b_packer *p);
+/* Start a frame.  Taken from *hdr: width, height, bit_depth, ss_x, ss_y, lossless, intra_only,
+ * show_frame, lf_level, lf_sharpness, dst_slot, ref[3], lf_lim, lf_mblim, frame_index.  Geometry
+ * (mi / sb counts), coef_bytes, the section table and the counters are filled in by the packer. */
+int vp9b_packer_begin(vp9b_packer *p, const vp9b_frame_hdr *hdr);
+/* One prediction block, in decode order.  sub_mv: the four 4x4 motion vectors [block][ref][row,col]
+ * of an inter block below 8x8 (bmi[], vp9_blockd.h:74-97), else NULL; b->mv is ignored for those. */
+int vp9b_packer_add_block(vp9b_packer *p, const vp9b_block *b, const int16_t sub_mv[4][2][2]);
+/* One transform block.  x4, y4: position in the plane in units of 4 samples.  inter != 0: residual
+ * of an inter block (dropped when eob == 0); inter == 0: intra block (always recorded) with its
+ * prediction mode (PREDICTION_MODE 0..9) and the edge availability vp9_predict_intra_block derives
+ * (vp9_reconintra.c:404-424).  dqcoeff: dequantised coefficients at their raster positions, as
+ * vp9_decode_block_tokens leaves them (vp9_detokenize.c:217-248), coef_bytes 2 (int16) or 4
+ * (int32); scan: the scan table used for the block (>= eob entries). */
+int vp9b_packer_add_txb(vp9b_packer *p, int plane, int inter, int x4, int y4, int tx_size, int tx_type, int mode,
+                        int have_top, int have_left, int have_right, const void *dqcoeff, int coef_bytes,
+                        const int16_t *scan, int eob);
+/* Final loop-filter mask of one superblock (after vp9_adjust_mask, vp9_loopfilter.c:766-878). */
+int vp9b_packer_set_lfm(vp9b_packer *p, int sb_row, int sb_col, const vp9b_lfm *m);
+/* Close the frame: *packed (packer-owned, valid until the next begin) is ready for
+ * vp9gpu_frame_submit. */
+int vp9b_packer_finish(vp9b_packer *p, const void **packed, size_t *bytes);
 
 /* ------------------------------------------------------------------ 2. host parser --------- */
 typedef struct vp9b_parser vp9b_parser;

@@ -1,9 +1,9 @@
-// TEST INFRASTRUCTURE -- CPU emulation of the superblock data-flow loop filter (k_lf_sb).
+// TEST INFRASTRUCTURE -- CPU emulation of the column-worker loop filter (k_lf_sb).
 // Compiles the kernel's own per-thread phase functions (cuda-vp9_b200/csrc/vp9_lf_sb.cuh) for the
-// host and runs them "thread by thread" per CTA, in schedules that are legal under the kernel's
-// flag protocol but as adversarial as possible (every CTA loads and pre-filters its tile before
-// any neighbour has published anything, or a random mix of early and late CTAs).  The result is
-// compared with the oracle by tests/test_lf_emul.py.  Not part of the product.
+// host and runs them "thread by thread" per worker, in schedules that are legal under the kernel's
+// flag protocol but as adversarial as possible: all workers in lock step, one worker completely
+// before the next, or a seeded random interleaving.  The result is compared with the oracle by
+// tests/test_lf_emul.py.  Not part of the product.
 #define VP9B_EMUL
 #include "../../cuda-vp9_b200/csrc/vp9_lf_sb.cuh"
 
@@ -14,9 +14,23 @@
 using namespace vp9b;
 
 template <typename Px, bool SUB>
+struct Worker {
+  typedef LfGeom<Px, SUB> G;
+  typedef typename LfVecT<Px>::T Vec;
+  std::vector<Px> buf[2];
+  std::vector<Vec> pre;       // [NT][kPre]
+  uint16_t dset[24];
+  LfCtx<Px, SUB> C;
+  Px *base[3];
+  int r = 0, part = 0;        // next step: (row r, part 0 or 1)
+  bool chain = false;
+};
+
+template <typename Px, bool SUB>
 static int run(const vp9b_frame_hdr *h, const uint8_t *base, uint16_t *const planes[3], const int strides[3],
                const int rows[3], unsigned schedule, int *n_chain) {
   typedef LfGeom<Px, SUB> G;
+  typedef typename LfVecT<Px>::T Vec;
   // planes in the device geometry: aligned size + 64 samples of padding right / bottom
   const int aw = (int)h->mi_cols * 8, ah = (int)h->mi_rows * 8;
   std::vector<Px> buf[3];
@@ -29,72 +43,112 @@ static int run(const vp9b_frame_hdr *h, const uint8_t *base, uint16_t *const pla
     for (int r = 0; r < std::min(prow[p], rows[p]); r++)
       for (int x = 0; x < std::min(stride[p], strides[p]); x++) buf[p][(size_t)r * stride[p] + x] = (Px)planes[p][(size_t)r * strides[p] + x];
   }
-  const int sb_cols = h->sb_cols, sb_rows = h->sb_rows, nsb = sb_cols * sb_rows;
+  const int sb_cols = h->sb_cols, sb_rows = h->sb_rows;
   const vp9b_lfm *lfm = (const vp9b_lfm *)(base + h->sec[VP9B_SEC_LFM].offset);
-  std::vector<std::vector<Px>> tiles(nsb, std::vector<Px>(G::kTileSamples, (Px)0xAA));
-  std::vector<LfCtx<Px, SUB>> ctx(nsb);
-  std::vector<char> chain(nsb, 0), early(nsb, 0);
-  std::vector<uint16_t> dsets((size_t)nsb * 24, 0);
-  std::mt19937 rng(schedule);
-  auto phase1 = [&](int t) {
-    LfCtx<Px, SUB> &C = ctx[t];
-    const int sbr = t / sb_cols, sbc = t % sb_cols;
-    C.tile = tiles[t].data();
-    C.dset = &dsets[(size_t)t * 24];
-    for (int p = 0; p < 3; p++) {
-      const int n = p ? G::nC : 64;
-      C.g[p] = buf[p].data() + (size_t)sbr * n * stride[p] + sbc * n;
-      C.stride[p] = stride[p];
-    }
+  std::vector<Worker<Px, SUB>> W(sb_cols);
+  std::vector<int> edge_done(sb_cols, 0);     // rows whose F_edge this worker has published
+  *n_chain = 0;
+  auto set_row = [&](Worker<Px, SUB> &w, int r) {
+    LfCtx<Px, SUB> &C = w.C;
+    C.tile = w.buf[r & 1].data();
+    C.sbr = r;
+    C.has_top = r > 0;
+    const int t = r * sb_cols + C.sbc;
     C.M = &lfm[t];
-    C.Mn = &lfm[sbc + 1 < sb_cols ? t + 1 : t];
+    C.Mn = &lfm[C.has_next ? t + 1 : t];
+    for (int p = 0; p < 3; p++) C.g[p] = w.base[p] + (size_t)r * (p ? G::nC : 64) * stride[p];
+  };
+  for (int c = 0; c < sb_cols; c++) {
+    Worker<Px, SUB> &w = W[c];
+    for (int k = 0; k < 2; k++) w.buf[k].assign(G::kTileSamples, (Px)0xAA);
+    w.pre.resize((size_t)G::NT * G::kPre);
+    LfCtx<Px, SUB> &C = w.C;
+    C.dset = w.dset;
     C.lf_lim = h->lf_lim;
     C.lf_mblim = h->lf_mblim;
-    C.sbr = sbr; C.sbc = sbc; C.sb_cols = sb_cols; C.mi_rows = h->mi_rows; C.bd = h->bit_depth;
-    C.has_next = sbc + 1 < sb_cols;
-    C.has_top = sbr > 0;
-    bool ch = false;
-    for (int tid = 0; tid < G::NT; tid++) ch |= lf_phase_dsets(C, tid);
-    chain[t] = ch;
-    for (int tid = 0; tid < G::NT; tid++) lf_phase_load_interior(C, tid);
-    for (int tid = 0; tid < G::NT; tid++) lf_phase_vertical(C, tid, false);
-  };
-  auto dependent = [&](int t) {
-    LfCtx<Px, SUB> &C = ctx[t];
-    if (C.sbc == 0) return;
-    for (int tid = 0; tid < G::NT; tid++) { lf_phase_merge_left(C, tid); lf_phase_vertical(C, tid, true); }
-  };
-  auto edge_part = [&](int t) {
-    LfCtx<Px, SUB> &C = ctx[t];
-    if (chain[t]) dependent(t);
-    for (int tid = 0; tid < G::NT; tid++) lf_phase_load_top(C, tid, 0);
-    for (int tid = 0; tid < G::NT; tid++) lf_phase_horizontal(C, tid, 0);
-    if (C.has_next)
-      for (int tid = 0; tid < G::NT; tid++) lf_phase_next_left_edge(C, tid);
-    for (int tid = 0; tid < G::NT; tid++) lf_phase_store(C, tid, 0);
-  };
-  auto rest_part = [&](int t) {
-    LfCtx<Px, SUB> &C = ctx[t];
-    if (!chain[t]) dependent(t);
-    for (int tid = 0; tid < G::NT; tid++) lf_phase_load_top(C, tid, 1);
-    for (int tid = 0; tid < G::NT; tid++) lf_phase_horizontal(C, tid, 1);
-    for (int tid = 0; tid < G::NT; tid++) lf_phase_store(C, tid, 1);
-  };
-  // schedule 0: every CTA runs phase 1 before anything is published; 1: strictly one CTA after the
-  // other in ticket order; otherwise a seeded random mix of early and late CTAs
-  for (int t = 0; t < nsb; t++) early[t] = schedule == 0 ? 1 : (schedule == 1 ? 0 : (rng() & 1));
-  for (int t = 0; t < nsb; t++)
-    if (early[t]) phase1(t);
-  for (int r = 0; r < sb_rows; r++) {
-    if (schedule == 1) {
-      for (int c = 0; c < sb_cols; c++) { const int t = r * sb_cols + c; phase1(t); edge_part(t); rest_part(t); }
-    } else {
-      for (int c = 0; c < sb_cols; c++) { const int t = r * sb_cols + c; if (!early[t]) phase1(t); edge_part(t); }
-      for (int c = 0; c < sb_cols; c++) rest_part(r * sb_cols + c);
+    C.sbc = c; C.sb_cols = sb_cols; C.mi_rows = h->mi_rows; C.bd = h->bit_depth;
+    C.has_next = c + 1 < sb_cols;
+    for (int p = 0; p < 3; p++) {
+      C.stride[p] = stride[p];
+      w.base[p] = buf[p].data() + c * (p ? G::nC : 64);
+    }
+    // prologue: the first superblock is fetched and committed before the loop
+    set_row(w, 0);
+    for (int tid = 0; tid < G::NT; tid++) {
+      Vec(&pre)[G::kPre] = *(Vec(*)[G::kPre]) & w.pre[(size_t)tid * G::kPre];
+      lf_phase_prefetch<Px, SUB>(C.g, C.stride, C.has_next, tid, pre);
+      lf_phase_commit<Px, SUB>(C, tid, pre);
     }
   }
-  *n_chain = 0;
-  for (int t = 0; t < nsb; t++) *n_chain += chain[t];
+  auto dependent = [&](Worker<Px, SUB> &w) {
+    if (w.C.sbc == 0) return;
+    for (int tid = 0; tid < G::NT; tid++) { lf_phase_merge_left(w.C, tid); lf_phase_vertical(w.C, tid, true); }
+  };
+  // one step of a worker; returns false if its wait is not satisfied yet
+  auto step = [&](int c) -> bool {
+    Worker<Px, SUB> &w = W[c];
+    if (w.r >= sb_rows) return false;
+    LfCtx<Px, SUB> &C = w.C;
+    const bool next_row = w.r + 1 < sb_rows;
+    const int keep = next_row ? 8 : 0;
+    if (w.part == 0) {
+      set_row(w, w.r);
+      bool ch = false;
+      for (int u = 0; u < LfPlanUnits<Px, SUB>::value; u++) ch |= lf_plan_unit<Px, SUB>(*C.M, c > 0, u, C.dset);
+      if (ch && c > 0 && edge_done[c - 1] <= w.r) return false;      // would wait for F_edge(r, c-1)
+      w.chain = ch;
+      *n_chain += ch;
+      if (next_row) {      // fetch of the next superblock is issued first
+        Px *g[3];
+        for (int p = 0; p < 3; p++) g[p] = w.base[p] + (size_t)(w.r + 1) * (p ? G::nC : 64) * stride[p];
+        for (int tid = 0; tid < G::NT; tid++)
+          lf_phase_prefetch<Px, SUB>(g, C.stride, C.has_next, tid, *(Vec(*)[G::kPre]) & w.pre[(size_t)tid * G::kPre]);
+      }
+      for (int tid = 0; tid < G::NT; tid++) lf_phase_vertical(C, tid, false);
+      if (w.chain) dependent(w);
+      for (int tid = 0; tid < G::NT; tid++) lf_phase_horizontal(C, tid, 0);
+      if (C.has_next)
+        for (int tid = 0; tid < G::NT; tid++) lf_phase_next_left_edge(C, tid);
+      for (int tid = 0; tid < G::NT; tid++) lf_phase_store(C, tid, 0, keep);
+      edge_done[c] = w.r + 1;
+      w.part = 1;
+      return true;
+    }
+    if (!w.chain && c > 0 && edge_done[c - 1] <= w.r) return false;
+    if (!w.chain) dependent(w);
+    for (int tid = 0; tid < G::NT; tid++) lf_phase_horizontal(C, tid, 1);
+    for (int tid = 0; tid < G::NT; tid++) lf_phase_store(C, tid, 1, keep);
+    if (next_row) {
+      Px *nt = w.buf[(w.r + 1) & 1].data();
+      for (int tid = 0; tid < G::NT; tid++) lf_phase_carry(C, nt, tid);
+      LfCtx<Px, SUB> N = C;
+      N.tile = nt;
+      for (int tid = 0; tid < G::NT; tid++) lf_phase_commit<Px, SUB>(N, tid, *(Vec(*)[G::kPre]) & w.pre[(size_t)tid * G::kPre]);
+    }
+    w.part = 0;
+    w.r++;
+    return true;
+  };
+  // schedule 0: lock step (all workers part 0 of a row, then all part 1); 1: worker 0 completely,
+  // then worker 1, ...; otherwise a seeded random choice among the workers that can advance
+  if (schedule == 0) {
+    for (int r = 0; r < sb_rows; r++)
+      for (int part = 0; part < 2; part++)
+        for (int c = 0; c < sb_cols; c++)
+          if (!step(c)) return -10;
+  } else if (schedule == 1) {
+    for (int c = 0; c < sb_cols; c++)
+      for (int k = 0; k < 2 * sb_rows; k++)
+        if (!step(c)) return -11;
+  } else {
+    std::mt19937 rng(schedule);
+    int left = 2 * sb_rows * sb_cols, stuck = 0;
+    while (left > 0) {
+      const int c = (int)(rng() % (unsigned)sb_cols);
+      if (step(c)) { left--; stuck = 0; }
+      else if (++stuck > 100000) return -12;
+    }
+  }
   for (int p = 0; p < 3; p++)
     for (int r = 0; r < std::min(prow[p], rows[p]); r++)
       for (int x = 0; x < std::min(stride[p], strides[p]); x++) planes[p][(size_t)r * strides[p] + x] = buf[p][(size_t)r * stride[p] + x];
