@@ -44,6 +44,33 @@ def test_reference_c_decoder_prints_the_golden_md5s(name):
     assert run_vpxdec(name, "cpu") == golden_md5(name)
 
 
+FAKE = os.path.join(ROOT, "tests", "emul", "_build_fakegpu.so")
+
+
+def fake_gpu_lib():
+    """vp9gpu_* on top of the CPU oracle + the product packer: the shim's gpu mode without a GPU."""
+    src = [os.path.join(ROOT, "tests", "emul", "fake_gpu.c"), os.path.join(ROOT, "oracle", "vp9_recon_ref.c"),
+           os.path.join(ROOT, "cuda-vp9_b200", "csrc", "vp9_packer.cc"), os.path.join(ROOT, "include", "vp9_b200.h")]
+    if not os.path.exists(FAKE) or os.path.getmtime(FAKE) < max(os.path.getmtime(f) for f in src):
+        obj = FAKE[:-3] + ".o"
+        subprocess.check_call(["gcc", "-O2", "-std=c99", "-fPIC", "-c", "-Wno-unused-function", src[0], "-o", obj])
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-I" + os.path.join(ROOT, "include"), obj, src[2],
+                               "-o", FAKE])
+    return FAKE
+
+
+@needs_binary
+@pytest.mark.parametrize("name", SMALL)
+def test_libvpx_parser_through_the_packer_reproduces_the_golden_md5s(name):
+    """gpu mode of the shim with vp9gpu_* served by the CPU oracle: libvpx's own parser feeds
+    vp9b_packer_*, so the packing contract is checked with a parser that is not ours."""
+    env = dict(os.environ, VP9B_SHIM="gpu", VP9B_LIB=fake_gpu_lib())
+    r = subprocess.run([VPXDEC, "--md5", "--i420", "-o", "img-%w-%h-%4.i420", clip_path(name)], env=env,
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert [l.split()[0] for l in r.stdout.splitlines() if l.strip()] == golden_md5(name)
+
+
 @needs_binary
 @pytest.mark.gpu
 @pytest.mark.parametrize("name", ALL8)

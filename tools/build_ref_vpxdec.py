@@ -130,9 +130,10 @@ def patch_decoder(path):
         raise SystemExit("vp9_decoder.c: vp9_get_raw_frame not found")
     body_end = src.index("\n}\n", m.end())
     body = src[m.end():body_end]
-    k = body.index("*sd = *cm->frame_to_show;")
-    hook = ("{\n    RefCntBuffer *const b200_rc = (RefCntBuffer *)((char *)cm->frame_to_show - offsetof(RefCntBuffer, buf));\n"
-            "    vp9_b200_fetch_frame(pbi, (int)(b200_rc - cm->buffer_pool->frame_bufs));\n  }\n  ")
+    marker = "if (!cm->show_frame) return ret;"
+    k = body.index(marker) + len(marker)
+    hook = ("\n  {\n    RefCntBuffer *const b200_rc = (RefCntBuffer *)((char *)cm->frame_to_show - offsetof(RefCntBuffer, buf));\n"
+            "    vp9_b200_fetch_frame(pbi, (int)(b200_rc - cm->buffer_pool->frame_bufs));\n  }\n")
     body = body[:k] + hook + body[k:]
     src = src[:m.end()] + body + src[body_end:]
     m = re.search(r"void vp9_decoder_remove\(VP9Decoder \*pbi\)\s*\{\n", src)
