@@ -12,6 +12,6 @@ There is no CPU fallback for reconstruction: if the CUDA library or a GPU is mis
 reconstruction classes raise.
 """
 from .capi import (HostParser, GpuRecon, Decoder, FrameHdr, lib_host, lib_gpu, VP9BError,  # noqa: F401
-                   parse_superframe, NUM_SLOTS, PinnedFrame)
+                   parse_superframe, NUM_SLOTS, MAX_BATCH, PinnedFrame)
 from .ivf import ivf_read, ivf_write, md5_planes  # noqa: F401
 from .vpxdec import decode_ivf_md5, decode_ivf  # noqa: F401

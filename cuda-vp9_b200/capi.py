@@ -7,6 +7,7 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 NUM_SLOTS = 12
+MAX_BATCH = 32   # VP9B_MAX_BATCH: frames of different contexts per launch (vp9gpu_frame_submit_device_multi)
 SEC_COUNT = 12
 
 (SEC_BLOCKS, SEC_SUBMV, SEC_TXB_INTER, SEC_TXB_INTRA_Y, SEC_TXB_INTRA_U, SEC_TXB_INTRA_V, SEC_SB_INTRA,

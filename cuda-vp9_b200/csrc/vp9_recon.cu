@@ -8,6 +8,7 @@
 //   3  k_intra           intra prediction + residual, superblock wavefront (a4-a7)
 //   4  k_loopfilter      lpf 4/8/16 in libvpx's normative superblock order (a9-a10)
 // Integer byte work, HBM/L2 bound -- no tensor cores by design (bit exactness).
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -55,6 +56,7 @@ struct PlaneGeom {
 
 struct RefGeom {
   PlaneGeom pl[3];
+  int slot;        // frame slot (selects the TMA descriptors)
   int w[3], h[3];  // crop size per plane
   int x_scale_fp, y_scale_fp, x_step_q4, y_step_q4;
 };
@@ -77,6 +79,7 @@ struct FrameParams {
   const void *coef;
   const vp9b_lfm *lfm;
   MiEntry *mi;
+  const CUtensorMap *tmaps;     // [slot][plane][class] TMA descriptors of the frame pool (nullptr: no staging)
   uint32_t *prog_intra;         // [3][sb_rows] progress counters: prog_base + superblocks done in the row
   uint32_t *prog_lf;            // [sb_rows]
   uint32_t prog_base;           // per-frame epoch offset: counters never need clearing between frames
@@ -91,24 +94,30 @@ struct FrameParams {
   // which stages this frame takes part in, and its own motion-compensation grid (a launch covers a
   // batch of frames of different contexts; its grid is the maximum over the batch)
   int do_inter, do_res, do_intra, do_lf;
-  int gy_y, gy_c, gx_c;
 };
 
 // Frames of up to kMaxBatch different contexts that go through one launch per stage: the hardware
 // has 32 work queues, so more than 32 concurrent streams need several frames per launch.
-constexpr int kMaxBatch = 4;
-struct FrameBatch {
-  FrameParams f[kMaxBatch];
+constexpr int kMaxBatch = VP9B_MAX_BATCH;   // 32 x 728 bytes of kernel parameters (limit: 32764)
+// Two parameter-block sizes: a launch copies the whole block (728 bytes per frame), and 23 KB of
+// parameters cost ~10 us of host time per launch -- single frames and pairs use the small block.
+template <int NB> struct FrameBatchT {
+  static constexpr int kN = NB;
+  FrameParams f[NB];
 };
+typedef FrameBatchT<kMaxBatch> FrameBatch;
+typedef FrameBatchT<2> FrameBatchSmall;
 
 __device__ __constant__ uint8_t d_bw8[13] = { 1, 1, 1, 1, 1, 2, 2, 2, 4, 4, 4, 8, 8 };
 __device__ __constant__ uint8_t d_bh8[13] = { 1, 1, 1, 1, 2, 1, 2, 4, 2, 4, 8, 4, 8 };
 
+#define VP9B_HD __host__ __device__ __forceinline__
 VP9B_DEV int clampi(int v, int lo, int hi) { return min(max(v, lo), hi); }
 
 // ------------------------------------------------------------------------------------------
 // stage 0: block list -> dense mi map
-__global__ void k_expand_blocks(const __grid_constant__ FrameBatch B) {
+template <typename FB>
+__global__ void k_expand_blocks(const __grid_constant__ FB B) {
   const FrameParams &P = B.f[blockIdx.z];
   if (!P.do_inter) return;
   const vp9b_block *__restrict__ blocks = P.blocks;
@@ -261,14 +270,17 @@ __device__ __noinline__ uint4 mc_load_row_clamped(const uint8_t *__restrict__ re
   return make_uint4(w[0], w[1], w[2], w[3]);
 }
 
+// `ref` + rstride describe either a reference plane in global memory or a window of it staged in
+// shared memory (generic address); (xs, ys) = position of the first tap (x0 - 3, y0 - 3) relative
+// to it.  The clamped loads of `edge` units only exist for global planes.
 template <int H>
-VP9B_DEV void mc_unit_fast(const uint8_t *__restrict__ ref, int rstride, int x0, int y0, int sx, int sy, int filter,
+VP9B_DEV void mc_unit_fast(const uint8_t *ref, int rstride, int xs, int ys, int sx, int sy, int filter,
                            bool edge, int rw, int rh, uint32_t *out) {
   constexpr int R = H + 7;  // rows y0-3 .. y0+H+3
   const uint32_t txl = d_taps4[(filter * 16 + sx) * 2], txh = d_taps4[(filter * 16 + sx) * 2 + 1];
   const uint32_t tyl = d_taps4[(filter * 16 + sy) * 2], tyh = d_taps4[(filter * 16 + sy) * 2 + 1];
-  const int xs = x0 - 3, o = (xs & 3) * 8;
-  const uint32_t *p = (const uint32_t *)(ref + (ptrdiff_t)(y0 - 3) * rstride + (xs & ~3));
+  const int o = (xs & 3) * 8;
+  const uint32_t *p = (const uint32_t *)(ref + (ptrdiff_t)ys * rstride + (xs & ~3));
   uint32_t im[R + 1];
 #pragma unroll
   for (int r = 0; r < R; r++) {
@@ -276,9 +288,9 @@ VP9B_DEV void mc_unit_fast(const uint8_t *__restrict__ ref, int rstride, int x0,
     if (sy || (r >= 3 && r < 3 + H)) {
       uint32_t a0, a1, a2, a3;
       if (!edge) {
-        a0 = __ldg(p); a1 = __ldg(p + 1); a2 = __ldg(p + 2); a3 = __ldg(p + 3);
+        a0 = p[0]; a1 = p[1]; a2 = p[2]; a3 = p[3];
       } else {
-        const uint4 a = mc_load_row_clamped(ref, rstride, y0 - 3 + r, xs & ~3, rw, rh);
+        const uint4 a = mc_load_row_clamped(ref, rstride, ys + r, xs & ~3, rw, rh);
         a0 = a.x; a1 = a.y; a2 = a.z; a3 = a.w;
       }
       const uint32_t v0 = __funnelshift_r(a0, a1, o), v1 = __funnelshift_r(a1, a2, o), v2 = __funnelshift_r(a2, a3, o);
@@ -354,102 +366,6 @@ __device__ __noinline__ uint32_t mc_row_slow(const FrameParams &P, const RefGeom
   return w;
 }
 
-// one 4xH unit: all references of the prediction unit, compound average
-template <int H>
-VP9B_DEV void mc_unit(const FrameParams &P, int plane, const MiEntry &e, int mi_row, int mi_col, int x, int y,
-                      uint32_t *out) {
-  const int ss_x = plane ? P.ss_x : 0, ss_y = plane ? P.ss_y : 0;
-  const bool sub8 = e.bsize < 3;
-#pragma unroll 1
-  for (int r = 0; r < (e.ref1 ? 2 : 1); r++) {
-    const RefGeom &R = P.ref[(r ? e.ref1 : e.ref0) - 1];
-    int mvr, mvc;
-    if (sub8) {
-      const vp9b_submv &s = P.submv[e.aux];
-      if (ss_x && ss_y) { mvr = s.chroma[r][0]; mvc = s.chroma[r][1]; }
-      else {
-        const int k = (((y << ss_y) & 7) >> 2) * 2 + (((x << ss_x) & 7) >> 2);
-        mvr = s.luma[k][r][0]; mvc = s.luma[k][r][1];
-      }
-    } else {
-      mvr = e.mv[r][0];
-      mvc = e.mv[r][1];
-    }
-    uint32_t pr[H];
-    bool fast = false;
-    if (R.x_step_q4 == 16 && R.y_step_q4 == 16) {
-      const int smvr = mvr * (1 << (1 - ss_y)), smvc = mvc * (1 << (1 - ss_x));
-      const int x0 = x + (smvc >> 4), y0 = y + (smvr >> 4);
-      // units whose fetch window leaves the reference take the same path with clamped row loads
-      mc_unit_fast<H>((const uint8_t *)R.pl[plane].ptr, R.pl[plane].stride, x0, y0, smvc & 15, smvr & 15, e.filter,
-                      !mc_inside(x0, y0, H, R.w[plane], R.h[plane]), R.w[plane], R.h[plane], pr);
-      fast = true;
-    }
-    if (!fast) {  // scaled reference: exact per-sample path
-#pragma unroll
-      for (int yy = 0; yy < H; yy++) pr[yy] = mc_row_slow(P, R, plane, e, mi_row, mi_col, x, y, yy, mvr, mvc);
-    }
-    if (r == 0) {
-#pragma unroll
-      for (int i = 0; i < H; i++) out[i] = pr[i];
-    } else {
-#pragma unroll
-      for (int i = 0; i < H; i++) out[i] = avg_u8x4(out[i], pr[i]);
-    }
-  }
-}
-
-// Thread = one 4 x H unit; warp = 8 x 4 units (32 x 4H samples) so that a warp mostly stays
-// inside one prediction block.  Luma runs with H = 8 (sub-8x8 blocks split into two 4x4
-// units), 4:2:0 chroma with H = 4 (one unit per 8x8 luma block).
-template <int H>
-VP9B_DEV void inter_pred_u8_body(const FrameParams &P, int plane, int bx_, int by_) {
-  const int ss_x = plane ? P.ss_x : 0, ss_y = plane ? P.ss_y : 0;
-  const int pw = (P.mi_cols * 8) >> ss_x, ph = (P.mi_rows * 8) >> ss_y;
-  const int x = (bx_ * 8 + (threadIdx.x & 7)) * 4;
-  const int y = (by_ * 16 + (threadIdx.x >> 3)) * H;
-  if (x >= pw || y >= ph) return;
-  uint8_t *dst = (uint8_t *)P.dst[plane].ptr + (size_t)y * P.dst[plane].stride + x;
-  const int dstride = P.dst[plane].stride;
-  const int mi_col = (x << ss_x) >> 3, mi_row = (y << ss_y) >> 3;
-  const MiEntry e = P.mi[(size_t)mi_row * P.mi_cols + mi_col];
-  if (!e.ref0) return;
-  if (H == 8 && e.bsize < 3) {  // sub-8x8 block in an unsubsampled plane: two 4x4 units
-#pragma unroll 1
-    for (int half = 0; half < 2; half++) {
-      uint32_t o[4];
-      mc_unit<4>(P, plane, e, mi_row, mi_col, x, y + 4 * half, o);
-#pragma unroll
-      for (int i = 0; i < 4; i++) *(uint32_t *)(dst + (size_t)(i + 4 * half) * dstride) = o[i];
-    }
-    return;
-  }
-  uint32_t o[H];
-  mc_unit<H>(P, plane, e, mi_row, mi_col, x, y, o);
-#pragma unroll
-  for (int i = 0; i < H; i++) *(uint32_t *)(dst + (size_t)i * dstride) = o[i];
-}
-
-// All three planes in one launch: a flat grid of CTAs, luma tiles (32x128 samples) first, then
-// the two chroma planes (4:2:0: 32x64-sample tiles of 4x4 units; 4:4:4: same as luma).
-__global__ void __launch_bounds__(128, 8) k_inter_pred_u8(const __grid_constant__ FrameBatch B) {
-  const FrameParams &P = B.f[blockIdx.z];
-  if (!P.do_inter) return;
-  const int gy_y = P.gy_y, gy_c = P.gy_c, gx_c = P.gx_c;
-  // grid = (tiles across the luma plane, luma tile rows + 2 x chroma tile rows): plane and tile come
-  // from blockIdx without divisions; chroma rows use the first gx_c columns only
-  int by = blockIdx.y, plane = 0;
-  if (by >= gy_y) {
-    by -= gy_y;
-    plane = 1;
-    if (by >= gy_c) { by -= gy_c; plane = 2; }
-    if ((int)blockIdx.x >= gx_c) return;
-  }
-  // one call site per unit height keeps the kernel inside the instruction cache
-  if (plane && P.ss_x) inter_pred_u8_body<4>(P, plane, blockIdx.x, by);
-  else inter_pred_u8_body<8>(P, plane, blockIdx.x, by);
-}
-
 // ------------------------------------------------------------------------------------------
 // stage 1 fast path, high bit depth (vpx_highbd_convolve8*, vpx_convolve.c:292-535): the same
 // 4 x H units on u16 samples.  Reference rows are fetched as aligned 32-bit words (two samples),
@@ -487,13 +403,13 @@ __device__ __noinline__ Row6 mc16_load_row_clamped(const uint16_t *__restrict__ 
 }
 
 template <int H>
-VP9B_DEV void mc_unit_fast16(const uint16_t *__restrict__ ref, int rstride, int x0, int y0, int sx, int sy, int filter,
+VP9B_DEV void mc_unit_fast16(const uint16_t *ref, int rstride, int xs, int ys, int sx, int sy, int filter,
                              bool edge, int rw, int rh, int maxv, uint2 *out) {
-  constexpr int R = H + 7;  // rows y0-3 .. y0+H+3
+  constexpr int R = H + 7;  // rows y0-3 .. y0+H+3; (xs, ys) = first tap relative to `ref` (plane or staged window)
   const uint32_t txl = d_taps4[(filter * 16 + sx) * 2], txh = d_taps4[(filter * 16 + sx) * 2 + 1];
   const uint32_t tyl = d_taps4[(filter * 16 + sy) * 2], tyh = d_taps4[(filter * 16 + sy) * 2 + 1];
-  const int xs = x0 - 3, par = xs & 1, xa = xs - par;
-  const uint16_t *p = ref + (ptrdiff_t)(y0 - 3) * rstride + xa;
+  const int par = xs & 1, xa = xs - par;
+  const uint16_t *p = ref + (ptrdiff_t)ys * rstride + xa;
   uint2 im[R];
 #pragma unroll
   for (int r = 0; r < R; r++) {
@@ -502,9 +418,9 @@ VP9B_DEV void mc_unit_fast16(const uint16_t *__restrict__ ref, int rstride, int 
       uint32_t w[6];
       if (!edge) {
 #pragma unroll
-        for (int i = 0; i < 6; i++) w[i] = __ldg((const uint32_t *)p + i);
+        for (int i = 0; i < 6; i++) w[i] = ((const uint32_t *)p)[i];
       } else {
-        const Row6 t = mc16_load_row_clamped(ref, rstride, y0 - 3 + r, xa, rw, rh);
+        const Row6 t = mc16_load_row_clamped(ref, rstride, ys + r, xa, rw, rh);
 #pragma unroll
         for (int i = 0; i < 6; i++) w[i] = t.w[i];
       }
@@ -579,9 +495,77 @@ __device__ __noinline__ uint2 mc16_row_slow(const FrameParams &P, const RefGeom 
   return make_uint2(s[0] | (s[1] << 16), s[2] | (s[3] << 16));
 }
 
-template <int H>
-VP9B_DEV void mc_unit16(const FrameParams &P, int plane, const MiEntry &e, int mi_row, int mi_col, int x, int y,
-                        uint2 *out) {
+// ------------------------------------------------------------------------------------------
+// stage 1 driver: one CTA per 64x64 superblock, reference windows of the big prediction blocks
+// staged in shared memory by TMA.
+//
+// A thread predicts one 4 x 8 luma unit and one chroma unit of the superblock.  Prediction blocks of
+// 16x16 and larger (most of the area of real streams) are cut into square staging units of
+// S = min(width, height) samples; for each unit and reference one thread issues three
+// cp.async.bulk.tensor.2d copies -- the (S + 7)^2 window of the luma plane and of both chroma
+// planes, at the motion vector's integer offset (rounded down to a 16-byte column) -- into a bump-allocated region of the CTA's
+// staging buffer, all completing on one mbarrier.  The 4 x H units then read their taps from the
+// staged window (generic loads: the same code path reads global memory for small blocks, for units
+// at the frame edge -- TMA fills out-of-range samples with zeros, libvpx replicates the border,
+// vp9_decodeframe.c:432-504 -- and for scaled references).  The window is read from HBM / L2 once,
+// 128 bytes at a time, instead of once per 4-wide unit through L1.
+template <typename Px> struct McStage {
+  static constexpr int kBudget = 24576;     // staging buffer, samples
+  // TMA wants the first column of a box on a 16-byte boundary (measured on B200: an unaligned inner
+  // coordinate raises an illegal-instruction fault), so a window starts at the aligned column at or
+  // before its first tap: box width = alignment slack (15 / 7 samples) + S + 7, rounded up to 16 bytes
+  static constexpr int kAlign = 16 / (int)sizeof(Px);     // samples
+  VP9B_HD static int boxw(int S) {
+    return sizeof(Px) == 1 ? (S == 64 ? 96 : (S == 32 ? 64 : (S == 16 ? 48 : 32))) : (S == 64 ? 80 : (S == 32 ? 48 : (S == 16 ? 32 : 24)));
+  }
+  VP9B_DEV static int cls(int S) { return S == 64 ? 3 : (S == 32 ? 2 : (S == 16 ? 1 : 0)); }   // tensor-map class
+  VP9B_DEV static int region(int S) { return (boxw(S) * (S + 7) + 127) & ~127; }                // samples, 128-aligned
+};
+
+VP9B_DEV uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+VP9B_DEV void mbar_init(uint64_t *bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+VP9B_DEV void mbar_arrive(uint64_t *bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+VP9B_DEV void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+VP9B_DEV void mbar_wait(uint64_t *bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+VP9B_DEV void tma_load_2d(void *dst, const CUtensorMap *map, int x, int y, uint64_t *bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+               ::"r"(smem_u32(dst)), "l"(map), "r"(x), "r"(y), "r"(smem_u32(bar)) : "memory");
+}
+
+// what a unit needs to know about its block's staged windows
+struct McWin {
+  int off[2];     // offset (samples) of the unit's luma window in the staging buffer per reference, -1: not staged
+  int bx, by;     // luma position of the staging unit
+  int S;          // its size
+};
+
+template <typename Px> struct McOut;
+template <> struct McOut<uint8_t> { typedef uint32_t T; };     // 4 samples of a unit row
+template <> struct McOut<uint16_t> { typedef uint2 T; };
+
+// one 4 x H unit of plane `plane` at (x, y): all references, compound average (vpx_convolve_avg,
+// vpx_convolve.c:58-59).  stage == nullptr: nothing staged for this unit.
+template <typename Px, int H>
+VP9B_DEV void mc_unit(const FrameParams &P, const Px *stage, const McWin &W, int plane, const MiEntry &e, int mi_row, int mi_col,
+                      int x, int y, typename McOut<Px>::T *out) {
+  typedef typename McOut<Px>::T Row;
   const int ss_x = plane ? P.ss_x : 0, ss_y = plane ? P.ss_y : 0;
   const bool sub8 = e.bsize < 3;
   const int maxv = (1 << P.bd) - 1;
@@ -590,79 +574,177 @@ VP9B_DEV void mc_unit16(const FrameParams &P, int plane, const MiEntry &e, int m
     const RefGeom &R = P.ref[(r ? e.ref1 : e.ref0) - 1];
     int mvr, mvc;
     if (sub8) {
-      const vp9b_submv &s = P.submv[e.aux];
-      if (ss_x && ss_y) { mvr = s.chroma[r][0]; mvc = s.chroma[r][1]; }
+      const vp9b_submv &sm = P.submv[e.aux];
+      if (ss_x && ss_y) { mvr = sm.chroma[r][0]; mvc = sm.chroma[r][1]; }
       else {
         const int k = (((y << ss_y) & 7) >> 2) * 2 + (((x << ss_x) & 7) >> 2);
-        mvr = s.luma[k][r][0]; mvc = s.luma[k][r][1];
+        mvr = sm.luma[k][r][0]; mvc = sm.luma[k][r][1];
       }
     } else {
       mvr = e.mv[r][0];
       mvc = e.mv[r][1];
     }
-    uint2 pr[H];
+    Row pr[H];
     if (R.x_step_q4 == 16 && R.y_step_q4 == 16) {
       const int smvr = mvr * (1 << (1 - ss_y)), smvc = mvc * (1 << (1 - ss_x));
       const int x0 = x + (smvc >> 4), y0 = y + (smvr >> 4);
-      // fetch window (aligned word reads included): columns x0-4 .. x0+8, rows y0-3 .. y0+H+3
-      const bool inside = x0 - 4 >= 0 && y0 - 3 >= 0 && x0 + 9 <= R.w[plane] && y0 + H + 4 <= R.h[plane];
-      mc_unit_fast16<H>((const uint16_t *)R.pl[plane].ptr, R.pl[plane].stride, x0, y0, smvc & 15, smvr & 15, e.filter,
-                        !inside, R.w[plane], R.h[plane], maxv, pr);
+      const Px *src = (const Px *)R.pl[plane].ptr;
+      int stride = R.pl[plane].stride, xs = x0 - 3, ys = y0 - 3;
+      bool edge;
+      if (stage && W.off[r] >= 0) {
+        // window of the staging unit in this plane: origin = unit position + integer MV - 3
+        const int Sp = W.S >> ss_x;
+        int off = W.off[r];
+        if (plane) off += McStage<Px>::region(W.S) + (plane - 1) * McStage<Px>::region(Sp);
+        src = stage + off;
+        stride = McStage<Px>::boxw(Sp);
+        // first tap of the staging unit in this plane sits (x0 - 3 of the unit's first column) mod alignment into the box
+        xs = x - (W.bx >> ss_x) + (((W.bx >> ss_x) + (smvc >> 4) - 3) & (McStage<Px>::kAlign - 1));
+        ys = y - (W.by >> ss_y);
+        edge = false;
+      } else if (sizeof(Px) == 1) {
+        edge = !(xs >= 0 && ys >= 0 && x0 + 8 <= R.w[plane] && y0 + H + 4 <= R.h[plane]);
+      } else {   // aligned word reads: columns x0-4 .. x0+8
+        edge = !(x0 - 4 >= 0 && ys >= 0 && x0 + 9 <= R.w[plane] && y0 + H + 4 <= R.h[plane]);
+      }
+      if (sizeof(Px) == 1)
+        mc_unit_fast<H>((const uint8_t *)src, stride, xs, ys, smvc & 15, smvr & 15, e.filter, edge, R.w[plane], R.h[plane], (uint32_t *)pr);
+      else
+        mc_unit_fast16<H>((const uint16_t *)src, stride, xs, ys, smvc & 15, smvr & 15, e.filter, edge, R.w[plane], R.h[plane], maxv,
+                          (uint2 *)pr);
     } else {  // scaled reference: exact per-sample path
 #pragma unroll
-      for (int yy = 0; yy < H; yy++) pr[yy] = mc16_row_slow(P, R, plane, e, mi_row, mi_col, x, y, yy, mvr, mvc);
+      for (int yy = 0; yy < H; yy++) {
+        if (sizeof(Px) == 1) ((uint32_t *)pr)[yy] = mc_row_slow(P, R, plane, e, mi_row, mi_col, x, y, yy, mvr, mvc);
+        else ((uint2 *)pr)[yy] = mc16_row_slow(P, R, plane, e, mi_row, mi_col, x, y, yy, mvr, mvc);
+      }
     }
-    if (r == 0) {
 #pragma unroll
-      for (int i = 0; i < H; i++) out[i] = pr[i];
-    } else {
-#pragma unroll
-      for (int i = 0; i < H; i++) out[i] = make_uint2(avg_u16x2(out[i].x, pr[i].x), avg_u16x2(out[i].y, pr[i].y));
+    for (int i = 0; i < H; i++) {
+      if (r == 0) out[i] = pr[i];
+      else if (sizeof(Px) == 1) ((uint32_t *)out)[i] = avg_u8x4(((uint32_t *)out)[i], ((uint32_t *)pr)[i]);
+      else ((uint2 *)out)[i] = make_uint2(avg_u16x2(((uint2 *)out)[i].x, ((uint2 *)pr)[i].x), avg_u16x2(((uint2 *)out)[i].y, ((uint2 *)pr)[i].y));
     }
   }
 }
 
-template <int H>
-VP9B_DEV void inter_pred_u16_body(const FrameParams &P, int plane, int bx_, int by_) {
+// unit (x, y) of `plane` belonging to 8x8 cell `cell` of the superblock: predict and store
+template <typename Px, int H>
+VP9B_DEV void mc_do_unit(const FrameParams &P, const Px *stage, const MiEntry *s_mi, const int (*s_woff)[2], int plane, int cell,
+                         int sbr, int sbc, int x, int y) {
+  typedef typename McOut<Px>::T Row;
   const int ss_x = plane ? P.ss_x : 0, ss_y = plane ? P.ss_y : 0;
-  const int pw = (P.mi_cols * 8) >> ss_x, ph = (P.mi_rows * 8) >> ss_y;
-  const int x = (bx_ * 8 + (threadIdx.x & 7)) * 4;
-  const int y = (by_ * 16 + (threadIdx.x >> 3)) * H;
-  if (x >= pw || y >= ph) return;
-  const int dstride = P.dst[plane].stride;
-  uint16_t *dst = (uint16_t *)P.dst[plane].ptr + (size_t)y * dstride + x;
-  const int mi_col = (x << ss_x) >> 3, mi_row = (y << ss_y) >> 3;
-  const MiEntry e = P.mi[(size_t)mi_row * P.mi_cols + mi_col];
+  if (x >= ((P.mi_cols * 8) >> ss_x) || y >= ((P.mi_rows * 8) >> ss_y)) return;
+  const MiEntry e = s_mi[cell];
   if (!e.ref0) return;
+  const int ci = cell >> 3, cj = cell & 7, mi_row = sbr * 8 + ci, mi_col = sbc * 8 + cj;
+  const int dstride = P.dst[plane].stride;
+  Px *dst = (Px *)P.dst[plane].ptr + (size_t)y * dstride + x;
+  McWin W;
+  W.off[0] = W.off[1] = -1;
+  W.bx = W.by = 0;
+  W.S = 0;
   if (H == 8 && e.bsize < 3) {  // sub-8x8 block in an unsubsampled plane: two 4x4 units
 #pragma unroll 1
     for (int half = 0; half < 2; half++) {
-      uint2 o[4];
-      mc_unit16<4>(P, plane, e, mi_row, mi_col, x, y + 4 * half, o);
+      Row o[4];
+      mc_unit<Px, 4>(P, nullptr, W, plane, e, mi_row, mi_col, x, y + 4 * half, o);
 #pragma unroll
-      for (int i = 0; i < 4; i++) *(uint2 *)(dst + (size_t)(i + 4 * half) * dstride) = o[i];
+      for (int i = 0; i < 4; i++) *(Row *)(dst + (size_t)(i + 4 * half) * dstride) = o[i];
     }
     return;
   }
-  uint2 o[H];
-  mc_unit16<H>(P, plane, e, mi_row, mi_col, x, y, o);
+  if (e.bsize >= 6) {           // 16x16 and larger: the block's staging unit that contains this cell
+    const int S8 = min((int)d_bw8[e.bsize], (int)d_bh8[e.bsize]);
+    const int ci0 = ci & ~(S8 - 1), cj0 = cj & ~(S8 - 1);
+    W.off[0] = s_woff[ci0 * 8 + cj0][0];
+    W.off[1] = s_woff[ci0 * 8 + cj0][1];
+    W.bx = (sbc * 8 + cj0) * 8;
+    W.by = (sbr * 8 + ci0) * 8;
+    W.S = S8 * 8;
+  }
+  Row o[H];
+  mc_unit<Px, H>(P, stage, W, plane, e, mi_row, mi_col, x, y, o);
 #pragma unroll
-  for (int i = 0; i < H; i++) *(uint2 *)(dst + (size_t)i * dstride) = o[i];
+  for (int i = 0; i < H; i++) *(Row *)(dst + (size_t)i * dstride) = o[i];
 }
 
-__global__ void __launch_bounds__(128, 4) k_inter_pred_u16(const __grid_constant__ FrameBatch B) {
+template <typename Px, typename FB>
+__global__ void __launch_bounds__(128, sizeof(Px) == 1 ? 5 : 3) k_inter_pred_sb(const __grid_constant__ FB B) {
   const FrameParams &P = B.f[blockIdx.z];
   if (!P.do_inter) return;
-  const int gy_y = P.gy_y, gy_c = P.gy_c, gx_c = P.gx_c;
-  int by = blockIdx.y, plane = 0;
-  if (by >= gy_y) {
-    by -= gy_y;
-    plane = 1;
-    if (by >= gy_c) { by -= gy_c; plane = 2; }
-    if ((int)blockIdx.x >= gx_c) return;
+  const int sbc = blockIdx.x, sbr = blockIdx.y, tid = threadIdx.x;
+  if (sbc >= P.sb_cols || sbr >= P.sb_rows) return;   // the grid covers the largest frame of the batch
+  extern __shared__ __align__(128) unsigned char mc_smem[];
+  Px *const stage = (Px *)mc_smem;
+  __shared__ MiEntry s_mi[64];
+  __shared__ int s_woff[64][2];
+  __shared__ int s_alloc;
+  __shared__ __align__(8) uint64_t s_bar;
+  // ---- the 64 cells of the superblock
+  if (tid < 64) {
+    const int mi_row = sbr * 8 + (tid >> 3), mi_col = sbc * 8 + (tid & 7);
+    MiEntry e;
+    e.mv[0][0] = e.mv[0][1] = e.mv[1][0] = e.mv[1][1] = 0;
+    e.ref0 = e.ref1 = e.filter = e.bsize = 0;
+    e.aux = 0;
+    if (mi_row < P.mi_rows && mi_col < P.mi_cols) e = P.mi[(size_t)mi_row * P.mi_cols + mi_col];
+    s_mi[tid] = e;
+    s_woff[tid][0] = s_woff[tid][1] = -1;
   }
-  if (plane && P.ss_x) inter_pred_u16_body<4>(P, plane, blockIdx.x, by);
-  else inter_pred_u16_body<8>(P, plane, blockIdx.x, by);
+  if (tid == 0) {
+    s_alloc = 0;
+    mbar_init(&s_bar, 64);
+  }
+  __syncthreads();
+  // ---- staging: the thread of a staging unit's first cell issues its copies
+  if (tid < 64) {
+    const MiEntry e = s_mi[tid];
+    uint32_t bytes = 0;
+    const int ci = tid >> 3, cj = tid & 7;
+    if (P.tmaps && e.ref0 && e.bsize >= 6) {
+      const int S8 = min((int)d_bw8[e.bsize], (int)d_bh8[e.bsize]), S = S8 * 8, Sc = S >> P.ss_x;
+      if (!(ci & (S8 - 1)) && !(cj & (S8 - 1))) {
+        const int bx = (sbc * 8 + cj) * 8, by = (sbr * 8 + ci) * 8;
+        const int need = McStage<Px>::region(S) + 2 * McStage<Px>::region(Sc);
+#pragma unroll 1
+        for (int r = 0; r < (e.ref1 ? 2 : 1); r++) {
+          const RefGeom &R = P.ref[(r ? e.ref1 : e.ref0) - 1];
+          if (R.x_step_q4 != 16 || R.y_step_q4 != 16) continue;
+          // window origins (first tap) in luma and chroma; every tap must lie inside the reference
+          const int wx = bx + ((e.mv[r][1] * 2) >> 4) - 3, wy = by + ((e.mv[r][0] * 2) >> 4) - 3;
+          const int cmx = e.mv[r][1] * (1 << (1 - P.ss_x)), cmy = e.mv[r][0] * (1 << (1 - P.ss_y));
+          const int wxc = (bx >> P.ss_x) + (cmx >> 4) - 3, wyc = (by >> P.ss_y) + (cmy >> 4) - 3;
+          if (wx < 0 || wy < 0 || wx + S + 7 > R.w[0] || wy + S + 7 > R.h[0] || wxc < 0 || wyc < 0 || wxc + Sc + 7 > R.w[1] ||
+              wyc + Sc + 7 > R.h[1])
+            continue;
+          const int off = atomicAdd(&s_alloc, need);
+          if (off + need > McStage<Px>::kBudget) continue;      // buffer full: this unit reads global memory
+          s_woff[tid][r] = off;
+          const CUtensorMap *maps = P.tmaps + (size_t)R.slot * 12;
+          constexpr int am = ~(McStage<Px>::kAlign - 1);
+          tma_load_2d(stage + off, maps + McStage<Px>::cls(S), wx & am, wy, &s_bar);
+          tma_load_2d(stage + off + McStage<Px>::region(S), maps + 4 + McStage<Px>::cls(Sc), wxc & am, wyc, &s_bar);
+          tma_load_2d(stage + off + McStage<Px>::region(S) + McStage<Px>::region(Sc), maps + 8 + McStage<Px>::cls(Sc), wxc & am, wyc, &s_bar);
+          bytes += (uint32_t)sizeof(Px) * (McStage<Px>::boxw(S) * (S + 7) + 2 * McStage<Px>::boxw(Sc) * (Sc + 7));
+        }
+      }
+    }
+    // expect_tx may follow the copies: the phase cannot complete before this thread has arrived
+    if (bytes) mbar_arrive_expect_tx(&s_bar, bytes);
+    else mbar_arrive(&s_bar);
+  }
+  mbar_wait(&s_bar, 0);     // every staged window has landed; s_woff is visible (arrive = release, wait = acquire)
+  // ---- luma: 16 x 8 units of 4 x 8; chroma 4:2:0: 8 x 8 units of 4 x 4 per plane, 4:4:4: like luma
+  mc_do_unit<Px, 8>(P, stage, s_mi, s_woff, 0, ((tid >> 4) << 3) | ((tid & 15) >> 1), sbr, sbc, sbc * 64 + (tid & 15) * 4, sbr * 64 + (tid >> 4) * 8);
+  if (P.ss_x) {
+    const int pl = 1 + (tid >> 6), i = tid & 63;
+    mc_do_unit<Px, 4>(P, stage, s_mi, s_woff, pl, i, sbr, sbc, sbc * 32 + (i & 7) * 4, sbr * 32 + (i >> 3) * 4);
+  } else {
+#pragma unroll 1
+    for (int pl = 1; pl < 3; pl++)
+      mc_do_unit<Px, 8>(P, stage, s_mi, s_woff, pl, ((tid >> 4) << 3) | ((tid & 15) >> 1), sbr, sbc, sbc * 64 + (tid & 15) * 4, sbr * 64 + (tid >> 4) * 8);
+  }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -868,8 +950,8 @@ VP9B_DEV void group_itx_add(int *tbuf, const FrameParams &P, int first, int coun
 }
 
 constexpr int kResWarps = 4;
-template <typename Px, typename PT>
-__global__ void __launch_bounds__(kResWarps * 32) k_residual(const __grid_constant__ FrameBatch B) {
+template <typename Px, typename PT, typename FB>
+__global__ void __launch_bounds__(kResWarps * 32) k_residual(const __grid_constant__ FB B) {
   const FrameParams &P = B.f[blockIdx.z];
   if (!P.do_res) return;
   __shared__ int tbuf[kResWarps][32 * 33];
@@ -895,8 +977,8 @@ __global__ void __launch_bounds__(kResWarps * 32) k_residual(const __grid_consta
 // Residuals of the intra blocks: every block's inverse transform is independent of the prediction,
 // so it is taken off the intra wavefront's dependency chain and computed here, one warp per block,
 // into a residual plane; the wavefront (k_intra) then only predicts and adds.
-template <typename Px, typename PT>
-__global__ void __launch_bounds__(kResWarps * 32) k_intra_residual(const __grid_constant__ FrameBatch B) {
+template <typename Px, typename PT, typename FB>
+__global__ void __launch_bounds__(kResWarps * 32) k_intra_residual(const __grid_constant__ FB B) {
   const FrameParams &P = B.f[blockIdx.z];
   if (!P.do_intra) return;
   __shared__ int tbuf[kResWarps][32 * 33];
@@ -1113,8 +1195,8 @@ template <typename Px> struct IntraTileGeom {
   static constexpr size_t kWarpBytes = (kTileBytes + 32 * 33 * sizeof(int) + sizeof(IntraEdge) + 15) & ~(size_t)15;
 };
 
-template <typename Px, typename PT>
-__global__ void __launch_bounds__(kWaveWarps * 32) k_intra(const __grid_constant__ FrameBatch B) {
+template <typename Px, typename PT, typename FB>
+__global__ void __launch_bounds__(kWaveWarps * 32) k_intra(const __grid_constant__ FB B) {
   const FrameParams &P = B.f[blockIdx.z];
   if (!P.do_intra) return;
   extern __shared__ __align__(16) unsigned char intra_smem[];
@@ -1274,8 +1356,8 @@ VP9B_DEV unsigned long long gtime() { unsigned long long t; asm volatile("mov.u6
 // of (r, c) and the look-ahead columns (left edge of c+1 applied) are in global memory.
 // Producer: all threads store (st.cg), block barrier, one thread fence + st.release.gpu.
 // Consumer (worker c+1): one thread polls (relaxed, then one ld.acquire.gpu), block barrier, ld.cg.
-template <typename Px, bool SUB>
-__global__ void __launch_bounds__(LfGeom<Px, SUB>::NT, SUB ? 6 : 3) k_lf_sb(const __grid_constant__ FrameBatch B) {
+template <typename Px, bool SUB, typename FB>
+__global__ void __launch_bounds__(LfGeom<Px, SUB>::NT, SUB ? 6 : 3) k_lf_sb(const __grid_constant__ FB B) {
   const FrameParams &P = B.f[blockIdx.z];
   if (!P.do_lf) return;
   typedef LfGeom<Px, SUB> G;
@@ -1445,6 +1527,9 @@ struct DevFrame {
   uint32_t width = 0, height = 0;
   int bd = 0, ss_x = 0, ss_y = 0, bps = 1;
   bool valid = false;
+  // geometry the slot's TMA descriptors were encoded for
+  void *tm_base = nullptr;
+  int tm_stride[3] = { 0, 0, 0 }, tm_rows[3] = { 0, 0, 0 }, tm_bps = 0;
 };
 
 struct vp9gpu_ctx {
@@ -1460,10 +1545,12 @@ struct vp9gpu_ctx {
   cudaEvent_t ring_ev[kRing];
   int ring_pos = 0;
   // per-geometry workspace
-  int ws_sb_cols = 0, ws_sb_rows = 0, ws_mi_cols = 0, ws_mi_rows = 0;
+  size_t cap_mi = 0, cap_sb = 0;  // capacities of d_mi (8x8 cells) and d_lf_flags (superblocks)
   MiEntry *d_mi = nullptr;
   uint32_t *d_tickets = nullptr;  // wavefront progress counters
-  uint32_t *d_lf_flags = nullptr; // loop-filter data-flow flags, 2 per superblock
+  uint32_t *d_lf_flags = nullptr; // loop-filter data-flow flags, 1 per superblock
+  CUtensorMap *d_tmaps = nullptr; // [slot][plane][class] TMA descriptors of the frame pool (motion compensation)
+  bool tma_ok = true;             // false once the driver refused a descriptor: kernels then read global memory only
   uint32_t epoch = 0;
   cudaEvent_t join_ev = nullptr;  // joins this context's stream with a batch leader's (submit_device_multi)
   unsigned attr_done = 0;         // kernels whose dynamic shared-memory limit has been raised on this device
@@ -1482,7 +1569,7 @@ struct vp9gpu_ctx {
   uint64_t launches = 0;
   int num_sms = 148;
   bool profiling = false;
-  cudaEvent_t prof_ev[6];
+  cudaEvent_t prof_ev[7];
   float stage_ms[8] = { 0 };
   bool tables_ready = false;
 };
@@ -1538,7 +1625,7 @@ extern "C" vp9gpu_ctx *vp9gpu_create(int device) {
   if (cudaSetDevice(device) != cudaSuccess) { delete ctx; return nullptr; }
   if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return nullptr; }
   for (int i = 0; i < vp9gpu_ctx::kRing; i++) cudaEventCreateWithFlags(&ctx->ring_ev[i], cudaEventDisableTiming);
-  for (int i = 0; i < 6; i++) cudaEventCreate(&ctx->prof_ev[i]);
+  for (int i = 0; i < 7; i++) cudaEventCreate(&ctx->prof_ev[i]);
   cudaDeviceProp prop;
   if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->num_sms = prop.multiProcessorCount;
   if (init_tables(ctx)) { fprintf(stderr, "vp9gpu_create: %s\n", ctx->err.c_str()); delete ctx; return nullptr; }
@@ -1555,7 +1642,7 @@ extern "C" void vp9gpu_destroy(vp9gpu_ctx *ctx) {
     cudaFree(ctx->d_packed[i]);
     cudaEventDestroy(ctx->ring_ev[i]);
   }
-  for (int i = 0; i < 6; i++) cudaEventDestroy(ctx->prof_ev[i]);
+  for (int i = 0; i < 7; i++) cudaEventDestroy(ctx->prof_ev[i]);
   if (ctx->tickets_ready)
     for (int i = 0; i < vp9gpu_ctx::kTickets; i++) cudaEventDestroy(ctx->ticket_ev[i]);
   if (ctx->join_ev) cudaEventDestroy(ctx->join_ev);
@@ -1564,6 +1651,7 @@ extern "C" void vp9gpu_destroy(vp9gpu_ctx *ctx) {
   cudaFree(ctx->d_resid);
   cudaFree(ctx->d_tickets);
   cudaFree(ctx->d_lf_flags);
+  cudaFree(ctx->d_tmaps);
   cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -1657,6 +1745,18 @@ extern "C" int vp9gpu_sync(vp9gpu_ctx *ctx) {
   return 0;
 }
 
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                    const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+// cuTensorMapEncodeTiled through the runtime (the library does not link libcuda)
+static PFN_encodeTiled get_encode_tiled() {
+  void *fn = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
+    return nullptr;
+  return (PFN_encodeTiled)fn;
+}
+
 // device frame geometry: planes padded by 64 samples right/bottom (transform blocks may hang
 // over the aligned frame edge, as they do into libvpx's frame border), stride multiple of 128 B.
 static int setup_slot(vp9gpu_ctx *ctx, int s, uint32_t w, uint32_t h, int bd, int ss_x, int ss_y) {
@@ -1688,27 +1788,73 @@ static int setup_slot(vp9gpu_ctx *ctx, int s, uint32_t w, uint32_t h, int bd, in
   }
   f.width = w; f.height = h; f.bd = bd; f.ss_x = ss_x; f.ss_y = ss_y; f.bps = bps;
   f.valid = true;
+  // TMA descriptors: per plane one box per staging-unit size (8, 16, 32, 64 samples + 7 taps).  The
+  // tensor is the whole padded plane allocation, so a box that hangs over the picture reads padding,
+  // never another allocation; the kernel only stages windows that lie inside the picture anyway.
+  int rows[3];
+  for (int p = 0; p < 3; p++) rows[p] = (ah >> (p ? ss_y : 0)) + 64;
+  const bool same = f.tm_base == f.base && f.tm_bps == bps && !memcmp(f.tm_stride, stride, sizeof(stride)) &&
+                    !memcmp(f.tm_rows, rows, sizeof(rows));
+  if (!same && ctx->tma_ok) {
+    static PFN_encodeTiled encode = get_encode_tiled();
+    if (!encode) ctx->tma_ok = false;
+    if (ctx->tma_ok && !ctx->d_tmaps) {
+      CK(cudaMalloc(&ctx->d_tmaps, sizeof(CUtensorMap) * VP9B_NUM_SLOTS * 12));
+      CK(cudaMemsetAsync(ctx->d_tmaps, 0, sizeof(CUtensorMap) * VP9B_NUM_SLOTS * 12, ctx->stream));
+    }
+    alignas(64) CUtensorMap maps[12];
+    for (int p = 0; p < 3 && ctx->tma_ok; p++)
+      for (int k = 0; k < 4; k++) {
+        const int S = 8 << k;
+        const int boxw = bps == 1 ? McStage<uint8_t>::boxw(S) : McStage<uint16_t>::boxw(S);
+        const cuuint64_t dims[2] = { (cuuint64_t)stride[p], (cuuint64_t)rows[p] };
+        const cuuint64_t strides[1] = { (cuuint64_t)stride[p] * bps };
+        const cuuint32_t box[2] = { (cuuint32_t)boxw, (cuuint32_t)(S + 7) }, estr[2] = { 1, 1 };
+        const CUresult r = encode(&maps[p * 4 + k], bps == 1 ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, f.pl[p].ptr, dims,
+                                  strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                  CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { ctx->tma_ok = false; break; }
+      }
+    if (ctx->tma_ok) {
+      // stream ordered: kernels already queued keep seeing the descriptors they were launched with
+      CK(cudaMemcpyAsync(ctx->d_tmaps + (size_t)s * 12, maps, sizeof(maps), cudaMemcpyHostToDevice, ctx->stream));
+      f.tm_base = f.base; f.tm_bps = bps;
+      memcpy(f.tm_stride, stride, sizeof(stride));
+      memcpy(f.tm_rows, rows, sizeof(rows));
+    }
+  }
   return 0;
 }
 
+// Per-geometry workspace.  Capacities only grow: a stream whose coded size changes (scaled reference
+// frames) must not pay a device-wide synchronisation (cudaFree) at every change.  Stale content is
+// harmless: k_expand_blocks rewrites every cell of the motion map of an inter frame, and the
+// loop-filter flags compare against the frame's epoch.
 static int setup_workspace(vp9gpu_ctx *ctx, const vp9b_frame_hdr *h) {
-  if ((int)h->mi_cols != ctx->ws_mi_cols || (int)h->mi_rows != ctx->ws_mi_rows) {
+  const size_t need_mi = (size_t)h->mi_cols * h->mi_rows, need_sb = (size_t)h->sb_cols * h->sb_rows;
+  if (need_mi > ctx->cap_mi || need_sb > ctx->cap_sb || !ctx->d_tickets) {
     CK(cudaStreamSynchronize(ctx->stream));
-    cudaFree(ctx->d_mi);
-    ctx->d_mi = nullptr;
-    CK(cudaMalloc(&ctx->d_mi, sizeof(MiEntry) * (size_t)h->mi_cols * h->mi_rows));
-    CK(cudaMemsetAsync(ctx->d_mi, 0, sizeof(MiEntry) * (size_t)h->mi_cols * h->mi_rows, ctx->stream));
-    cudaFree(ctx->d_lf_flags);
-    ctx->d_lf_flags = nullptr;
-    CK(cudaMalloc(&ctx->d_lf_flags, sizeof(uint32_t) * 2 * (size_t)h->sb_cols * h->sb_rows));
-    CK(cudaMemsetAsync(ctx->d_lf_flags, 0, sizeof(uint32_t) * 2 * (size_t)h->sb_cols * h->sb_rows, ctx->stream));
+    if (need_mi > ctx->cap_mi) {
+      cudaFree(ctx->d_mi);
+      ctx->d_mi = nullptr;
+      ctx->cap_mi = 0;
+      CK(cudaMalloc(&ctx->d_mi, sizeof(MiEntry) * need_mi));
+      CK(cudaMemsetAsync(ctx->d_mi, 0, sizeof(MiEntry) * need_mi, ctx->stream));
+      ctx->cap_mi = need_mi;
+    }
+    if (need_sb > ctx->cap_sb) {
+      cudaFree(ctx->d_lf_flags);
+      ctx->d_lf_flags = nullptr;
+      ctx->cap_sb = 0;
+      CK(cudaMalloc(&ctx->d_lf_flags, sizeof(uint32_t) * 2 * need_sb));
+      CK(cudaMemsetAsync(ctx->d_lf_flags, 0, sizeof(uint32_t) * 2 * need_sb, ctx->stream));
+      ctx->cap_sb = need_sb;
+    }
     if (!ctx->d_tickets) {
       CK(cudaMalloc(&ctx->d_tickets, sizeof(uint32_t) * (4096 + 64)));
       CK(cudaMemsetAsync(ctx->d_tickets, 0, sizeof(uint32_t) * (4096 + 64), ctx->stream));
     }
     CK(cudaStreamSynchronize(ctx->stream));
-    ctx->ws_mi_cols = h->mi_cols; ctx->ws_mi_rows = h->mi_rows;
-    ctx->ws_sb_cols = h->sb_cols; ctx->ws_sb_rows = h->sb_rows;
   }
   return 0;
 }
@@ -1716,24 +1862,20 @@ static int setup_workspace(vp9gpu_ctx *ctx, const vp9b_frame_hdr *h) {
 // One launch per stage for a batch of n prepared frames (one per context, all of the same sample
 // type and chroma format) on the stream of the first context.  Grids are the maximum over the
 // batch; a frame that does not take part in a stage has its flag cleared and its CTAs return.
-template <typename Px, typename PT>
-static int launch_batch(vp9gpu_ctx *const *ctxs, FrameBatch &B, int n) {
+template <typename Px, typename PT, typename FB>
+static int launch_batch(vp9gpu_ctx *const *ctxs, FB &B, int n) {
+  constexpr unsigned abase = FB::kN == kMaxBatch ? 0u : 16u;   // attribute bits of the small-block instantiations
   vp9gpu_ctx *ctx = ctxs[0];
   cudaStream_t st = ctx->stream;
   const int stop = ctx->stop_stage;
-  const bool prof = ctx->profiling && n == 1;
+  const bool prof = ctx->profiling;
   int g_expand = 0, g_mcx = 0, g_mcy = 0, g_res = 0, g_ires = 0, g_intra = 0, g_lf = 0;
   for (int i = 0; i < n; i++) {
     FrameParams &P = B.f[i];
     if (P.do_inter) {
       g_expand = std::max(g_expand, (P.n_blocks * 8 + 127) / 128);
-      const int pwy = P.mi_cols * 8, phy = P.mi_rows * 8;
-      const int pwc = pwy >> P.ss_x, phc = phy >> P.ss_y;
-      P.gy_y = (phy + 127) / 128;
-      P.gx_c = (pwc + 31) / 32;
-      P.gy_c = P.ss_x ? (phc + 63) / 64 : (phc + 127) / 128;
-      g_mcx = std::max(g_mcx, (pwy + 31) / 32);
-      g_mcy = std::max(g_mcy, P.gy_y + 2 * P.gy_c);
+      g_mcx = std::max(g_mcx, P.sb_cols);
+      g_mcy = std::max(g_mcy, P.sb_rows);
     }
     P.do_res = P.do_inter && stop != 1 && P.n_txb_inter > 0;
     if (P.do_res) {
@@ -1759,36 +1901,44 @@ static int launch_batch(vp9gpu_ctx *const *ctxs, FrameBatch &B, int n) {
   }
   if (prof) cudaEventRecord(ctx->prof_ev[0], st);
   if (g_expand) {
-    k_expand_blocks<<<dim3(g_expand, 1, n), 128, 0, st>>>(B);
+    k_expand_blocks<FB><<<dim3(g_expand, 1, n), 128, 0, st>>>(B);
     ctx->launches++;
   }
   if (prof) cudaEventRecord(ctx->prof_ev[1], st);
   if (g_mcx) {
-    const dim3 grid(g_mcx, g_mcy, n);
-    if (sizeof(Px) == 1) k_inter_pred_u8<<<grid, 128, 0, st>>>(B);
-    else k_inter_pred_u16<<<grid, 128, 0, st>>>(B);
+    const dim3 grid(g_mcx, g_mcy, n);   // one CTA per superblock
+    const size_t smem = McStage<Px>::kBudget * sizeof(Px);
+    const unsigned abit = (sizeof(Px) == 1 ? 64u : 128u) << abase;
+    if (!(ctx->attr_done & abit)) {
+      CK(cudaFuncSetAttribute(k_inter_pred_sb<Px, FB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      ctx->attr_done |= abit;
+    }
+    k_inter_pred_sb<Px, FB><<<grid, 128, smem, st>>>(B);
     ctx->launches++;
   }
   if (prof) cudaEventRecord(ctx->prof_ev[2], st);
   if (g_res) {
-    k_residual<Px, PT><<<dim3(g_res, 1, n), kResWarps * 32, 0, st>>>(B);
+    k_residual<Px, PT, FB><<<dim3(g_res, 1, n), kResWarps * 32, 0, st>>>(B);
     ctx->launches++;
   }
   if (prof) cudaEventRecord(ctx->prof_ev[3], st);
   if (g_intra) {
     const size_t ismem = IntraTileGeom<Px>::kWarpBytes * kWaveWarps;
     // opt-in shared memory size: per device, so remembered per context (one context = one device)
-    const unsigned abit = sizeof(Px) == 1 ? 1u : 2u;
+    const unsigned abit = (sizeof(Px) == 1 ? 1u : 2u) << abase;
     if (!(ctx->attr_done & abit)) {
-      CK(cudaFuncSetAttribute(k_intra<Px, PT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ismem));
+      CK(cudaFuncSetAttribute(k_intra<Px, PT, FB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ismem));
       ctx->attr_done |= abit;
     }
-    k_intra_residual<Px, PT><<<dim3(g_ires, 1, n), kResWarps * 32, 0, st>>>(B);
+    k_intra_residual<Px, PT, FB><<<dim3(g_ires, 1, n), kResWarps * 32, 0, st>>>(B);
     ctx->launches++;
-    k_intra<Px, PT><<<dim3(g_intra, 1, n), kWaveWarps * 32, ismem, st>>>(B);
+    if (prof) cudaEventRecord(ctx->prof_ev[4], st);
+    k_intra<Px, PT, FB><<<dim3(g_intra, 1, n), kWaveWarps * 32, ismem, st>>>(B);
     ctx->launches++;
+  } else if (prof) {
+    cudaEventRecord(ctx->prof_ev[4], st);
   }
-  if (prof) cudaEventRecord(ctx->prof_ev[4], st);
+  if (prof) cudaEventRecord(ctx->prof_ev[5], st);
   if (g_lf) {
     // one persistent CTA per superblock column of the widest frame in the batch; threads = sample rows of the three planes
     int max_rows = 0;
@@ -1797,21 +1947,21 @@ static int launch_batch(vp9gpu_ctx *const *ctxs, FrameBatch &B, int n) {
     // opt-in shared-memory limit, once per device and kernel variant: two tiles + the plan of the tallest frame (16384 / 64 rows)
     const bool sub = B.f[0].ss_x != 0;
     const size_t tiles = 2 * (sub ? LfGeom<Px, true>::kTileBytes : LfGeom<Px, false>::kTileBytes);
-    const unsigned abit = (sizeof(Px) == 1 ? 4u : 8u) << (sub ? 2 : 0);
+    const unsigned abit = ((sizeof(Px) == 1 ? 4u : 8u) << (sub ? 2 : 0)) << abase;
     if (!(ctx->attr_done & abit)) {
       const int lim = (int)(tiles + 256 * 49 + 16);
-      if (sub) CK(cudaFuncSetAttribute(k_lf_sb<Px, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
-      else CK(cudaFuncSetAttribute(k_lf_sb<Px, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+      if (sub) CK(cudaFuncSetAttribute((k_lf_sb<Px, true, FB>), cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+      else CK(cudaFuncSetAttribute((k_lf_sb<Px, false, FB>), cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
       ctx->attr_done |= abit;
     }
-    if (sub) k_lf_sb<Px, true><<<dim3(g_lf, 1, n), LfGeom<Px, true>::NT, tiles + plan_bytes, st>>>(B);
-    else k_lf_sb<Px, false><<<dim3(g_lf, 1, n), LfGeom<Px, false>::NT, tiles + plan_bytes, st>>>(B);
+    if (sub) k_lf_sb<Px, true, FB><<<dim3(g_lf, 1, n), LfGeom<Px, true>::NT, tiles + plan_bytes, st>>>(B);
+    else k_lf_sb<Px, false, FB><<<dim3(g_lf, 1, n), LfGeom<Px, false>::NT, tiles + plan_bytes, st>>>(B);
     ctx->launches++;
   }
   if (prof) {
-    cudaEventRecord(ctx->prof_ev[5], st);
-    cudaEventSynchronize(ctx->prof_ev[5]);
-    for (int i = 0; i < 5; i++) {
+    cudaEventRecord(ctx->prof_ev[6], st);
+    cudaEventSynchronize(ctx->prof_ev[6]);
+    for (int i = 0; i < 6; i++) {
       float ms = 0;
       cudaEventElapsedTime(&ms, ctx->prof_ev[i], ctx->prof_ev[i + 1]);
       ctx->stage_ms[i] += ms;
@@ -1969,6 +2119,7 @@ static int prepare_frame(vp9gpu_ctx *ctx, const uint8_t *d_packed, const vp9b_fr
         ctx->err = "reference scale out of range";
         return VP9B_ERR_INVALID;
       }
+      P.ref[r].slot = rd.slot;
       for (int p = 0; p < 3; p++) {
         P.ref[r].pl[p] = F.pl[p];
         P.ref[r].w[p] = p ? (int)((rd.width + h->ss_x) >> h->ss_x) : (int)rd.width;
@@ -2017,6 +2168,7 @@ static int prepare_frame(vp9gpu_ctx *ctx, const uint8_t *d_packed, const vp9b_fr
   P.coef = d_packed + h->sec[VP9B_SEC_COEF].offset;
   P.lfm = (const vp9b_lfm *)(d_packed + h->sec[VP9B_SEC_LFM].offset);
   P.mi = ctx->d_mi;
+  P.tmaps = ctx->tma_ok ? ctx->d_tmaps : nullptr;
   // progress counters: [0, 3*1024) intra (plane, row), [3072, 4096) loop filter.  Values are
   // prog_base + count with prog_base advancing by 2048 per frame; cleared only when it wraps.
   if (h->width > 16384 || h->height > 16384) { ctx->err = "frame too large"; return VP9B_ERR_UNSUP; }
@@ -2037,12 +2189,37 @@ static int prepare_frame(vp9gpu_ctx *ctx, const uint8_t *d_packed, const vp9b_fr
 }
 
 static int submit_device(vp9gpu_ctx *ctx, const uint8_t *d_packed, const vp9b_frame_hdr *h) {
-  FrameBatch B;
+  FrameBatchSmall B;
   int e = prepare_frame(ctx, d_packed, h, B.f[0]);
   if (e) return e;
   vp9gpu_ctx *one[1] = { ctx };
   if (h->bit_depth == 8) return launch_batch<uint8_t, int>(one, B, 1);
   return launch_batch<uint16_t, long long>(one, B, 1);
+}
+
+template <typename FB>
+static int submit_multi_impl(vp9gpu_ctx *const *ctxs, const void *const *d_packed, const vp9b_frame_hdr *const *hdr, int n) {
+  vp9gpu_ctx *lead = ctxs[0];
+  FB B;
+  for (int i = 0; i < n; i++) {
+    const int e = prepare_frame(ctxs[i], (const uint8_t *)d_packed[i], hdr[i], B.f[i]);
+    if (e) { lead->err = ctxs[i]->err; return e; }
+  }
+  CK2(lead, cudaSetDevice(lead->device));
+  for (int i = 1; i < n; i++) {   // join: the lead stream continues after everything queued on the others
+    if (!ctxs[i]->join_ev) CK2(lead, cudaEventCreateWithFlags(&ctxs[i]->join_ev, cudaEventDisableTiming));
+    CK2(lead, cudaEventRecord(ctxs[i]->join_ev, ctxs[i]->stream));
+    CK2(lead, cudaStreamWaitEvent(lead->stream, ctxs[i]->join_ev, 0));
+  }
+  int e;
+  if (hdr[0]->bit_depth == 8) e = launch_batch<uint8_t, int>(ctxs, B, n);
+  else e = launch_batch<uint16_t, long long>(ctxs, B, n);
+  if (e) return e;
+  for (int i = 1; i < n; i++) {   // fork: later work on the other streams waits for this batch
+    CK2(lead, cudaEventRecord(ctxs[i]->join_ev, lead->stream));
+    CK2(lead, cudaStreamWaitEvent(ctxs[i]->stream, ctxs[i]->join_ev, 0));
+  }
+  return 0;
 }
 
 // Frames of n different contexts through one launch per stage.  They run on the stream of the first
@@ -2067,27 +2244,8 @@ extern "C" int vp9gpu_frame_submit_device_multi(vp9gpu_ctx *const *ctxs, const v
     }
     return 0;
   }
-  vp9gpu_ctx *lead = ctxs[0];
-  FrameBatch B;
-  for (int i = 0; i < n; i++) {
-    const int e = prepare_frame(ctxs[i], (const uint8_t *)d_packed[i], hdr[i], B.f[i]);
-    if (e) { lead->err = ctxs[i]->err; return e; }
-  }
-  CK2(lead, cudaSetDevice(lead->device));
-  for (int i = 1; i < n; i++) {   // join: the lead stream continues after everything queued on the others
-    if (!ctxs[i]->join_ev) CK2(lead, cudaEventCreateWithFlags(&ctxs[i]->join_ev, cudaEventDisableTiming));
-    CK2(lead, cudaEventRecord(ctxs[i]->join_ev, ctxs[i]->stream));
-    CK2(lead, cudaStreamWaitEvent(lead->stream, ctxs[i]->join_ev, 0));
-  }
-  int e;
-  if (hdr[0]->bit_depth == 8) e = launch_batch<uint8_t, int>(ctxs, B, n);
-  else e = launch_batch<uint16_t, long long>(ctxs, B, n);
-  if (e) return e;
-  for (int i = 1; i < n; i++) {   // fork: later work on the other streams waits for this batch
-    CK2(lead, cudaEventRecord(ctxs[i]->join_ev, lead->stream));
-    CK2(lead, cudaStreamWaitEvent(ctxs[i]->stream, ctxs[i]->join_ev, 0));
-  }
-  return 0;
+  if (n <= FrameBatchSmall::kN) return submit_multi_impl<FrameBatchSmall>(ctxs, d_packed, hdr, n);
+  return submit_multi_impl<FrameBatch>(ctxs, d_packed, hdr, n);
 }
 
 extern "C" int vp9gpu_frame_submit_device(vp9gpu_ctx *ctx, const void *d_packed, const vp9b_frame_hdr *hdr) {

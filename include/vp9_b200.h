@@ -153,9 +153,10 @@ int vp9gpu_frame_submit_device_n(vp9gpu_ctx *ctx, const void *const *d_packed,
                                  const vp9b_frame_hdr *const *hdr, int n);
 /* One frame of each of n DIFFERENT contexts (same device) through one kernel launch per stage: the
  * hardware has 32 work queues, so serving more than 32 concurrent streams per GPU means batching
- * several streams per launch.  Up to 4 frames of the same sample type (8-bit / high bit depth) and
- * chroma format share the launches (others are submitted one by one); they run on the stream of
- * ctxs[0], the other contexts' streams are joined before and after.  Frame sizes may differ. */
+ * several streams per launch.  Up to VP9B_MAX_BATCH frames of the same sample type (8-bit / high bit
+ * depth) and chroma format share the launches (others are submitted one by one); they run on the
+ * stream of ctxs[0], the other contexts' streams are joined before and after.  Frame sizes may differ. */
+#define VP9B_MAX_BATCH 32
 int vp9gpu_frame_submit_device_multi(vp9gpu_ctx *const *ctxs, const void *const *d_packed,
                                      const vp9b_frame_hdr *const *hdr, int n);
 /* Upload a packed buffer to a ctx-owned device allocation for later submit_device calls. */
@@ -202,8 +203,10 @@ int vp9gpu_set_stop_stage(vp9gpu_ctx *ctx, int stage);
 void *vp9gpu_stream(vp9gpu_ctx *ctx);
 /* Number of kernel launches issued since creation. */
 uint64_t vp9gpu_launch_count(vp9gpu_ctx *ctx);
-/* Accumulated device milliseconds per stage since last reset (needs profiling enabled):
- * 0 upload/expand, 1 inter pred, 2 inter residual, 3 intra, 4 loop filter. */
+/* Accumulated device milliseconds per stage since last reset (needs profiling enabled on the
+ * context whose stream the launches run on -- ctxs[0] of a batch): 0 expand, 1 inter pred,
+ * 2 inter residual, 3 intra residual (inverse transforms of intra blocks), 4 intra wavefront,
+ * 5 loop filter. */
 int vp9gpu_set_profiling(vp9gpu_ctx *ctx, int enable);
 int vp9gpu_get_stage_ms(vp9gpu_ctx *ctx, float ms[8], int reset);
 

@@ -20,4 +20,5 @@ if [ -n "$1" ]; then
   timeout 300 python tools/replay.py bench_1440p 1 > gpurun_out/plain.log 2>&1 &&
   timeout 900 ncu --set full --clock-control none --import-source on -k regex:$1 -s 6 -c 2 -f -o gpurun_out/prof_$1 python tools/replay.py bench_1440p 1 > gpurun_out/ncu_$1.log 2>&1
   echo "ncu rc=$?"
+  cp cuda-vp9_b200/libvp9b200.so gpurun_out/lib_for_prof_$1.so   # the by-line tool needs the exact binary
 fi

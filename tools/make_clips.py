@@ -75,18 +75,39 @@ BENCH = {
     "bench_hbd1080": dict(w=1920, h=1080, n=16, bit_depth=10, cpu_used=3, lag=16, auto_alt_ref=1, two_pass=True,
                           bitrate=5000, end_usage=0, tile_cols_log2=2, arnr_maxframes=7, arnr_strength=5, detail=0.02,
                           temporal_noise=3.5, noise_corner=False, threads=8, force_lf=True),
-    "bench_4k": dict(w=3840, h=2160, n=20, cpu_used=2, lag=16, auto_alt_ref=1, two_pass=True, bitrate=12000,
-                     end_usage=0, tile_cols_log2=2, arnr_maxframes=7, arnr_strength=5, detail=0.02,
-                     temporal_noise=3.5, noise_corner=False, threads=8, force_lf=True),
+    # BASELINE.json configs[3]: 4K, 4 tile columns, compound + scaled references.  libvpx ignores
+    # VP8E_SET_SCALEMODE whenever frames are lagged (no alt-ref, hence no compound prediction, in the
+    # encodes that can change the coded size), so the clip is two segments of the same content
+    # spliced at a key frame: a two-pass alt-ref segment (hidden ARF + compound) followed by a
+    # one-pass segment whose coded size goes 4K -> 4/5 -> 3/5 -> 4K, every step predicted from
+    # references of the previous size (x_step_q4 != 16 on up to three references).
+    "bench_4k": dict(segments=[
+        dict(w=3840, h=2160, n=14, cpu_used=2, lag=16, auto_alt_ref=1, two_pass=True, bitrate=12000,
+             end_usage=0, tile_cols_log2=2, arnr_maxframes=7, arnr_strength=5, detail=0.02,
+             temporal_noise=3.5, noise_corner=False, threads=8, force_lf=True),
+        dict(w=3840, h=2160, n=8, seed=77, cpu_used=3, cq_level=52, min_q=40, tile_cols_log2=2, detail=0.02, temporal_noise=3.5,
+             noise_corner=False, threads=8, force_lf=True, scale_at={2: (1, 1), 4: (2, 2), 6: (0, 0)}),
+    ]),
+    # BASELINE.json configs[4], second half: lossless stream (4x4 WHT for every block) at bench size
+    "bench_lossless": dict(w=1920, h=1080, n=6, lossless=1, cpu_used=4, tile_cols_log2=2, detail=0.02,
+                           temporal_noise=2.0, noise_corner=False, threads=8),
 }
 
 
 def make(name, params, outdir):
     kw = dict(params)
-    w, h, n = kw.pop("w"), kw.pop("h"), kw.pop("n")
     path = os.path.join(outdir, "clips", name + ".ivf")
     t = time.time()
-    synth.encode_clip(path, w, h, n, **kw)
+    if "segments" in kw:      # independent encodes spliced at their key frames
+        chunks = []
+        for seg in kw["segments"]:
+            seg = dict(seg)
+            w, h, n = seg.pop("w"), seg.pop("h"), seg.pop("n")
+            chunks += synth.encode_clip(path, w, h, n, **seg)
+        vo.ivf_write(path, chunks, w, h)
+    else:
+        w, h, n = kw.pop("w"), kw.pop("h"), kw.pop("n")
+        synth.encode_clip(path, w, h, n, **kw)
     md5 = vo.decode_ivf_md5(path)
     with open(os.path.join(outdir, "md5", name + ".md5"), "w") as f:
         for i, m in enumerate(md5):

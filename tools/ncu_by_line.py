@@ -38,6 +38,7 @@ def main():
         dis = subprocess.run(["nvdisasm", "-gi", "-c", os.path.join(td, cub)], capture_output=True, text=True).stdout
     # find the function whose mangled name matches: use c++filt on .text.* sections
     funcs, name, lines, cur_line = {}, None, None, None
+    inner, in_group = os.environ.get("INNER") == "1", False
     for l in dis.splitlines():
         m = re.match(r"\s*\.section\s+\.text\.(\S+?),", l)
         if m:
@@ -47,19 +48,24 @@ def main():
             continue
         m = re.search(r'//## File "([^"]+)", line (\d+)(.*)', l)
         if m and name:
-            # with -gi inlined frames are printed innermost first; keep the first of a group
-            cur_line = (os.path.basename(m.group(1)), int(m.group(2)))
+            # with -gi an instruction is preceded by one line per inlined frame, outermost call site
+            # first: INNER=1 attributes to the innermost frame, default to the kernel-level line
+            if inner or not in_group:
+                cur_line = (os.path.basename(m.group(1)), int(m.group(2)))
+            in_group = True
             continue
         if name and re.match(r"\s*/\*[0-9a-f]{4,}\*/\s+\S", l):
             funcs[name].append(cur_line)
+            in_group = False
     dem = {}
     for k in funcs:
         dem[k] = subprocess.run(["c++filt", k], capture_output=True, text=True).stdout.strip()
-    want = blk["name"].replace("(bool)1", "true").replace("(bool)0", "false")
+    def norm(n):
+        return n.replace("(bool)1", "true").replace("(bool)0", "false").replace("vp9b::", "").replace("void ", "").replace(" ", "")
+    want = norm(blk["name"])
     key = None
     for k, d in dem.items():
-        dn = d.replace("vp9b::", "").replace("(bool)1", "true").replace("(bool)0", "false")
-        if kern in d and dn.split("(")[0].replace(" ", "") == want.replace("vp9b::", "").split("(")[0].replace(" ", "").replace("void", ""):
+        if norm(d) == want:
             key = k
     if key is None:
         cands = [k for k, d in dem.items() if kern in d and len(funcs[k]) == len(blk["rows"])]

@@ -28,12 +28,12 @@ def main():
             gpu.submit_device(d, h)
         gpu.sync()
         gpu.stage_ms(reset=True)
-        print("frame  intra_only  expand  inter  resid  intra  lf   (ms)  txb_intra  txb_inter  coefs")
+        print("frame  intra_only  expand  inter  resid  intra_resid  intra  lf   (ms)  txb_intra  txb_inter  coefs")
         for i, (d, h) in enumerate(up):
             gpu.submit_device(d, h)
             gpu.sync()
             ms = gpu.stage_ms(reset=True)
-            print("%3d %d  %s   %d %d %d" % (i, h.intra_only, " ".join("%7.3f" % m for m in ms[:5]),
+            print("%3d %d  %s   %d %d %d" % (i, h.intra_only, " ".join("%7.3f" % m for m in ms[:6]),
                                              h.sec[3].count + h.sec[4].count + h.sec[5].count, h.sec[2].count, h.sec[7].count))
         return
     for _ in range(passes):
