@@ -12,6 +12,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -23,6 +24,7 @@
 #include "vp9_tables.h"
 #include "vp9_txfm.cuh"
 #include "vp9_lf_sb.cuh"
+#include "vp9_lf_warp.cuh"
 
 namespace vp9b {
 
@@ -1498,6 +1500,145 @@ __global__ void __launch_bounds__(LfGeom<Px, SUB>::NT, SUB ? 6 : 3) k_lf_sb(cons
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// stage 4, 8-bit 4:2:0: the same column workers as k_lf_sb, but a worker is ONE WARP whose lanes
+// own four sample rows / columns each and filter them with packed arithmetic (vp9_lf_warp.cuh).
+// A quarter of the threads, a third of the instructions, no block barriers: the phases of a
+// superblock are separated by __syncwarp().  The next superblock's samples are fetched with
+// cp.async into the second tile buffer while the current one is filtered.
+template <typename FB>
+__global__ void __launch_bounds__(32, 16) k_lf_warp(const __grid_constant__ FB B) {
+  const FrameParams &P = B.f[blockIdx.z];
+  if (!P.do_lf) return;
+  extern __shared__ __align__(16) unsigned char lfw_smem[];   // the tile buffer, then the plan
+  __shared__ vp9b_lfm s_M[2][2];                              // [row parity][this superblock, next in the row]
+  const int lane = threadIdx.x;
+  int sbc = 0;
+  if (lane == 0) sbc = (int)(atomicAdd(P.ticket_lf, 1u) - P.ticket_lf_base);
+  sbc = __shfl_sync(0xffffffffu, sbc, 0);
+  const int sb_cols = P.sb_cols, sb_rows = P.sb_rows;
+  if (sbc >= sb_cols) return;   // the launch is as wide as the widest frame of the batch
+  LfwCtx C;
+  C.sbc = sbc;
+  C.sb_cols = sb_cols; C.mi_rows = P.mi_rows;
+  C.has_next = sbc + 1 < sb_cols;
+  C.lf_lim = P.lf_lim;
+  C.lf_mblim = P.lf_mblim;
+  uint8_t *base[3];
+#pragma unroll
+  for (int p = 0; p < 3; p++) {
+    C.stride[p] = P.dst[p].stride;
+    base[p] = (uint8_t *)P.dst[p].ptr + sbc * (p ? 32 : 64);
+  }
+  uint32_t *const flags = P.lf_flags;
+  const uint32_t epoch = P.lf_epoch;
+  auto wait_left = [&](int r) {     // F_edge(r, sbc - 1)
+    if (lane == 0) {
+      const uint32_t *f = flags + r * sb_cols + sbc - 1;
+      while (ld_acquire(f) != epoch) __nanosleep(32);
+    }
+    __syncwarp();
+  };
+  // masks of (r, sbc) and (r, sbc + 1), 40 words each, fetched one superblock ahead
+  uint32_t mw[3] = { 0, 0, 0 };
+  auto fetch_masks = [&](int r) {
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+      const int i = lane + 32 * k;
+      if (i < 80) {
+        const int which = i >= 40;
+        const uint32_t *src = (const uint32_t *)&P.lfm[r * sb_cols + sbc + ((which && C.has_next) ? 1 : 0)];
+        mw[k] = __ldg(src + (which ? i - 40 : i));
+      }
+    }
+  };
+  auto commit_masks = [&](int r) {
+#pragma unroll
+    for (int k = 0; k < 3; k++)
+      if (lane + 32 * k < 80) ((uint32_t *)&s_M[r & 1][0])[lane + 32 * k] = mw[k];
+  };
+  auto row_ptrs = [&](int r, uint8_t *g[3]) {
+#pragma unroll
+    for (int p = 0; p < 3; p++) g[p] = base[p] + (size_t)(r * (p ? 32 : 64)) * C.stride[p];
+  };
+  // plan of the whole column (dependent sets + chain flag per superblock), computed once
+  uint16_t *const plan = (uint16_t *)(lfw_smem + LfwGeom::kTileBytes);   // [sb_rows][24]
+  uint8_t *const plan_chain = (uint8_t *)(plan + (size_t)sb_rows * 24);       // [sb_rows]
+  for (int i = lane; i < sb_rows; i += 32) plan_chain[i] = 0;
+  for (int i = lane; i < sb_rows * 12; i += 32) ((uint32_t *)plan)[i] = 0;
+  __syncwarp();
+  for (int i = lane; i < sb_rows * kLfwPlanUnits; i += 32) {
+    const int r = i / kLfwPlanUnits, u = i - r * kLfwPlanUnits;
+    if (lfw_plan_unit(P.lfm[r * sb_cols + sbc], sbc > 0, u, plan + r * 24)) plan_chain[r] = 1;
+  }
+  __syncwarp();
+  for (int r = lane; r < sb_rows; r += 32)   // bit 1: a dependent set reaches beyond block column 0
+    if (lfw_plan_deep(plan + r * 24)) plan_chain[r] |= 2;
+  // prologue: first superblock of the column
+  fetch_masks(0);
+  commit_masks(0);
+  row_ptrs(0, C.g);
+  C.tile = lfw_smem;
+  lfw_phase_fetch(C.tile, C.g, C.stride, C.has_next, lane);
+  for (int r = 0; r < sb_rows; r++) {
+    const bool next_row = r + 1 < sb_rows;
+    const int keep = next_row ? 8 : 0;
+    C.sbr = r;
+    C.has_top = r > 0;
+    C.M = &s_M[r & 1][0];
+    C.Mn = &s_M[r & 1][1];
+    row_ptrs(r, C.g);
+    lfw_fetch_wait();
+    __syncwarp();                    // tile + masks of this row are in shared memory
+    if (next_row) fetch_masks(r + 1);
+    C.dset = plan + r * 24;
+    const bool chain = (plan_chain[r] & 1) != 0;
+    lfw_phase_vertical(C, lane, false);                  // A
+    if (chain && sbc > 0) {                              // D before H7: this row serialises through F_edge
+      wait_left(r);
+      lfw_phase_merge_left(C, lane);
+      __syncwarp();
+      lfw_phase_vertical(C, lane, true);
+    }
+    __syncwarp();
+    lfw_phase_horizontal(C, lane, 0);                    // H7
+    __syncwarp();
+    if (C.has_next) {
+      lfw_phase_next_left_edge(C, lane);                 // E
+      __syncwarp();
+    }
+    lfw_phase_store(C, lane, 0, keep);
+    if (C.has_next) {                                    // publish F_edge(r, sbc)
+      __syncwarp();
+      if (lane == 0) st_release(flags + r * sb_cols + sbc, epoch);
+    }
+    // D + H.  The left edge and what depends on it normally stay inside block column 0: the other
+    // block columns are filtered first, which hides the wait for the left neighbour.
+    const bool early = !chain && sbc > 0 && !(plan_chain[r] & 2);
+    if (early) lfw_phase_horizontal(C, lane, 2);
+    if (!chain && sbc > 0) {                             // D
+      wait_left(r);
+      lfw_phase_merge_left(C, lane);
+      __syncwarp();
+      lfw_phase_vertical(C, lane, true);
+    }
+    __syncwarp();
+    lfw_phase_horizontal(C, lane, early ? 3 : 1);        // H
+    __syncwarp();
+    lfw_phase_store(C, lane, 1, keep);
+    if (next_row) {
+      // one tile buffer per worker (twice as many workers fit on an SM): the bottom rows move to the
+      // top, then the next superblock is fetched over the interior; other workers cover the latency
+      lfw_phase_carry(C, C.tile, lane);
+      commit_masks(r + 1);
+      __syncwarp();
+      uint8_t *g[3];
+      row_ptrs(r + 1, g);
+      lfw_phase_fetch(C.tile, g, C.stride, C.has_next, lane);
+    }
+  }
+}
+
 // output path: 16-bit samples -> 8 bits (truncating shift, highbd_img_downshift in tools_common.c)
 __global__ void k_downshift(const uint16_t *__restrict__ src, int sstride, uint8_t *__restrict__ dst, int dstride, int w,
                             int h, int shift) {
@@ -1565,6 +1706,7 @@ struct vp9gpu_ctx {
   bool tickets_ready = false;
   uint64_t next_ticket = 1;
   int stop_stage = 0;
+  bool lf_warp = getenv("VP9B_LF_WARP") != nullptr;   // A/B: 8-bit 4:2:0 through k_lf_warp instead of k_lf_sb
   bool validate = true;           // record-level validation of host packed buffers (vp9gpu_set_validation)
   uint64_t launches = 0;
   int num_sms = 148;
@@ -1891,6 +2033,8 @@ static int launch_batch(vp9gpu_ctx *const *ctxs, FB &B, int n) {
     P.do_lf = P.do_lf && stop == 0;
     if (P.do_lf) g_lf = std::max(g_lf, P.sb_cols);
   }
+  // 8-bit 4:2:0 can take the warp-per-column loop filter (VP9B_LF_WARP=1)
+  const bool lf_warp = sizeof(Px) == 1 && B.f[0].ss_x != 0 && ctx->lf_warp;
   // tickets: every participating frame's counter advances by the number of CTAs launched for it
   for (int i = 0; i < n; i++) {
     FrameParams &P = B.f[i];
@@ -1954,7 +2098,9 @@ static int launch_batch(vp9gpu_ctx *const *ctxs, FB &B, int n) {
       else CK(cudaFuncSetAttribute((k_lf_sb<Px, false, FB>), cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
       ctx->attr_done |= abit;
     }
-    if (sub) k_lf_sb<Px, true, FB><<<dim3(g_lf, 1, n), LfGeom<Px, true>::NT, tiles + plan_bytes, st>>>(B);
+    if (lf_warp)
+      k_lf_warp<FB><<<dim3(g_lf, 1, n), 32, LfwGeom::kTileBytes + plan_bytes, st>>>(B);
+    else if (sub) k_lf_sb<Px, true, FB><<<dim3(g_lf, 1, n), LfGeom<Px, true>::NT, tiles + plan_bytes, st>>>(B);
     else k_lf_sb<Px, false, FB><<<dim3(g_lf, 1, n), LfGeom<Px, false>::NT, tiles + plan_bytes, st>>>(B);
     ctx->launches++;
   }

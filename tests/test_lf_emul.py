@@ -46,7 +46,7 @@ def raw_planes(rec, slot):
     return out
 
 
-def check_frame(packed, pre, post, schedules, tag):
+def check_frame(packed, pre, post, schedules, tag, emu_fn=None):
     """pre / post: oracle planes before / after the loop filter (raw geometry)."""
     hdr = vb.FrameHdr.from_buffer_copy(packed[:C.sizeof(vb.FrameHdr)])
     chains = 0
@@ -55,7 +55,7 @@ def check_frame(packed, pre, post, schedules, tag):
         strides = (C.c_int * 3)(*[p.shape[1] for p in pl])
         rows = (C.c_int * 3)(*[p.shape[0] for p in pl])
         nch = C.c_int()
-        e = emu().lfemu_frame(packed, pl[0].ctypes.data, pl[1].ctypes.data, pl[2].ctypes.data, strides, rows, sched,
+        e = (emu_fn or emu().lfemu_frame)(packed, pl[0].ctypes.data, pl[1].ctypes.data, pl[2].ctypes.data, strides, rows, sched,
                               C.byref(nch))
         assert e == 0
         chains = max(chains, nch.value)
@@ -70,7 +70,7 @@ def check_frame(packed, pre, post, schedules, tag):
     return chains
 
 
-def run_stream(name, max_frames=4):
+def run_stream(name, max_frames=4, emu_fn=None):
     _, _, chunks = vb.ivf_read(clip_path(name))
     parser = vb.HostParser()
     a, b = ref_decoder.RefRecon(), ref_decoder.RefRecon()   # a: stops before the loop filter, b: complete
@@ -89,7 +89,7 @@ def run_stream(name, max_frames=4):
                 a.set_frame(s, b.get_frame(s, w, h, bd, sx, sy), bd, sx, sy)
             a.submit(packed, stop_stage=3)
             if hdr.lf_level:
-                check_frame(packed, raw_planes(a, hdr.dst_slot), raw_planes(b, hdr.dst_slot), (0, 1, 7), "%s frame %d" % (name, n))
+                check_frame(packed, raw_planes(a, hdr.dst_slot), raw_planes(b, hdr.dst_slot), (0, 1, 7), "%s frame %d" % (name, n), emu_fn)
                 n += 1
             if n >= max_frames:
                 return n
@@ -119,6 +119,10 @@ def sparse_masks(rng, f, density):
 @pytest.mark.parametrize("bd,ss,w,h", [(8, 1, 328, 200), (8, 1, 520, 136), (10, 1, 200, 264), (8, 0, 200, 136), (12, 0, 136, 72)])
 @pytest.mark.parametrize("density", [2.0, 1.0, 0.5, 0.15])
 def test_emulated_kernel_equals_oracle_on_random_masks(bd, ss, w, h, density):
+    random_mask_case(bd, ss, w, h, density)
+
+
+def random_mask_case(bd, ss, w, h, density, emu_fn=None):
     chains, changed = [], 0
     for seed in range(3):
         rng = np.random.default_rng(1000 * seed + int(density * 100) + bd + w)
@@ -154,7 +158,7 @@ def test_emulated_kernel_equals_oracle_on_random_masks(bd, ss, w, h, density):
         pre = raw_planes(a, 3)
         post = raw_planes(b, 3)
         changed += sum(int((x != y).sum()) for x, y in zip(pre, post))
-        chains.append(check_frame(packed, pre, post, (0, 1, 11, 12), "random bd%d ss%d %dx%d d%.2f seed %d" % (bd, ss, w, h, density, seed)))
+        chains.append(check_frame(packed, pre, post, (0, 1, 11, 12), "random bd%d ss%d %dx%d d%.2f seed %d" % (bd, ss, w, h, density, seed), emu_fn))
     assert changed > 1000            # the filters really did something
     if density > 1.0:
         assert max(chains) > 0      # all-4x4 masks: every superblock takes the serialised (chain) path
