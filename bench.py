@@ -564,7 +564,7 @@ def main():
     ap.add_argument("--e2e-streams", type=int, default=0, help="host threads for the e2e leg (default: host cores)")
     ap.add_argument("--clip", default="4k", choices=sorted(CLIPS))
     ap.add_argument("--passes", type=int, default=4, help="clip passes per step (sizes the timed region: >= 3 s at the defaults)")
-    ap.add_argument("--batch", type=int, default=4, help="streams per kernel launch")
+    ap.add_argument("--batch", type=int, default=16, help="streams per kernel launch")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-others", action="store_true")

@@ -83,7 +83,7 @@ struct FrameParams {
   MiEntry *mi;
   const CUtensorMap *tmaps;     // [slot][plane][class] TMA descriptors of the frame pool (nullptr: no staging)
   uint32_t *prog_intra;         // [3][sb_rows] progress counters: prog_base + superblocks done in the row
-  uint32_t *prog_lf;            // [sb_rows]
+  uint32_t *prog_done;          // [3][sb_rows] the same, counted once the superblock is completely in memory (read by the loop filter)
   uint32_t prog_base;           // per-frame epoch offset: counters never need clearing between frames
   // Work tickets: a wavefront CTA / warp takes its row from a counter instead of blockIdx, so a
   // unit that waits for a lower-numbered one can only be running if that one was started before
@@ -1213,6 +1213,10 @@ __global__ void __launch_bounds__(kWaveWarps * 32) k_intra(const __grid_constant
   __shared__ int s_cta;
   if (threadIdx.x == 0) s_cta = (int)(atomicAdd(P.ticket_intra, 1u) - P.ticket_intra_base);
   __syncthreads();
+  // Programmatic dependent launch: the loop filter of this frame may start as soon as every CTA of
+  // this grid is running (or done).  It follows the reconstruction one superblock row behind through
+  // prog_done and never blocks a CTA of this grid, so starting it early cannot stall the wavefront.
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   const int unit = s_cta * kWaveWarps + warp;
   if (unit >= 3 * P.sb_rows) return;
   // units are ordered row-major so that a row's dependency (row-1, same plane) has a lower index
@@ -1222,6 +1226,7 @@ __global__ void __launch_bounds__(kWaveWarps * 32) k_intra(const __grid_constant
   const int stride = P.dst[plane].stride;
   Px *gplane = (Px *)P.dst[plane].ptr;
   uint32_t *prog = P.prog_intra + plane * P.sb_rows;
+  uint32_t *done = P.prog_done + plane * P.sb_rows;
   const vp9b_sbrange *rgs = P.sb_intra + plane * nsb + sbr * P.sb_cols;
   constexpr int TS = G::kTS, M = G::kMargin;
   Px *T0 = tile + TS + M;  // sample (0,0) of the superblock; row -1 / column -1 hold the neighbours
@@ -1246,7 +1251,10 @@ __global__ void __launch_bounds__(kWaveWarps * 32) k_intra(const __grid_constant
     rg.count = __shfl_sync(0xffffffffu, mine.count, src);
     if (sbc > published) {
       // everything to the left is done (program order); nothing of it is in flight
-      if (lane == 0) st_release(prog + sbr, P.prog_base + (uint32_t)sbc);
+      if (lane == 0) {
+        st_release(prog + sbr, P.prog_base + (uint32_t)sbc);
+        st_release(done + sbr, P.prog_base + (uint32_t)sbc);   // earlier tiles were stored in program order
+      }
       left_in_smem = false;
     }
     Px *g = gplane + (size_t)(sbr * n) * stride + sbc * n;
@@ -1336,9 +1344,13 @@ __global__ void __launch_bounds__(kWaveWarps * 32) k_intra(const __grid_constant
     for (int r = lane; r < n; r += 32) T0[r * TS - 1] = T0[r * TS + n - 1];
     left_in_smem = true;
     __syncwarp();
+    if (lane == 0) st_release(done + sbr, P.prog_base + (uint32_t)(sbc + 1));   // the whole tile is out
     }
   }
-  if (published < P.sb_cols && lane == 0) st_release(prog + sbr, P.prog_base + (uint32_t)P.sb_cols);
+  if (lane == 0) {
+    if (published < P.sb_cols) st_release(prog + sbr, P.prog_base + (uint32_t)P.sb_cols);
+    st_release(done + sbr, P.prog_base + (uint32_t)P.sb_cols);
+  }
 }
 
 // optional phase timing of two loop-filter workers (compile with -DVP9B_LF_TIMING; tools/lf_phases.py
@@ -1407,6 +1419,17 @@ __global__ void __launch_bounds__(LfGeom<Px, SUB>::NT, SUB ? 6 : 3) k_lf_sb(cons
 #pragma unroll
     for (int p = 0; p < 3; p++) g[p] = base[p] + (size_t)(r * (p ? G::nC : 64)) * C.stride[p];
   };
+  // This kernel may have been launched while the intra wavefront of the same frame is still running
+  // (programmatic dependent launch): before the samples of superblock row r are fetched, this
+  // superblock and the next one in the row (look-ahead columns) must be completely reconstructed.
+  const bool follow = P.do_intra != 0;
+  const int need_recon = min(sbc + 2, sb_cols);
+  auto wait_recon = [&](int r) {
+    if (follow) {
+      if (tid < 3) wait_progress(P.prog_done + tid * sb_rows + r, P.prog_base, need_recon);
+      __syncthreads();
+    }
+  };
   // Plan of the whole column, computed once by all threads while the first tile is on its way:
   // per superblock the dependent sets (24 x u16) and the chain flag.  (One superblock's plan is
   // ~400 dependent instructions on one warp: far too long for the per-superblock critical path.)
@@ -1427,6 +1450,7 @@ __global__ void __launch_bounds__(LfGeom<Px, SUB>::NT, SUB ? 6 : 3) k_lf_sb(cons
   commit_masks(0);
   row_ptrs(0, C.g);
   C.tile = (Px *)lf_smem;
+  wait_recon(0);
   lf_phase_prefetch<Px, SUB>(C.g, C.stride, C.has_next, tid, pre);
   lf_phase_commit<Px, SUB>(C, tid, pre);
   for (int r = 0; r < sb_rows; r++) {
@@ -1444,6 +1468,7 @@ __global__ void __launch_bounds__(LfGeom<Px, SUB>::NT, SUB ? 6 : 3) k_lf_sb(cons
     if (next_row) {                  // the next superblock's samples and masks fly while this one is filtered
       Px *g[3];
       row_ptrs(r + 1, g);
+      wait_recon(r + 1);             // one superblock row behind the reconstruction
       lf_phase_prefetch<Px, SUB>(g, C.stride, C.has_next, tid, pre);
       fetch_masks(r + 1);
     }
@@ -1706,6 +1731,7 @@ struct vp9gpu_ctx {
   bool tickets_ready = false;
   uint64_t next_ticket = 1;
   int stop_stage = 0;
+  bool lf_overlap = getenv("VP9B_LF_NO_OVERLAP") == nullptr;   // loop filter launched programmatically behind k_intra
   bool lf_warp = getenv("VP9B_LF_WARP") != nullptr;   // A/B: 8-bit 4:2:0 through k_lf_warp instead of k_lf_sb
   bool validate = true;           // record-level validation of host packed buffers (vp9gpu_set_validation)
   uint64_t launches = 0;
@@ -2098,10 +2124,25 @@ static int launch_batch(vp9gpu_ctx *const *ctxs, FB &B, int n) {
       else CK(cudaFuncSetAttribute((k_lf_sb<Px, false, FB>), cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
       ctx->attr_done |= abit;
     }
-    if (lf_warp)
+    if (lf_warp) {
       k_lf_warp<FB><<<dim3(g_lf, 1, n), 32, LfwGeom::kTileBytes + plan_bytes, st>>>(B);
-    else if (sub) k_lf_sb<Px, true, FB><<<dim3(g_lf, 1, n), LfGeom<Px, true>::NT, tiles + plan_bytes, st>>>(B);
-    else k_lf_sb<Px, false, FB><<<dim3(g_lf, 1, n), LfGeom<Px, false>::NT, tiles + plan_bytes, st>>>(B);
+    } else {
+      // programmatic dependent launch behind k_intra (see there): the column workers start while the
+      // intra wavefront is still running and follow it through prog_done.  Not while profiling (the
+      // stage events would sit between the two kernels) and only directly behind k_intra.
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(g_lf, 1, n);
+      cfg.blockDim = dim3(sub ? LfGeom<Px, true>::NT : LfGeom<Px, false>::NT, 1, 1);
+      cfg.dynamicSmemBytes = tiles + plan_bytes;
+      cfg.stream = st;
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      at[0].val.programmaticStreamSerializationAllowed = 1;
+      cfg.attrs = at;
+      cfg.numAttrs = (g_intra && !prof && ctx->lf_overlap) ? 1 : 0;
+      if (sub) CK(cudaLaunchKernelEx(&cfg, k_lf_sb<Px, true, FB>, B));
+      else CK(cudaLaunchKernelEx(&cfg, k_lf_sb<Px, false, FB>, B));
+    }
     ctx->launches++;
   }
   if (prof) {
@@ -2321,7 +2362,7 @@ static int prepare_frame(vp9gpu_ctx *ctx, const uint8_t *d_packed, const vp9b_fr
   if (++ctx->epoch == 0) ctx->epoch = 1;
   if ((ctx->epoch & 0xfffff) == 0) CK(cudaMemsetAsync(ctx->d_tickets, 0, sizeof(uint32_t) * 4096, ctx->stream));
   P.prog_intra = ctx->d_tickets;
-  P.prog_lf = ctx->d_tickets + 3072;
+  P.prog_done = ctx->d_tickets + 3072;
   P.prog_base = (ctx->epoch & 0xfffff) << 11;
   P.ticket_lf = ctx->d_tickets + 4096;
   P.lf_flags = ctx->d_lf_flags;
