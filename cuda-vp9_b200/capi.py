@@ -50,6 +50,19 @@ class Image(C.Structure):
                 ("ss_x", C.c_int), ("ss_y", C.c_int), ("slot", C.c_int)]
 
 
+class FrameBuffer(C.Structure):      # vp9b_frame_buffer
+    _fields_ = [("data", C.c_void_p), ("size", C.c_size_t), ("priv", C.c_void_p)]
+
+
+class OutFrame(C.Structure):         # vp9b_out_frame
+    _fields_ = [("img", Image), ("planes", C.c_void_p * 3), ("stride", C.c_int * 3), ("fb", FrameBuffer),
+                ("ticket", C.c_uint64)]
+
+
+GET_FB_CB = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_size_t, C.POINTER(FrameBuffer))
+RELEASE_FB_CB = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(FrameBuffer))
+
+
 _host = None
 _gpu = None
 
@@ -377,6 +390,47 @@ class Decoder:
         self._chk(fn(self.d, C.byref(img), pl[0].ctypes.data, pl[1].ctypes.data, pl[2].ctypes.data,
                      pl[0].strides[0], pl[1].strides[0]))
         return True
+
+    def set_frame_buffer_functions(self, get, release):
+        """External output buffers (vpx_codec_set_frame_buffer_functions): get(min_size) -> (address, size, tag),
+        release(tag).  Must be called before the first decode()."""
+        def _get(priv, min_size, fb):
+            try:
+                addr, size, tag = get(min_size)
+            except Exception:
+                return -1
+            fb[0].data, fb[0].size, fb[0].priv = addr, size, tag
+            return 0
+
+        def _rel(priv, fb):
+            try:
+                release(fb[0].priv)
+            except Exception:
+                return -1
+            return 0
+        self._cbs = (GET_FB_CB(_get), RELEASE_FB_CB(_rel))     # keep the trampolines alive
+        self.L.vp9b_decoder_set_frame_buffer_functions.argtypes = [C.c_void_p, GET_FB_CB, RELEASE_FB_CB, C.c_void_p]
+        self._chk(self.L.vp9b_decoder_set_frame_buffer_functions(self.d, self._cbs[0], self._cbs[1], None))
+
+    def get_frame_ext(self):
+        """Shown frame delivered in an application buffer: None, or (OutFrame, [plane arrays]); the arrays are
+        valid after wait(out.ticket) and until release_frame(out)."""
+        out = OutFrame()
+        self.L.vp9b_decoder_get_frame_ext.argtypes = [C.c_void_p, C.POINTER(OutFrame)]
+        if self._chk(self.L.vp9b_decoder_get_frame_ext(self.d, C.byref(out))) == 0:
+            return None
+        im = out.img
+        dt = np.uint16 if im.bit_depth > 8 else np.uint8
+        planes = []
+        for p, (h, w) in enumerate(plane_shapes(im.width, im.height, im.ss_x, im.ss_y)):
+            st = out.stride[p]
+            raw = np.frombuffer((C.c_uint8 * (st * h)).from_address(out.planes[p]), dtype=np.uint8).reshape(h, st)
+            planes.append(raw.view(dt)[:, :w])
+        return out, planes
+
+    def release_frame(self, out):
+        self.L.vp9b_decoder_release_frame.argtypes = [C.c_void_p, C.POINTER(OutFrame)]
+        self._chk(self.L.vp9b_decoder_release_frame(self.d, C.byref(out)))
 
     def sync(self):
         self._chk(self.L.vp9b_decoder_sync(self.d))

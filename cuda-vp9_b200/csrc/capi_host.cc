@@ -1,4 +1,5 @@
 // C ABI, host-only part: parser + superframe splitter (include/vp9_b200.h section 2).
+#include <stdio.h>
 #include <string.h>
 
 #include <exception>
@@ -15,7 +16,16 @@ struct vp9b_parser {
 
 extern "C" {
 
-vp9b_parser *vp9b_parser_create(void) { return new (std::nothrow) vp9b_parser(); }
+vp9b_parser *vp9b_parser_create(void) {
+#if defined(__x86_64__) && defined(__AVX2__)
+  // the host code is built for x86-64-v3 (see __graft_entry__.py): fail cleanly on an older CPU
+  if (!__builtin_cpu_supports("avx2") || !__builtin_cpu_supports("bmi2")) {
+    fprintf(stderr, "vp9b_parser_create: this build needs an x86-64-v3 CPU (AVX2/BMI2); rebuild with VP9B_HOST_ARCH=x86-64\n");
+    return nullptr;
+  }
+#endif
+  return new (std::nothrow) vp9b_parser();
+}
 
 void vp9b_parser_destroy(vp9b_parser *p) { delete p; }
 

@@ -14,6 +14,10 @@ struct vp9b_decoder {
   vp9gpu_ctx *gpu = nullptr;
   std::string err;
   int show_slot = -1;
+  bool started = false;   // a chunk has been decoded: the frame-buffer callbacks are fixed from here on
+  vp9b_get_frame_buffer_cb_fn_t fb_get = nullptr;
+  vp9b_release_frame_buffer_cb_fn_t fb_release = nullptr;
+  void *fb_priv = nullptr;
 };
 
 extern "C" {
@@ -47,6 +51,7 @@ vp9b_parser *vp9b_decoder_parser(vp9b_decoder *d) { return d ? d->parser : nullp
 int vp9b_decoder_decode(vp9b_decoder *d, const uint8_t *data, size_t size) {
   if (!d || !data || !size) return VP9B_ERR_INVALID;
   d->show_slot = -1;
+  d->started = true;
   uint32_t sizes[8];
   const int n = vp9b_parse_superframe(data, size, sizes);
   if (n < 0) {
@@ -122,6 +127,63 @@ int vp9b_decoder_wait(vp9b_decoder *d, uint64_t ticket) {
   const int e = vp9gpu_wait(d->gpu, ticket);
   if (e) d->err = vp9gpu_last_error(d->gpu);
   return e;
+}
+
+// vpx_codec_set_frame_buffer_functions (vpx/src/vpx_decoder.c:174-191): both callbacks or an error,
+// and not after the first frame (vp9_dx_iface.c:decoder_set_fb_fn: "ctx->pbi == NULL" only).
+int vp9b_decoder_set_frame_buffer_functions(vp9b_decoder *d, vp9b_get_frame_buffer_cb_fn_t get,
+                                            vp9b_release_frame_buffer_cb_fn_t release, void *priv) {
+  if (!d || !get || !release) return VP9B_ERR_INVALID;
+  if (d->started) {
+    d->err = "frame buffer functions must be set before the first frame is decoded";
+    return VP9B_ERR_INVALID;
+  }
+  d->fb_get = get;
+  d->fb_release = release;
+  d->fb_priv = priv;
+  return VP9B_OK;
+}
+
+int vp9b_decoder_get_frame_ext(vp9b_decoder *d, vp9b_out_frame *out) {
+  if (!d || !out) return VP9B_ERR_INVALID;
+  if (!d->fb_get) {
+    d->err = "no frame buffer functions installed";
+    return VP9B_ERR_INVALID;
+  }
+  memset(out, 0, sizeof(*out));
+  const int r = vp9b_decoder_get_frame(d, &out->img);
+  if (r <= 0) return r;
+  const vp9b_image &im = out->img;
+  const int bps = im.bit_depth > 8 ? 2 : 1;
+  size_t off[3], total = 0;
+  for (int p = 0; p < 3; p++) {
+    const uint32_t w = p ? (im.width + im.ss_x) >> im.ss_x : im.width, h = p ? (im.height + im.ss_y) >> im.ss_y : im.height;
+    out->stride[p] = (int)((w * bps + 63) & ~63u);
+    off[p] = total;
+    total += (size_t)out->stride[p] * h;
+  }
+  if (d->fb_get(d->fb_priv, total, &out->fb) || !out->fb.data || out->fb.size < total) {
+    d->err = "get_frame_buffer callback failed or returned a buffer that is too small";
+    return VP9B_ERR_MEM;
+  }
+  for (int p = 0; p < 3; p++) out->planes[p] = out->fb.data + off[p];
+  int e = vp9gpu_get_frame_async(d->gpu, im.slot, out->planes[0], out->planes[1], out->planes[2], out->stride[0], out->stride[1]);
+  if (!e) e = vp9gpu_mark(d->gpu, &out->ticket);
+  if (e) {
+    d->err = vp9gpu_last_error(d->gpu);
+    d->fb_release(d->fb_priv, &out->fb);
+    return e;
+  }
+  return 1;
+}
+
+int vp9b_decoder_release_frame(vp9b_decoder *d, vp9b_out_frame *out) {
+  if (!d || !out || !d->fb_release || !out->fb.data) return VP9B_ERR_INVALID;
+  // the copy into the buffer must have finished before the application can reuse it
+  if (out->ticket) vp9gpu_wait(d->gpu, out->ticket);
+  const int e = d->fb_release(d->fb_priv, &out->fb);
+  memset(&out->fb, 0, sizeof(out->fb));
+  return e ? VP9B_ERR_INVALID : VP9B_OK;
 }
 
 }  // extern "C"

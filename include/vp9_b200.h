@@ -290,7 +290,51 @@ int vp9b_decoder_wait(vp9b_decoder *d, uint64_t ticket);
 vp9gpu_ctx *vp9b_decoder_gpu(vp9b_decoder *d);
 vp9b_parser *vp9b_decoder_parser(vp9b_decoder *d);
 
+/* External output buffers (role of vpx_codec_set_frame_buffer_functions, vpx/src/vpx_decoder.c:174,
+ * vpx/vpx_frame_buffer.h:35-80).  Reference frames live on the GPU, so what the application lends
+ * are the buffers the SHOWN frames are delivered in -- ideally page-locked (vp9gpu_alloc_host), so
+ * that the device-to-host copy overlaps the following frames.  get() is called once per shown frame
+ * with the minimum size, release() when the application returns the frame.  Like libvpx: both
+ * callbacks are required, and they cannot be installed once decoding has started. */
+typedef struct vp9b_frame_buffer {
+  uint8_t *data; /* set by get(): at least min_size bytes */
+  size_t size;
+  void *priv;    /* for the application's bookkeeping; handed back to release() */
+} vp9b_frame_buffer;
+typedef int (*vp9b_get_frame_buffer_cb_fn_t)(void *priv, size_t min_size, vp9b_frame_buffer *fb);
+typedef int (*vp9b_release_frame_buffer_cb_fn_t)(void *priv, vp9b_frame_buffer *fb);
+int vp9b_decoder_set_frame_buffer_functions(vp9b_decoder *d, vp9b_get_frame_buffer_cb_fn_t get,
+                                            vp9b_release_frame_buffer_cb_fn_t release, void *priv);
+typedef struct vp9b_out_frame {
+  vp9b_image img;
+  uint8_t *planes[3]; /* inside fb.data, rows of stride[] bytes (64-byte multiples) */
+  int stride[3];
+  vp9b_frame_buffer fb;
+  uint64_t ticket;    /* the samples are in host memory once vp9b_decoder_wait(d, ticket) returns */
+} vp9b_out_frame;
+/* After decode: 1 if a frame is shown -- a buffer is taken from get(), the copy of the frame into it
+ * is enqueued and *out is filled; 0 if there is nothing to show.  (vpx_codec_get_frame with external
+ * frame buffers.)  The frame is returned with vp9b_decoder_release_frame (-> release()). */
+int vp9b_decoder_get_frame_ext(vp9b_decoder *d, vp9b_out_frame *out);
+int vp9b_decoder_release_frame(vp9b_decoder *d, vp9b_out_frame *out);
+
 #ifdef __cplusplus
 }
 #endif
+
+/* The packed format is shared with foreign producers (a libvpx-side packer, the ctypes mirror in
+ * cuda-vp9_b200/capi.py): pin the record sizes at compile time. */
+#if defined(__cplusplus)
+#define VP9B_STATIC_ASSERT(c, m) static_assert(c, m)
+#elif defined(__STDC_VERSION__) && __STDC_VERSION__ >= 201112L
+#define VP9B_STATIC_ASSERT(c, m) _Static_assert(c, m)
+#else
+#define VP9B_STATIC_ASSERT(c, m)
+#endif
+VP9B_STATIC_ASSERT(sizeof(vp9b_block) == 16, "vp9b_block is 16 bytes");
+VP9B_STATIC_ASSERT(sizeof(vp9b_submv) == 40, "vp9b_submv is 40 bytes");
+VP9B_STATIC_ASSERT(sizeof(vp9b_txb) == 12, "vp9b_txb is 12 bytes");
+VP9B_STATIC_ASSERT(sizeof(vp9b_sbrange) == 8, "vp9b_sbrange is 8 bytes");
+VP9B_STATIC_ASSERT(sizeof(vp9b_lfm) == 160, "vp9b_lfm is 160 bytes");
+VP9B_STATIC_ASSERT(sizeof(vp9b_frame_hdr) == 416, "vp9b_frame_hdr is 416 bytes");
 #endif /* VP9_B200_H_ */

@@ -39,8 +39,29 @@ def test_gpu_library_exports_every_declared_symbol():
     assert not missing, missing
 
 
+def test_ctypes_mirror_has_the_layout_of_the_header(tmp_path):
+    """sizeof / offsetof of vp9b_frame_hdr as the C compiler sees them == the hand-written ctypes mirror."""
+    import subprocess
+    fields = ["magic", "total_bytes", "width", "height", "mi_cols", "mi_rows", "sb_cols", "sb_rows", "bit_depth", "ss_x",
+              "ss_y", "lossless", "intra_only", "show_frame", "lf_level", "lf_sharpness", "coef_bytes", "dst_slot", "ref", "sec",
+              "lf_lim", "lf_mblim", "frame_index", "n_inter_px", "n_compound_px", "n_txb_inter_size"]
+    src = tmp_path / "layout.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "vp9_b200.h"\nint main(void) {\n' +
+                   'printf("%zu %zu %zu %zu\\n", sizeof(vp9b_frame_hdr), sizeof(vp9b_image), sizeof(vp9b_out_frame), sizeof(vp9b_frame_buffer));\n' +
+                   "".join('printf("%s %%zu\\n", offsetof(vp9b_frame_hdr, %s));\n' % (f, f) for f in fields) + "return 0; }\n")
+    exe = tmp_path / "layout"
+    subprocess.check_call(["gcc", "-std=c11", "-I" + os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
+    out = subprocess.check_output([str(exe)], text=True).splitlines()
+    sizes = [int(x) for x in out[0].split()]
+    assert sizes == [C.sizeof(vb.FrameHdr), C.sizeof(vb.capi.Image), C.sizeof(vb.capi.OutFrame), C.sizeof(vb.capi.FrameBuffer)]
+    assert C.sizeof(vb.FrameHdr) == 416
+    for line in out[1:]:
+        name, off = line.split()
+        assert getattr(vb.FrameHdr, name).offset == int(off), name
+
+
 def test_struct_sizes_match_the_header():
-    assert C.sizeof(vb.FrameHdr) == 416 or C.sizeof(vb.FrameHdr) % 4 == 0
+    assert C.sizeof(vb.FrameHdr) == 416
     # the C side checks the magic and total_bytes; a packed buffer produced by the parser parses back
     from conftest import clip_path
     _, _, chunks = vb.ivf_read(clip_path("odd2"))

@@ -141,12 +141,17 @@ def test_gpu_concurrent_streams_stay_bit_exact():
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("name", ["hbd10", "hbd12", "p444_hbd", "odd_rt"])
-def test_gpu_8bit_output_is_the_shifted_frame(name):
-    """vp9gpu_get_frame_8bit_async == vpx_img_downshift of the full-depth frame (vpxdec.c:950-978)."""
+def test_gpu_8bit_output_equals_libvpx_downshift(name):
+    """vp9gpu_get_frame_8bit_async == vpx_img_downshift of libvpx's own output (vpxdec
+    --output-bit-depth=8, vpxdec.c:950-978; tools_common.c highbd_img_downshift: sample >> shift).  The
+    reference frames come from libvpx v1.15.2, not from this decoder."""
+    from oracle import vpx_oracle as vo
     _, _, chunks = vb.ivf_read(clip_path(name))
-    parser, gpu = vb.HostParser(), vb.GpuRecon(0)
+    parser, gpu, ref = vb.HostParser(), vb.GpuRecon(0), vo.Decoder(threads=1)
     shown = 0
     for ch in chunks:
+        want = ref.decode(ch, want="planes")
+        got = []
         for fr in vb.parse_superframe(ch):
             packed, show = parser.parse(fr)
             if packed is not None:
@@ -154,14 +159,73 @@ def test_gpu_8bit_output_is_the_shifted_frame(name):
             if show < 0:
                 continue
             w, h, bd, sx, sy = parser.slot_info(show)
-            full = gpu.get_frame(show, w, h, bd, sx, sy)
-            eight = gpu.get_frame_8bit(show, w, h, sx, sy)
+            got = [(gpu.get_frame_8bit(show, w, h, sx, sy), bd)]     # the chunk's last shown frame is its output
+        assert len(got) == len(want)
+        for (eight, bd), full in zip(got, want):
             for a, b in zip(full, eight):
-                assert b.dtype == np.uint8 and np.array_equal((a >> (bd - 8)).astype(np.uint8), b)
+                assert b.dtype == np.uint8 and np.array_equal((np.asarray(a).astype(np.uint16) >> (bd - 8)).astype(np.uint8), b)
             shown += 1
     assert shown > 0
     gpu.close()
     parser.close()
+    ref.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["odd_rt", "hbd10", "scaled_rt", "show_exist"])
+def test_gpu_external_frame_buffers(name):
+    """vp9b_decoder_set_frame_buffer_functions: every shown frame is delivered in an application
+    (page-locked) buffer, bit-exact, and every buffer comes back through release()."""
+    import ctypes as C
+    w, h, chunks = vb.ivf_read(clip_path(name))
+    L = vb.lib_gpu()
+    pool = {}            # tag -> (address, size, in use)
+    stats = {"get": 0, "release": 0}
+
+    def get(min_size):
+        stats["get"] += 1
+        for tag, (addr, size, used) in pool.items():
+            if not used and size >= min_size:
+                pool[tag] = (addr, size, True)
+                return addr, size, tag
+        tag = len(pool) + 1
+        size = max(min_size, 1 << 16)
+        addr = L.vp9gpu_alloc_host(size)
+        assert addr
+        pool[tag] = (addr, size, True)
+        return addr, size, tag
+
+    def release(tag):
+        stats["release"] += 1
+        addr, size, used = pool[tag]
+        assert used
+        pool[tag] = (addr, size, False)
+
+    d = vb.Decoder(0)
+    d.set_frame_buffer_functions(get, release)
+    md5, held = [], []
+    for ch in chunks:
+        d.decode(ch)
+        r = d.get_frame_ext()
+        if r is None:
+            continue
+        held.append(r)
+        if len(held) == 3:       # keep a few frames in flight, as a renderer would
+            out, planes = held.pop(0)
+            d.wait(out.ticket)
+            md5.append(vb.md5_planes(planes))
+            d.release_frame(out)
+    for out, planes in held:
+        d.wait(out.ticket)
+        md5.append(vb.md5_planes(planes))
+        d.release_frame(out)
+    assert md5 == golden_md5(name)
+    assert stats["get"] == stats["release"] == len(md5) and len(pool) <= 4
+    with pytest.raises(vb.VP9BError):      # like libvpx: not after decoding has started
+        d.set_frame_buffer_functions(get, release)
+    d.close()
+    for addr, _, _ in pool.values():
+        L.vp9gpu_free_host(addr)
 
 
 @pytest.mark.gpu

@@ -186,7 +186,7 @@ def main():
     bld = os.path.join(work, "build")
     os.makedirs(bld)
     cfg = ["../libvpx/configure", "--target=generic-gnu", "--disable-vp8", "--disable-vp9-encoder", "--disable-unit-tests",
-           "--disable-docs", "--disable-webm-io", "--disable-libyuv", "--enable-pic", "--extra-cflags=-O2 -w"]
+           "--disable-docs", "--disable-webm-io", "--disable-libyuv", "--enable-pic", "--extra-cflags=-O3 -w"]
     if args.highbitdepth:
         cfg.append("--enable-vp9-highbitdepth")
     subprocess.check_call(cfg, cwd=bld, stdout=subprocess.DEVNULL)
