@@ -58,6 +58,12 @@ int vp9b_parser_parse(vp9b_parser *p, const uint8_t *data, size_t size, const vo
   return VP9B_OK;
 }
 
+int vp9b_parser_set_output_allocator(vp9b_parser *p, void *(*alloc)(void *priv, size_t bytes), void *priv) {
+  if (!p) return VP9B_ERR_INVALID;
+  p->impl.set_output_allocator(alloc, priv);
+  return VP9B_OK;
+}
+
 int vp9b_parser_slot_info(vp9b_parser *p, int slot, uint32_t *width, uint32_t *height,
                           int *bit_depth, int *ss_x, int *ss_y) {
   if (!p || slot < 0 || slot >= VP9B_NUM_SLOTS) return VP9B_ERR_INVALID;

@@ -3,6 +3,7 @@
 // be a superframe; each frame is parsed on the host, its packed buffer is submitted to the GPU
 // stream, and the last frame flagged show_frame becomes the output of the chunk.
 #include <string.h>
+#include <nvtx3/nvToolsExt.h>
 
 #include <new>
 #include <string>
@@ -34,6 +35,8 @@ vp9b_decoder *vp9b_decoder_create(int device) {
     return nullptr;
   }
   vp9gpu_set_validation(d->gpu, 0);   // packed buffers come from vp9b_parser_* of this library
+  // the parser assembles every packed frame directly in the context's page-locked upload ring
+  vp9b_parser_set_output_allocator(d->parser, [](void *priv, size_t bytes) { return vp9gpu_upload_buffer((vp9gpu_ctx *)priv, bytes); }, d->gpu);
   return d;
 }
 
@@ -64,7 +67,9 @@ int vp9b_decoder_decode(vp9b_decoder *d, const uint8_t *data, size_t size) {
     size_t bytes = 0;
     int show = -1;
     // a frame of size 1 with only the marker is a skipped frame in libvpx superframes
+    nvtxRangePushA("vp9b: host parse (bool decoder, modes, tokens, masks)");
     int e = vp9b_parser_parse(d->parser, data + off, sizes[i], &packed, &bytes, &show);
+    nvtxRangePop();
     if (e) {
       d->err = vp9b_parser_last_error(d->parser);
       return e;

@@ -167,7 +167,7 @@ Parser::Parser() {
   memset(ref_sign_bias_, 0, sizeof(ref_sign_bias_));
   memset(ref_desc_, 0, sizeof(ref_desc_));
 }
-Parser::~Parser() {}
+Parser::~Parser() { adapt_worker_.wait(); }
 
 int Parser::fail(int code, const char *msg) {
   err_ = msg;
@@ -2051,15 +2051,26 @@ void Parser::pack() {
     off += (src[i].bytes + 15) & ~(size_t)15;
   }
   h.total_bytes = (uint32_t)off;
-  packed_.resize(off);
-  memcpy(packed_.data(), &h, sizeof(h));
+  // straight into the caller's (page-locked) upload buffer when there is one: no second copy
+  uint8_t *dst = out_alloc_ ? (uint8_t *)out_alloc_(out_priv_, off) : nullptr;
+  if (dst) {
+    ext_out_ = dst;
+    ext_bytes_ = off;
+  } else {
+    packed_.resize(off);
+    dst = packed_.data();
+  }
+  memcpy(dst, &h, sizeof(h));
   for (int i = 0; i < VP9B_SEC_COUNT; i++)
-    if (src[i].bytes) memcpy(packed_.data() + h.sec[i].offset, src[i].p, src[i].bytes);
+    if (src[i].bytes) memcpy(dst + h.sec[i].offset, src[i].p, src[i].bytes);
 }
 
 // vp9_receive_compressed_data + vp9_decode_frame (vp9_decoder.c:407-489, vp9_decodeframe.c:3476-3587)
 int Parser::parse(const uint8_t *data, size_t size) {
+  adapt_worker_.wait();   // the previous frame's backward adaptation
   packed_.clear();
+  ext_out_ = nullptr;
+  ext_bytes_ = 0;
   show_slot_ = -1;
   err_.clear();
   if (!data || size == 0) return fail(VP9B_ERR_INVALID, "empty frame");
@@ -2144,14 +2155,27 @@ int Parser::parse(const uint8_t *data, size_t size) {
       p += tsz;
     }
   }
-  if (!error_res_ && !frame_parallel_) {
-    adapt_coef_probs();
-    if (!(frame_type_ == KEY_FRAME || intra_only_)) {
-      adapt_mode_probs();
-      adapt_mv_probs();
-    }
+  // Backward adaptation (vp9_decodeframe.c:3570-3586) only feeds the NEXT frame's entropy context: it
+  // runs on a side thread while this thread finishes the loop-filter masks, assembles the packed
+  // buffer and hands the frame to the GPU; parse() of the next frame joins it before it touches
+  // the contexts.  (fc_, counts_ and frame_contexts_ are not used by anything below.)
+  {
+    const bool adapt = !error_res_ && !frame_parallel_;
+    const bool inter = !(frame_type_ == KEY_FRAME || intra_only_);
+    auto job = [this, adapt, inter] {
+      if (adapt) {
+        adapt_coef_probs();
+        if (inter) {
+          adapt_mode_probs();
+          adapt_mv_probs();
+        }
+      }
+      if (refresh_frame_context_) frame_contexts_[frame_context_idx_] = fc_;
+    };
+    static const bool inline_adapt = getenv("VP9B_SYNC_ADAPT") != nullptr;
+    if ((adapt || refresh_frame_context_) && !inline_adapt) adapt_worker_.run(job);
+    else job();
   }
-  if (refresh_frame_context_) frame_contexts_[frame_context_idx_] = fc_;
   if (lf_.filter_level) finish_lfm();
   pack();
   // swap_frame_buffers (vp9_decoder.c:334-367) + tail of vp9_receive_compressed_data

@@ -8,6 +8,10 @@
 #include <stddef.h>
 #include <stdint.h>
 
+#include <condition_variable>
+#include <functional>
+#include <mutex>
+#include <thread>
 #include <string>
 #include <vector>
 
@@ -89,14 +93,67 @@ struct SlotInfo {
 class BoolReader;
 struct TileCtx;
 
+// One helper thread per parser, started on first use: runs the previous frame's backward adaptation
+// while the parsing thread packs and submits the frame (creating a thread per frame costs more than
+// the adaptation itself).
+class SideWorker {
+ public:
+  ~SideWorker() {
+    {
+      std::lock_guard<std::mutex> l(m_);
+      quit_ = true;
+    }
+    cv_.notify_all();
+    if (th_.joinable()) th_.join();
+  }
+  void run(std::function<void()> f) {
+    {
+      std::lock_guard<std::mutex> l(m_);
+      job_ = std::move(f);
+      has_ = true;
+      done_ = false;
+    }
+    if (!th_.joinable()) th_ = std::thread([this] { loop(); });
+    cv_.notify_all();
+  }
+  void wait() {
+    std::unique_lock<std::mutex> l(m_);
+    cv_.wait(l, [this] { return done_; });
+  }
+
+ private:
+  void loop() {
+    std::unique_lock<std::mutex> l(m_);
+    for (;;) {
+      cv_.wait(l, [this] { return has_ || quit_; });
+      if (quit_) return;
+      std::function<void()> f = std::move(job_);
+      has_ = false;
+      l.unlock();
+      f();
+      l.lock();
+      done_ = true;
+      cv_.notify_all();
+    }
+  }
+  std::thread th_;
+  std::mutex m_;
+  std::condition_variable cv_;
+  std::function<void()> job_;
+  bool has_ = false, done_ = true, quit_ = false;
+};
+
 class Parser {
  public:
   Parser();
   ~Parser();
   // returns VP9B_OK or error; packed()/packed_bytes() valid until next call
   int parse(const uint8_t *data, size_t size);
-  const uint8_t *packed() const { return packed_.empty() ? nullptr : packed_.data(); }
-  size_t packed_bytes() const { return packed_.size(); }
+  const uint8_t *packed() const { return ext_out_ ? ext_out_ : (packed_.empty() ? nullptr : packed_.data()); }
+  size_t packed_bytes() const { return ext_out_ ? ext_bytes_ : packed_.size(); }
+  // Where pack() assembles the packed buffer: alloc(priv, bytes) returns the destination (e.g. the
+  // page-locked upload buffer of a reconstruction context); nullptr / no allocator: a parser-owned buffer.
+  void set_output_allocator(void *(*alloc)(void *priv, size_t bytes), void *priv) { out_alloc_ = alloc; out_priv_ = priv; }
   int show_slot() const { return show_slot_; }
   const SlotInfo &slot(int i) const { return slots_[i]; }
   const std::string &error() const { return err_; }
@@ -118,6 +175,11 @@ class Parser {
   void pack();
 
   std::string err_;
+  SideWorker adapt_worker_;          // backward adaptation of the previous frame, joined by the next parse()
+  void *(*out_alloc_)(void *, size_t) = nullptr;
+  void *out_priv_ = nullptr;
+  uint8_t *ext_out_ = nullptr;
+  size_t ext_bytes_ = 0;
   // ---- persistent decoder state
   SlotInfo slots_[VP9B_NUM_SLOTS];
   int ref_frame_map_[8];

@@ -10,6 +10,7 @@
 // Integer byte work, HBM/L2 bound -- no tensor cores by design (bit exactness).
 #include <cuda.h>
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -1742,6 +1743,12 @@ struct vp9gpu_ctx {
   bool tables_ready = false;
 };
 
+// NVTX range for the lifetime of a scope (no-op unless a profiler is attached)
+struct NvtxRange {
+  explicit NvtxRange(const char *name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+};
+
 #define CK(call)                                                                       \
   do {                                                                                 \
     cudaError_t e_ = (call);                                                           \
@@ -2035,6 +2042,7 @@ static int launch_batch(vp9gpu_ctx *const *ctxs, FB &B, int n) {
   constexpr unsigned abase = FB::kN == kMaxBatch ? 0u : 16u;   // attribute bits of the small-block instantiations
   vp9gpu_ctx *ctx = ctxs[0];
   cudaStream_t st = ctx->stream;
+  NvtxRange nvtx_range(n == 1 ? "vp9b: reconstruct frame" : "vp9b: reconstruct frame batch");   // visible in nsys / ncu timelines
   const int stop = ctx->stop_stage;
   const bool prof = ctx->profiling;
   int g_expand = 0, g_mcx = 0, g_mcy = 0, g_res = 0, g_ires = 0, g_intra = 0, g_lf = 0;
@@ -2451,18 +2459,10 @@ extern "C" int vp9gpu_frame_submit_device_n(vp9gpu_ctx *ctx, const void *const *
   return 0;
 }
 
-extern "C" int vp9gpu_frame_submit(vp9gpu_ctx *ctx, const void *packed, size_t bytes) {
-  if (!ctx || !packed || bytes < sizeof(vp9b_frame_hdr)) return VP9B_ERR_INVALID;
-  const vp9b_frame_hdr *h = (const vp9b_frame_hdr *)packed;
-  if (h->magic != VP9B_MAGIC || h->total_bytes > bytes) { ctx->err = "corrupt packed buffer"; return VP9B_ERR_INVALID; }
-  if (ctx->validate) {
-    int e = check_header(ctx, h);
-    if (!e) e = validate_records((const uint8_t *)packed, h, ctx->err);
-    if (e) return e;
-  }
+// next entry of the upload ring, at least `bytes` large and no longer in use by the GPU
+static int acquire_upload(vp9gpu_ctx *ctx, size_t bytes) {
   CK(cudaSetDevice(ctx->device));
   const int k = ctx->ring_pos;
-  ctx->ring_pos = (k + 1) % vp9gpu_ctx::kRing;
   CK(cudaEventSynchronize(ctx->ring_ev[k]));  // previous user of this ring entry is done
   if (ctx->ring_bytes[k] < bytes) {
     // grow every ring entry together (allocation synchronises the device: do it rarely)
@@ -2478,11 +2478,58 @@ extern "C" int vp9gpu_frame_submit(vp9gpu_ctx *ctx, const void *packed, size_t b
       ctx->ring_bytes[i] = nb;
     }
   }
-  memcpy(ctx->h_pinned[k], packed, h->total_bytes);
-  CK(cudaMemcpyAsync(ctx->d_packed[k], ctx->h_pinned[k], h->total_bytes, cudaMemcpyHostToDevice, ctx->stream));
+  return 0;
+}
+
+// upload + reconstruct the frame that sits in the current ring entry
+static int submit_ring_entry(vp9gpu_ctx *ctx, size_t bytes) {
+  NvtxRange nvtx_range("vp9b: upload packed frame + submit");
+  const int k = ctx->ring_pos;
+  ctx->ring_pos = (k + 1) % vp9gpu_ctx::kRing;
+  CK(cudaMemcpyAsync(ctx->d_packed[k], ctx->h_pinned[k], bytes, cudaMemcpyHostToDevice, ctx->stream));
   const int e = submit_device(ctx, (const uint8_t *)ctx->d_packed[k], (const vp9b_frame_hdr *)ctx->h_pinned[k]);
   cudaEventRecord(ctx->ring_ev[k], ctx->stream);
   return e;
+}
+
+static int check_host_packed(vp9gpu_ctx *ctx, const void *packed, size_t bytes) {
+  const vp9b_frame_hdr *h = (const vp9b_frame_hdr *)packed;
+  if (h->magic != VP9B_MAGIC || h->total_bytes > bytes) { ctx->err = "corrupt packed buffer"; return VP9B_ERR_INVALID; }
+  if (ctx->validate) {
+    int e = check_header(ctx, h);
+    if (!e) e = validate_records((const uint8_t *)packed, h, ctx->err);
+    if (e) return e;
+  }
+  return 0;
+}
+
+extern "C" int vp9gpu_frame_submit(vp9gpu_ctx *ctx, const void *packed, size_t bytes) {
+  if (!ctx || !packed || bytes < sizeof(vp9b_frame_hdr)) return VP9B_ERR_INVALID;
+  int e = check_host_packed(ctx, packed, bytes);
+  if (e) return e;
+  const vp9b_frame_hdr *h = (const vp9b_frame_hdr *)packed;
+  if (packed == ctx->h_pinned[ctx->ring_pos]) return submit_ring_entry(ctx, h->total_bytes);   // built in place
+  e = acquire_upload(ctx, bytes);
+  if (e) return e;
+  memcpy(ctx->h_pinned[ctx->ring_pos], packed, h->total_bytes);
+  return submit_ring_entry(ctx, h->total_bytes);
+}
+
+extern "C" void *vp9gpu_upload_buffer(vp9gpu_ctx *ctx, size_t bytes) {
+  if (!ctx || acquire_upload(ctx, bytes)) return nullptr;
+  return ctx->h_pinned[ctx->ring_pos];
+}
+
+extern "C" int vp9gpu_frame_submit_staged(vp9gpu_ctx *ctx, const void *packed, size_t bytes) {
+  if (!ctx || !packed || bytes < sizeof(vp9b_frame_hdr)) return VP9B_ERR_INVALID;
+  if (packed != ctx->h_pinned[ctx->ring_pos] || bytes > ctx->ring_bytes[ctx->ring_pos]) {
+    ctx->err = "vp9gpu_frame_submit_staged: not the buffer handed out by vp9gpu_upload_buffer";
+    return VP9B_ERR_INVALID;
+  }
+  const int e = check_host_packed(ctx, packed, bytes);
+  if (e) return e;
+  CK(cudaSetDevice(ctx->device));
+  return submit_ring_entry(ctx, ((const vp9b_frame_hdr *)packed)->total_bytes);
 }
 
 extern "C" int vp9gpu_upload_packed(vp9gpu_ctx *ctx, const void *packed, size_t bytes, void **d_packed) {

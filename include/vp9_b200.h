@@ -145,6 +145,13 @@ const char *vp9gpu_last_error(vp9gpu_ctx *ctx);
 /* Reconstruct one frame from a packed buffer in HOST memory (copied H2D asynchronously from an
  * internal pinned ring) -- enqueues upload + all kernels on the ctx stream and returns. */
 int vp9gpu_frame_submit(vp9gpu_ctx *ctx, const void *packed, size_t bytes);
+/* The same without the staging copy: vp9gpu_upload_buffer() hands out the next page-locked upload
+ * buffer of the ctx (at least `bytes` large; valid until the matching submit), the caller builds the
+ * packed frame in it, vp9gpu_frame_submit_staged() uploads and reconstructs it.  One buffer can be
+ * outstanding per ctx; asking again before submitting returns the same buffer (grown if needed,
+ * contents not preserved). */
+void *vp9gpu_upload_buffer(vp9gpu_ctx *ctx, size_t bytes);
+int vp9gpu_frame_submit_staged(vp9gpu_ctx *ctx, const void *packed, size_t bytes);
 /* Same, but the packed buffer already lives in DEVICE memory (recon-only replay, bench). */
 int vp9gpu_frame_submit_device(vp9gpu_ctx *ctx, const void *d_packed, const vp9b_frame_hdr *hdr);
 /* The same for n device-resident frames in decode order with one call (replay / transcoding
@@ -254,6 +261,11 @@ const char *vp9b_parser_last_error(vp9b_parser *p);
  * (-1: nothing to show).  (role of vp9_receive_compressed_data, vp9_decoder.c:407) */
 int vp9b_parser_parse(vp9b_parser *p, const uint8_t *data, size_t size, const void **packed,
                       size_t *bytes, int *show_slot);
+/* Where the packed buffer is assembled: alloc(priv, bytes) returns the destination, e.g. the
+ * page-locked upload buffer of a reconstruction context (vp9gpu_upload_buffer) so that the frame is
+ * packed straight into the memory the H2D copy reads.  alloc == NULL (default) or a NULL return:
+ * a parser-owned buffer. */
+int vp9b_parser_set_output_allocator(vp9b_parser *p, void *(*alloc)(void *priv, size_t bytes), void *priv);
 /* Geometry of a slot as the parser last set it up. */
 int vp9b_parser_slot_info(vp9b_parser *p, int slot, uint32_t *width, uint32_t *height,
                           int *bit_depth, int *ss_x, int *ss_y);
