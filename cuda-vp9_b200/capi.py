@@ -177,6 +177,12 @@ def plane_shapes(width, height, ss_x, ss_y):
 class HostParser:
     """Bitstream -> packed per-frame buffer (include/vp9_b200.h section 2)."""
 
+    def set_threads(self, n):
+        """Tile-column worker threads per frame (vp9b_parser_set_threads)."""
+        self.L.vp9b_parser_set_threads.argtypes = [C.c_void_p, C.c_int]
+        if self.L.vp9b_parser_set_threads(self.p, int(n)):
+            raise VP9BError(-1, "bad thread count")
+
     def __init__(self, L=None):
         self.L = L or lib_host()
         self.p = self.L.vp9b_parser_create()

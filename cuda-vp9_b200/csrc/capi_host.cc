@@ -1,5 +1,6 @@
 // C ABI, host-only part: parser + superframe splitter (include/vp9_b200.h section 2).
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <exception>
@@ -24,7 +25,12 @@ vp9b_parser *vp9b_parser_create(void) {
     return nullptr;
   }
 #endif
-  return new (std::nothrow) vp9b_parser();
+  vp9b_parser *p = new (std::nothrow) vp9b_parser();
+  if (p) {
+    const char *t = getenv("VP9B_PARSE_THREADS");     // default for every parser of the process
+    if (t && atoi(t) > 0) p->impl.set_threads(atoi(t));
+  }
+  return p;
 }
 
 void vp9b_parser_destroy(vp9b_parser *p) { delete p; }
@@ -55,6 +61,12 @@ int vp9b_parser_parse(vp9b_parser *p, const uint8_t *data, size_t size, const vo
   *packed = p->impl.packed();
   *bytes = p->impl.packed_bytes();
   *show_slot = p->impl.show_slot();
+  return VP9B_OK;
+}
+
+int vp9b_parser_set_threads(vp9b_parser *p, int threads) {
+  if (!p || threads < 1) return VP9B_ERR_INVALID;
+  p->impl.set_threads(threads);
   return VP9B_OK;
 }
 

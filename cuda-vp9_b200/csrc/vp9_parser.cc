@@ -651,6 +651,7 @@ void Parser::loop_filter_frame_init() {
 // Per-tile decoding context (role of TileWorkerData + MACROBLOCKD).
 struct TileCtx {
   Parser *P;
+  TileOut *O;      // what this tile column's worker appends to (merged by Parser::pack)
   BoolReader r;
   int mi_row_start, mi_row_end, mi_col_start, mi_col_end;
   uint8_t left_ctx[3][16];
@@ -707,11 +708,11 @@ void TileCtx::decode_tile() {
       const int sb = (r0 >> 3) * P->sb_cols_ + (c0 >> 3);
       const int nsb = P->sb_cols_ * P->sb_rows_;
       for (int p = 0; p < 3; p++)
-        P->out_sb_intra_[p * nsb + sb].start = (uint32_t)P->out_txb_intra_[p].size();
+        P->out_sb_intra_[p * nsb + sb].start = (uint32_t)O->txb_intra[p].size();   // index inside this worker's list
       decode_partition(r0, c0, BLOCK_64X64, 4);
       for (int p = 0; p < 3; p++)
         P->out_sb_intra_[p * nsb + sb].count =
-            (uint32_t)P->out_txb_intra_[p].size() - P->out_sb_intra_[p * nsb + sb].start;
+            (uint32_t)O->txb_intra[p].size() - P->out_sb_intra_[p * nsb + sb].start;
       if (corrupted) return;
     }
   }
@@ -736,7 +737,7 @@ void TileCtx::decode_partition(int row, int col, int bsize, int n4x4_l2) {
   else if (!has_rows && has_cols) p = r.read(probs[1]) ? PARTITION_SPLIT : PARTITION_HORZ;
   else if (has_rows && !has_cols) p = r.read(probs[2]) ? PARTITION_SPLIT : PARTITION_VERT;
   else p = PARTITION_SPLIT;
-  if (P->do_counts_) ++P->counts_.partition[ctx][p];
+  if (P->do_counts_) ++O->counts.partition[ctx][p];
   const int subsize = kSubsize[p * 13 + bsize];
   if (!hbs) {
     bmode_blocks_wl = 1 >> !!(p & PARTITION_VERT);
@@ -819,7 +820,7 @@ int TileCtx::read_skip(int segment_id) {
   if (seg_active(segment_id, SEG_LVL_SKIP)) return 1;
   const int ctx = (above_mi ? above_mi->skip : 0) + (left_mi ? left_mi->skip : 0);
   const int skip = r.read(P->fc_.skip[ctx]);
-  if (P->do_counts_) ++P->counts_.skip[ctx][skip];
+  if (P->do_counts_) ++O->counts.skip[ctx][skip];
   return skip;
 }
 
@@ -842,9 +843,9 @@ int TileCtx::read_tx_size(int allow_select) {
       if (tx != TX_8X8 && max_tx >= TX_32X32) tx += r.read(probs[2]);
     }
     if (P->do_counts_) {
-      if (max_tx == TX_8X8) ++P->counts_.tx8[ctx][tx];
-      else if (max_tx == TX_16X16) ++P->counts_.tx16[ctx][tx];
-      else ++P->counts_.tx32[ctx][tx];
+      if (max_tx == TX_8X8) ++O->counts.tx8[ctx][tx];
+      else if (max_tx == TX_16X16) ++O->counts.tx16[ctx][tx];
+      else ++O->counts.tx32[ctx][tx];
     }
     return tx;
   }
@@ -896,7 +897,7 @@ void TileCtx::read_intra_block_mode_info() {
   const int bsize = mi->sb_type;
   auto read_y = [&](int size_group) -> uint8_t {
     const int m = r.read_tree(kIntraModeTree, P->fc_.y_mode[size_group]);
-    if (P->do_counts_) ++P->counts_.y_mode[size_group][m];
+    if (P->do_counts_) ++O->counts.y_mode[size_group][m];
     return (uint8_t)m;
   };
   switch (bsize) {
@@ -917,7 +918,7 @@ void TileCtx::read_intra_block_mode_info() {
       mi->bmode[0] = mi->bmode[1] = mi->bmode[2] = mi->bmode[3] = mi->mode;
   }
   const int uv = r.read_tree(kIntraModeTree, P->fc_.uv_mode[mi->mode]);
-  if (P->do_counts_) ++P->counts_.uv_mode[mi->mode][uv];
+  if (P->do_counts_) ++O->counts.uv_mode[mi->mode][uv];
   mi->uv_mode = (uint8_t)uv;
   mi->interp_filter = SWITCHABLE_FILTERS;
   mi->ref_frame[0] = INTRA_FRAME;
@@ -952,7 +953,7 @@ void TileCtx::read_ref_frames(int8_t ref_frame[2]) {
       ctx = 1;
     }
     mode = r.read(fc.comp_inter[ctx]);
-    if (P->do_counts_) ++P->counts_.comp_inter[ctx][mode];
+    if (P->do_counts_) ++O->counts.comp_inter[ctx][mode];
   } else {
     mode = P->reference_mode_;
   }
@@ -1000,7 +1001,7 @@ void TileCtx::read_ref_frames(int8_t ref_frame[2]) {
       ctx = 2;
     }
     const int bit = r.read(fc.comp_ref[ctx]);
-    if (P->do_counts_) ++P->counts_.comp_ref[ctx][bit];
+    if (P->do_counts_) ++O->counts.comp_ref[ctx][bit];
     ref_frame[fix_ref_idx] = (int8_t)fixed;
     ref_frame[!fix_ref_idx] = (int8_t)P->comp_var_ref_[bit];
   } else {
@@ -1036,7 +1037,7 @@ void TileCtx::read_ref_frames(int8_t ref_frame[2]) {
       ctx0 = 2;
     }
     const int bit0 = r.read(fc.single_ref[ctx0][0]);
-    if (P->do_counts_) ++P->counts_.single_ref[ctx0][0][bit0];
+    if (P->do_counts_) ++O->counts.single_ref[ctx0][0][bit0];
     if (bit0) {
       int ctx1;  // vp9_get_pred_context_single_ref_p2
       if (has_above && has_left) {
@@ -1085,7 +1086,7 @@ void TileCtx::read_ref_frames(int8_t ref_frame[2]) {
         ctx1 = 2;
       }
       const int bit1 = r.read(fc.single_ref[ctx1][1]);
-      if (P->do_counts_) ++P->counts_.single_ref[ctx1][1][bit1];
+      if (P->do_counts_) ++O->counts.single_ref[ctx1][1][bit1];
       ref_frame[0] = bit1 ? ALTREF_FRAME : GOLDEN_FRAME;
     } else {
       ref_frame[0] = LAST_FRAME;
@@ -1152,9 +1153,9 @@ void TileCtx::read_mv(Mv *mv, const Mv *ref) {
   if (P->do_counts_) {
     const int j = (drow == 0) ? (dcol == 0 ? MV_JOINT_ZERO : MV_JOINT_HNZVZ)
                               : (dcol == 0 ? MV_JOINT_HZVNZ : MV_JOINT_HNZVNZ);
-    ++P->counts_.mv_joints[j];
-    if (drow) inc_mv_component(drow, P->counts_.mvc[0]);
-    if (dcol) inc_mv_component(dcol, P->counts_.mvc[1]);
+    ++O->counts.mv_joints[j];
+    if (drow) inc_mv_component(drow, O->counts.mvc[0]);
+    if (dcol) inc_mv_component(dcol, O->counts.mvc[1]);
   }
   mv->row = (int16_t)(ref->row + drow);
   mv->col = (int16_t)(ref->col + dcol);
@@ -1366,7 +1367,7 @@ void TileCtx::read_inter_block_mode_info() {
   const int inter_mode_ctx = get_mode_context(search);
   auto read_inter_mode = [&]() -> int {
     const int m = r.read_tree(kInterModeTree, P->fc_.inter_mode[inter_mode_ctx]);
-    if (P->do_counts_) ++P->counts_.inter_mode[inter_mode_ctx][m];
+    if (P->do_counts_) ++O->counts.inter_mode[inter_mode_ctx][m];
     return NEARESTMV + m;
   };
   if (seg_active(mi->segment_id, SEG_LVL_SKIP)) {
@@ -1388,7 +1389,7 @@ void TileCtx::read_inter_block_mode_info() {
     else if (above_type == SWITCHABLE_FILTERS) ctx = left_type;
     else ctx = SWITCHABLE_FILTERS;
     const int t = r.read_tree(kSwitchableInterpTree, P->fc_.switchable_interp[ctx]);
-    if (P->do_counts_) ++P->counts_.switchable_interp[ctx][t];
+    if (P->do_counts_) ++O->counts.switchable_interp[ctx][t];
     mi->interp_filter = (uint8_t)t;
   } else {
     mi->interp_filter = (uint8_t)P->interp_filter_;
@@ -1459,7 +1460,7 @@ void TileCtx::read_inter_frame_mode_info() {
       ctx = 0;
     }
     inter_block = r.read(P->fc_.intra_inter[ctx]);
-    if (P->do_counts_) ++P->counts_.intra_inter[ctx][inter_block];
+    if (P->do_counts_) ++O->counts.intra_inter[ctx][inter_block];
   }
   mi->tx_size = (uint8_t)read_tx_size(!mi->skip || !inter_block);
   if (inter_block) read_inter_block_mode_info();
@@ -1505,8 +1506,8 @@ int TileCtx::decode_block_tokens(int plane, int x, int y, int tx_size, int tx_ty
   const int ref = is_inter(mi);
   const int max_eob = 16 << (tx_size << 1);
   const uint8_t(*coef_probs)[6][3] = P->fc_.coef[tx_size][type][ref];
-  uint32_t(*coef_counts)[6][4] = P->counts_.coef[tx_size][type][ref];
-  uint32_t(*eob_branch)[6] = P->counts_.eob_branch[tx_size][type][ref];
+  uint32_t(*coef_counts)[6][4] = O->counts.coef[tx_size][type][ref];
+  uint32_t(*eob_branch)[6] = O->counts.eob_branch[tx_size][type][ref];
   const bool counts = P->do_counts_;
   const uint8_t *band_translate = tx_size == TX_4X4 ? kCoefBand4x4 : kCoefBand8x8Plus;
   const int dq_shift = (tx_size == TX_32X32);
@@ -1518,14 +1519,14 @@ int TileCtx::decode_block_tokens(int plane, int x, int y, int tx_size, int tx_ty
   // coefficient stream: grow geometrically, write through raw pointers (no per-block zero fill)
   size_t base;
   if (hbd) {
-    base = P->n_coef_;
-    if (P->out_coef32_.size() < base + max_eob) P->out_coef32_.resize(std::max(P->out_coef32_.size() * 2, base + 65536));
+    base = O->n_coef;
+    if (O->coef32.size() < base + max_eob) O->coef32.resize(std::max(O->coef32.size() * 2, base + 65536));
   } else {
-    base = P->n_coef_;
-    if (P->out_coef16_.size() < base + max_eob) P->out_coef16_.resize(std::max(P->out_coef16_.size() * 2, base + 65536));
+    base = O->n_coef;
+    if (O->coef16.size() < base + max_eob) O->coef16.resize(std::max(O->coef16.size() * 2, base + 65536));
   }
-  int16_t *o16 = hbd ? nullptr : &P->out_coef16_[base];
-  int32_t *o32 = hbd ? &P->out_coef32_[base] : nullptr;
+  int16_t *o16 = hbd ? nullptr : &O->coef16[base];
+  int32_t *o32 = hbd ? &O->coef32[base] : nullptr;
   BoolReader r = this->r;  // local copy: value/range/count live in registers for the whole block
   int c = 0;
   int dqv = dq[0];
@@ -1601,7 +1602,7 @@ int TileCtx::decode_block_tokens(int plane, int x, int y, int tx_size, int tx_ty
   }
   const int eob = c;
   this->r = r;
-  P->n_coef_ = base + eob;
+  O->n_coef = base + eob;
   *coef_off = (uint32_t)base;
   const uint8_t flag = eob > 0;
   for (int i = 0; i < n; i++) {
@@ -1659,8 +1660,8 @@ void TileCtx::residual_and_record() {
           t.coef_off = off;
           eobtotal += eob;
         }
-        if (!inter) P->out_txb_intra_[plane].push_back(t);
-        else if (t.eob > 0) P->out_txb_inter_[tx_size].push_back(t);
+        if (!inter) O->txb_intra[plane].push_back(t);
+        else if (t.eob > 0) O->txb_inter[tx_size].push_back(t);
       }
   }
   if (inter && !mi->skip && !less8x8 && eobtotal == 0) mi->skip = 1;  // skip loopfilter
@@ -1719,8 +1720,9 @@ void TileCtx::decode_block(int row, int col, int bsize, int bwl_, int bhl_) {
   mb_to_right_edge = ((P->mi_cols_ - bw - col) * 8) * 8;
   above_mi = row != 0 ? at(row - 1, col) : nullptr;
   left_mi = col > mi_col_start ? at(row, col - 1) : nullptr;
-  const uint32_t bidx = (uint32_t)P->blocks_.size();
-  P->blocks_.emplace_back();
+  // the worker's own range of the block array: at most one block per 8x8 cell of its tile columns
+  const uint32_t bidx = O->block_next++;
+  P->blocks_[bidx] = BlockInfo();
   // NOTE: emplace_back may reallocate; refresh neighbour pointers from indices afterwards
   above_mi = row != 0 ? at(row - 1, col) : nullptr;
   left_mi = col > mi_col_start ? at(row, col - 1) : nullptr;
@@ -1769,8 +1771,8 @@ void TileCtx::decode_block(int row, int col, int bsize, int bwl_, int bhl_) {
           s.chroma[rf][0] = (int16_t)((sr < 0 ? sr - 2 : sr + 2) / 4);
           s.chroma[rf][1] = (int16_t)((sc < 0 ? sc - 2 : sc + 2) / 4);
         }
-        const uint32_t idx = (uint32_t)P->out_submv_.size();
-        P->out_submv_.push_back(s);
+        const uint32_t idx = (uint32_t)O->submv.size();   // worker-local; rebased by pack()
+        O->submv.push_back(s);
         memcpy(&b.mv[0][0], &idx, 4);
       } else {
         for (int rf = 0; rf < 2; rf++) {
@@ -1781,11 +1783,11 @@ void TileCtx::decode_block(int row, int col, int bsize, int bwl_, int bhl_) {
       for (int p = 0; p < 3; p++) {
         const int ss_x = p ? P->ss_x_ : 0, ss_y = p ? P->ss_y_ : 0;
         const uint32_t px = (uint32_t)((x_mis * 8) >> ss_x) * ((y_mis * 8) >> ss_y);
-        P->n_inter_px_[p] += px;
-        if (b.ref1) P->n_compound_px_[p] += px;
+        O->n_inter_px[p] += px;
+        if (b.ref1) O->n_compound_px[p] += px;
       }
     }
-    P->out_blocks_.push_back(b);
+    O->blocks.push_back(b);
   }
   residual_and_record();
   if (r.has_error()) corrupted = true;
@@ -2009,10 +2011,6 @@ void Parser::pack() {
   h.dst_slot = new_slot_;
   for (int i = 0; i < 3; i++) h.ref[i] = ref_desc_[i];
   h.frame_index = frame_index_;
-  for (int p = 0; p < 3; p++) {
-    h.n_inter_px[p] = n_inter_px_[p];
-    h.n_compound_px[p] = n_compound_px_[p];
-  }
   // update_sharpness (vp9_loopfilter.c:212-231)
   for (int lvl = 0; lvl < 64; lvl++) {
     const int sh = lf_.sharpness_level;
@@ -2022,33 +2020,49 @@ void Parser::pack() {
     h.lf_lim[lvl] = (uint8_t)lim;
     h.lf_mblim[lvl] = (uint8_t)(2 * (lvl + 2) + lim);
   }
-  size_t off = (sizeof(h) + 15) & ~(size_t)15;
-  struct Src { const void *p; size_t bytes; uint32_t count; };
-  Src src[VP9B_SEC_COUNT];
-  memset(src, 0, sizeof(src));
-  auto set = [&](int id, const void *p, size_t elem, size_t n) {
-    src[id].p = p;
-    src[id].bytes = elem * n;
-    src[id].count = (uint32_t)n;
-  };
-  set(VP9B_SEC_BLOCKS, out_blocks_.data(), sizeof(vp9b_block), out_blocks_.size());
-  set(VP9B_SEC_SUBMV, out_submv_.data(), sizeof(vp9b_submv), out_submv_.size());
-  out_txb_inter_all_.clear();
-  for (int i = 0; i < 4; i++) {
-    h.n_txb_inter_size[i] = (uint32_t)out_txb_inter_[i].size();
-    out_txb_inter_all_.insert(out_txb_inter_all_.end(), out_txb_inter_[i].begin(), out_txb_inter_[i].end());
+  // Sections are concatenations of the tile-column workers' lists; worker-local indices (sub-8x8 MV
+  // table, coefficient offsets, per-superblock intra ranges) are rebased while copying.
+  const int nw = n_workers_;
+  size_t n_blocks = 0, n_submv = 0, n_inter[4] = { 0, 0, 0, 0 }, n_intra[3] = { 0, 0, 0 }, n_coef = 0;
+  std::vector<size_t> submv_base(nw), coef_base(nw), intra_base(3 * nw);
+  for (int w = 0; w < nw; w++) {
+    const TileOut &o = *outs_[w];
+    submv_base[w] = n_submv;
+    coef_base[w] = n_coef;
+    n_blocks += o.blocks.size();
+    n_submv += o.submv.size();
+    n_coef += o.n_coef;
+    for (int i = 0; i < 4; i++) n_inter[i] += o.txb_inter[i].size();
+    for (int p = 0; p < 3; p++) {
+      intra_base[p * nw + w] = n_intra[p];
+      n_intra[p] += o.txb_intra[p].size();
+    }
+    for (int p = 0; p < 3; p++) {
+      h.n_inter_px[p] += o.n_inter_px[p];
+      h.n_compound_px[p] += o.n_compound_px[p];
+    }
   }
-  set(VP9B_SEC_TXB_INTER, out_txb_inter_all_.data(), sizeof(vp9b_txb), out_txb_inter_all_.size());
-  for (int p = 0; p < 3; p++)
-    set(VP9B_SEC_TXB_INTRA_Y + p, out_txb_intra_[p].data(), sizeof(vp9b_txb), out_txb_intra_[p].size());
-  set(VP9B_SEC_SB_INTRA, out_sb_intra_.data(), sizeof(vp9b_sbrange), out_sb_intra_.size());
-  if (bit_depth_ > 8) set(VP9B_SEC_COEF, out_coef32_.data(), 4, n_coef_);
-  else set(VP9B_SEC_COEF, out_coef16_.data(), 2, n_coef_);
-  if (lf_.filter_level) set(VP9B_SEC_LFM, out_lfm_.data(), sizeof(vp9b_lfm), out_lfm_.size());
+  const size_t coef_elem = bit_depth_ > 8 ? 4 : 2;
+  size_t count[VP9B_SEC_COUNT], bytes[VP9B_SEC_COUNT];
+  memset(count, 0, sizeof(count));
+  memset(bytes, 0, sizeof(bytes));
+  auto set = [&](int id, size_t elem, size_t n) {
+    count[id] = n;
+    bytes[id] = elem * n;
+  };
+  set(VP9B_SEC_BLOCKS, sizeof(vp9b_block), n_blocks);
+  set(VP9B_SEC_SUBMV, sizeof(vp9b_submv), n_submv);
+  set(VP9B_SEC_TXB_INTER, sizeof(vp9b_txb), n_inter[0] + n_inter[1] + n_inter[2] + n_inter[3]);
+  for (int i = 0; i < 4; i++) h.n_txb_inter_size[i] = (uint32_t)n_inter[i];
+  for (int p = 0; p < 3; p++) set(VP9B_SEC_TXB_INTRA_Y + p, sizeof(vp9b_txb), n_intra[p]);
+  set(VP9B_SEC_SB_INTRA, sizeof(vp9b_sbrange), out_sb_intra_.size());
+  set(VP9B_SEC_COEF, coef_elem, n_coef);
+  if (lf_.filter_level) set(VP9B_SEC_LFM, sizeof(vp9b_lfm), out_lfm_.size());
+  size_t off = (sizeof(h) + 15) & ~(size_t)15;
   for (int i = 0; i < VP9B_SEC_COUNT; i++) {
     h.sec[i].offset = (uint32_t)off;
-    h.sec[i].count = src[i].count;
-    off += (src[i].bytes + 15) & ~(size_t)15;
+    h.sec[i].count = (uint32_t)count[i];
+    off += (bytes[i] + 15) & ~(size_t)15;
   }
   h.total_bytes = (uint32_t)off;
   // straight into the caller's (page-locked) upload buffer when there is one: no second copy
@@ -2061,8 +2075,78 @@ void Parser::pack() {
     dst = packed_.data();
   }
   memcpy(dst, &h, sizeof(h));
-  for (int i = 0; i < VP9B_SEC_COUNT; i++)
-    if (src[i].bytes) memcpy(dst + h.sec[i].offset, src[i].p, src[i].bytes);
+  auto copy_txb = [](vp9b_txb *d, const std::vector<vp9b_txb> &v, size_t cbase) {
+    memcpy(d, v.data(), v.size() * sizeof(vp9b_txb));
+    if (cbase)
+      for (size_t i = 0; i < v.size(); i++) d[i].coef_off += (uint32_t)cbase;
+    return d + v.size();
+  };
+  {
+    vp9b_block *db = (vp9b_block *)(dst + h.sec[VP9B_SEC_BLOCKS].offset);
+    vp9b_submv *ds = (vp9b_submv *)(dst + h.sec[VP9B_SEC_SUBMV].offset);
+    uint8_t *dc = dst + h.sec[VP9B_SEC_COEF].offset;
+    vp9b_txb *di[3];
+    for (int p = 0; p < 3; p++) di[p] = (vp9b_txb *)(dst + h.sec[VP9B_SEC_TXB_INTRA_Y + p].offset);
+    for (int w = 0; w < nw; w++) {
+      const TileOut &o = *outs_[w];
+      memcpy(db, o.blocks.data(), o.blocks.size() * sizeof(vp9b_block));
+      if (submv_base[w])
+        for (size_t i = 0; i < o.blocks.size(); i++)
+          if (db[i].ref0 && db[i].bsize < 3) {
+            uint32_t idx;
+            memcpy(&idx, &db[i].mv[0][0], 4);
+            idx += (uint32_t)submv_base[w];
+            memcpy(&db[i].mv[0][0], &idx, 4);
+          }
+      db += o.blocks.size();
+      memcpy(ds, o.submv.data(), o.submv.size() * sizeof(vp9b_submv));
+      ds += o.submv.size();
+      memcpy(dc, bit_depth_ > 8 ? (const void *)o.coef32.data() : (const void *)o.coef16.data(), o.n_coef * coef_elem);
+      dc += o.n_coef * coef_elem;
+      for (int p = 0; p < 3; p++) di[p] = copy_txb(di[p], o.txb_intra[p], coef_base[w]);
+    }
+    vp9b_txb *dt = (vp9b_txb *)(dst + h.sec[VP9B_SEC_TXB_INTER].offset);
+    for (int i = 0; i < 4; i++)          // grouped by transform size
+      for (int w = 0; w < nw; w++) dt = copy_txb(dt, outs_[w]->txb_inter[i], coef_base[w]);
+    // per-superblock intra ranges: rebase to the owning worker's position in the merged lists
+    vp9b_sbrange *dr = (vp9b_sbrange *)(dst + h.sec[VP9B_SEC_SB_INTRA].offset);
+    memcpy(dr, out_sb_intra_.data(), out_sb_intra_.size() * sizeof(vp9b_sbrange));
+    if (nw > 1) {
+      const int nsb = sb_cols_ * sb_rows_;
+      for (int p = 0; p < 3; p++)
+        for (int sbr = 0; sbr < sb_rows_; sbr++)
+          for (int sbc = 0; sbc < sb_cols_; sbc++)
+            dr[p * nsb + sbr * sb_cols_ + sbc].start += (uint32_t)intra_base[p * nw + sb_worker_[sbc]];
+    }
+    if (lf_.filter_level) memcpy(dst + h.sec[VP9B_SEC_LFM].offset, out_lfm_.data(), out_lfm_.size() * sizeof(vp9b_lfm));
+  }
+}
+
+// first mi column / row of tile idx (get_tile_offset, vp9_tile_common.c:20-27)
+static inline int tile_col_offset(int idx, int mis, int log2) {
+  const int sb = (mis + 7) >> 3;
+  const int off = ((idx * sb) >> log2) << 3;
+  return std::min(off, mis);
+}
+
+// All tiles of a group of tile columns, column by column, top to bottom (role of tile_worker_hook,
+// vp9_decodeframe.c:2663-2752).  The block array range of a tile column starts at
+// mi_rows * (first mi column): at most one BlockInfo per 8x8 cell, so ranges never overlap.
+void Parser::run_tile_column(TileOut *o, const TileJob *jobs, int n_jobs) {
+  for (int i = 0; i < n_jobs; i++) {
+    const TileJob &j = jobs[i];
+    TileCtx t;
+    t.P = this;
+    t.O = o;
+    t.mi_row_start = tile_col_offset(j.tr, mi_rows_, log2_tile_rows_);
+    t.mi_row_end = tile_col_offset(j.tr + 1, mi_rows_, log2_tile_rows_);
+    t.mi_col_start = tile_col_offset(j.tc, mi_cols_, log2_tile_cols_);
+    t.mi_col_end = tile_col_offset(j.tc + 1, mi_cols_, log2_tile_cols_);
+    if (j.tr == 0) o->block_next = (uint32_t)((size_t)mi_rows_ * t.mi_col_start);
+    if (t.r.init(j.data, j.size)) { o->bad_marker = 1; return; }
+    t.decode_tile();
+    if (t.corrupted) { o->corrupted = true; return; }
+  }
 }
 
 // vp9_receive_compressed_data + vp9_decode_frame (vp9_decoder.c:407-489, vp9_decodeframe.c:3476-3587)
@@ -2102,13 +2186,7 @@ int Parser::parse(const uint8_t *data, size_t size) {
   const int aligned_cols = sb_cols_ * 8;
   for (int p = 0; p < 3; p++) above_ctx_[p].assign((size_t)aligned_cols * 2 + 16, 0);
   above_seg_ctx_.assign(aligned_cols + 8, 0);
-  blocks_.clear();
-  blocks_.reserve((size_t)mi_cols_ * mi_rows_ + 64);
-  out_blocks_.clear();
-  out_submv_.clear();
-  for (int i = 0; i < 4; i++) out_txb_inter_[i].clear();
-  for (int p = 0; p < 3; p++) out_txb_intra_[p].clear();
-  n_coef_ = 0;
+  if (blocks_.size() < (size_t)mi_cols_ * mi_rows_ + 64) blocks_.resize((size_t)mi_cols_ * mi_rows_ + 64);
   out_sb_intra_.assign((size_t)3 * sb_cols_ * sb_rows_, vp9b_sbrange{ 0, 0 });
   out_lfm_.clear();
   if (lf_.filter_level) {
@@ -2116,17 +2194,13 @@ int Parser::parse(const uint8_t *data, size_t size) {
     memset(&z, 0, sizeof(z));
     out_lfm_.assign((size_t)sb_cols_ * sb_rows_, z);
   }
-  memset(n_inter_px_, 0, sizeof(n_inter_px_));
-  memset(n_compound_px_, 0, sizeof(n_compound_px_));
-  // tiles (get_tile_buffers + decode_tiles, vp9_decodeframe.c:1877-1925, 2303-2430)
+  // tiles (get_tile_buffers + decode_tiles, vp9_decodeframe.c:1877-1925, 2303-2430): the sizes first,
+  // then one worker per group of tile columns -- tile columns share nothing but the previous frame's
+  // motion vectors (decode_tiles_mt, :2919-3047); a column's tiles are parsed top to bottom.
   const uint8_t *p = data + hdr_bytes + first_partition_size;
   const uint8_t *end = data + size;
   const int tile_rows = 1 << log2_tile_rows_, tile_cols = 1 << log2_tile_cols_;
-  auto tile_offset = [](int idx, int mis, int log2) {
-    const int sb = (mis + 7) >> 3;
-    const int off = ((idx * sb) >> log2) << 3;
-    return std::min(off, mis);
-  };
+  std::vector<TileJob> jobs((size_t)tile_rows * tile_cols);     // [tc][tr]
   for (int tr = 0; tr < tile_rows; tr++) {
     for (int tc = 0; tc < tile_cols; tc++) {
       const bool last = (tr == tile_rows - 1) && (tc == tile_cols - 1);
@@ -2140,19 +2214,51 @@ int Parser::parse(const uint8_t *data, size_t size) {
         tsz = end - p;
       }
       if (tsz == 0) return fail(VP9B_ERR_CORRUPT, "empty tile");
-      TileCtx t;
-      t.P = this;
-      t.mi_row_start = tile_offset(tr, mi_rows_, log2_tile_rows_);
-      t.mi_row_end = tile_offset(tr + 1, mi_rows_, log2_tile_rows_);
-      t.mi_col_start = tile_offset(tc, mi_cols_, log2_tile_cols_);
-      t.mi_col_end = tile_offset(tc + 1, mi_cols_, log2_tile_cols_);
-      if (t.r.init(p, tsz)) return fail(VP9B_ERR_CORRUPT, "tile marker bit set");
-      t.decode_tile();
-      if (t.corrupted) return fail(VP9B_ERR_CORRUPT, "corrupt tile data");
-      if (getenv("VP9B_DEBUG"))
-        fprintf(stderr, "[vp9b] frame %u tile %d,%d size %zu unread %ld blocks %zu\n", frame_index_, tr, tc, tsz,
-                t.r.bytes_left(), blocks_.size());
+      jobs[(size_t)tc * tile_rows + tr] = TileJob{ p, tsz, tr, tc };
       p += tsz;
+    }
+  }
+  n_workers_ = std::min(threads_, tile_cols);
+  while ((int)outs_.size() < n_workers_) outs_.emplace_back(new TileOut());
+  while ((int)tile_workers_.size() < n_workers_ - 1) tile_workers_.emplace_back(new SideWorker());
+  sb_worker_.assign(sb_cols_, 0);
+  std::vector<int> first(n_workers_ + 1);
+  for (int w = 0; w <= n_workers_; w++) first[w] = w * tile_cols / n_workers_;   // contiguous tile columns per worker
+  for (int w = 0; w < n_workers_; w++) {
+    TileOut &o = *outs_[w];
+    o.blocks.clear();
+    o.submv.clear();
+    for (int i = 0; i < 4; i++) o.txb_inter[i].clear();
+    for (int q = 0; q < 3; q++) o.txb_intra[q].clear();
+    o.n_coef = 0;
+    if (do_counts_) memset(&o.counts, 0, sizeof(o.counts));
+    memset(o.n_inter_px, 0, sizeof(o.n_inter_px));
+    memset(o.n_compound_px, 0, sizeof(o.n_compound_px));
+    o.corrupted = false;
+    o.bad_marker = 0;
+    for (int tc = first[w]; tc < first[w + 1]; tc++) {
+      const int c0 = tile_col_offset(tc, mi_cols_, log2_tile_cols_) >> 3, c1 = (tile_col_offset(tc + 1, mi_cols_, log2_tile_cols_) + 7) >> 3;
+      for (int c = c0; c < c1 && c < sb_cols_; c++) sb_worker_[c] = (uint8_t)w;
+    }
+  }
+  for (int w = n_workers_ - 1; w >= 0; w--) {
+    TileOut *o = outs_[w].get();
+    const TileJob *j = &jobs[(size_t)first[w] * tile_rows];
+    const int nj = (first[w + 1] - first[w]) * tile_rows;
+    if (w > 0) tile_workers_[w - 1]->run([this, o, j, nj] { run_tile_column(o, j, nj); });
+    else run_tile_column(o, j, nj);      // the calling thread takes the first group itself
+  }
+  for (int w = 1; w < n_workers_; w++) tile_workers_[w - 1]->wait();
+  for (int w = 0; w < n_workers_; w++) {
+    if (outs_[w]->bad_marker) return fail(VP9B_ERR_CORRUPT, "tile marker bit set");
+    if (outs_[w]->corrupted) return fail(VP9B_ERR_CORRUPT, "corrupt tile data");
+  }
+  if (do_counts_) {      // symbol counts of the frame = sum over the workers
+    counts_ = outs_[0]->counts;
+    for (int w = 1; w < n_workers_; w++) {
+      uint32_t *d = (uint32_t *)&counts_;
+      const uint32_t *a = (const uint32_t *)&outs_[w]->counts;
+      for (size_t i = 0; i < sizeof(FrameCounts) / sizeof(uint32_t); i++) d[i] += a[i];
     }
   }
   // Backward adaptation (vp9_decodeframe.c:3570-3586) only feeds the NEXT frame's entropy context: it

@@ -10,6 +10,7 @@
 
 #include <condition_variable>
 #include <functional>
+#include <memory>
 #include <mutex>
 #include <thread>
 #include <string>
@@ -143,6 +144,25 @@ class SideWorker {
   bool has_ = false, done_ = true, quit_ = false;
 };
 
+// What one tile-column worker produces for a frame (tile columns are independent:
+// vp9_decodeframe.c:2919-3047 decode_tiles_mt / :2663-2752 tile_worker_hook): record lists with
+// worker-local indices, its share of the coefficient stream, its symbol counts.  Parser::pack()
+// concatenates the workers' lists and rebases the indices; the counts are summed before adaptation.
+struct TileOut {
+  std::vector<vp9b_block> blocks;
+  std::vector<vp9b_submv> submv;
+  std::vector<vp9b_txb> txb_inter[4];   // by transform size (blocks of one size share a warp on the GPU)
+  std::vector<vp9b_txb> txb_intra[3];
+  std::vector<int16_t> coef16;
+  std::vector<int32_t> coef32;
+  size_t n_coef = 0;                    // coefficients written this frame (the vectors only grow)
+  FrameCounts counts;
+  uint32_t n_inter_px[3], n_compound_px[3];
+  uint32_t block_next = 0;              // next free entry of this worker's range of Parser::blocks_
+  bool corrupted = false;
+  int bad_marker = 0;
+};
+
 class Parser {
  public:
   Parser();
@@ -154,6 +174,9 @@ class Parser {
   // Where pack() assembles the packed buffer: alloc(priv, bytes) returns the destination (e.g. the
   // page-locked upload buffer of a reconstruction context); nullptr / no allocator: a parser-owned buffer.
   void set_output_allocator(void *(*alloc)(void *priv, size_t bytes), void *priv) { out_alloc_ = alloc; out_priv_ = priv; }
+  // Tile-column workers per frame (1 = everything on the calling thread).  More than one pays off when
+  // there are fewer streams than host cores; the helpers are threads owned by this parser.
+  void set_threads(int n) { threads_ = n < 1 ? 1 : (n > 64 ? 64 : n); }
   int show_slot() const { return show_slot_; }
   const SlotInfo &slot(int i) const { return slots_[i]; }
   const std::string &error() const { return err_; }
@@ -173,6 +196,8 @@ class Parser {
   void adapt_mv_probs();
   void finish_lfm();
   void pack();
+  struct TileJob { const uint8_t *data; size_t size; int tr, tc; };
+  void run_tile_column(TileOut *o, const TileJob *jobs, int n_jobs);
 
   std::string err_;
   SideWorker adapt_worker_;          // backward adaptation of the previous frame, joined by the next parse()
@@ -222,17 +247,12 @@ class Parser {
   std::vector<uint8_t> above_ctx_[3];
   std::vector<uint8_t> above_seg_ctx_;
   // ---- per frame output
-  std::vector<vp9b_block> out_blocks_;
-  std::vector<vp9b_submv> out_submv_;
-  std::vector<vp9b_txb> out_txb_inter_[4];  // by transform size (blocks of one size share a warp on the GPU)
-  std::vector<vp9b_txb> out_txb_inter_all_;
-  std::vector<vp9b_txb> out_txb_intra_[3];
-  std::vector<vp9b_sbrange> out_sb_intra_;  // [3][sb_rows*sb_cols]
-  std::vector<int16_t> out_coef16_;
-  std::vector<int32_t> out_coef32_;
-  size_t n_coef_ = 0;  // coefficients written this frame (the vectors only grow)
+  int threads_ = 1, n_workers_ = 1;
+  std::vector<std::unique_ptr<TileOut>> outs_;          // one per tile-column worker
+  std::vector<std::unique_ptr<SideWorker>> tile_workers_;
+  std::vector<uint8_t> sb_worker_;                       // superblock column -> worker that parsed it
+  std::vector<vp9b_sbrange> out_sb_intra_;  // [3][sb_rows*sb_cols], start = index in the owning worker's list
   std::vector<vp9b_lfm> out_lfm_;
-  uint32_t n_inter_px_[3], n_compound_px_[3];
   std::vector<uint8_t> packed_;
 };
 

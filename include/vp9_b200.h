@@ -261,6 +261,11 @@ const char *vp9b_parser_last_error(vp9b_parser *p);
  * (-1: nothing to show).  (role of vp9_receive_compressed_data, vp9_decoder.c:407) */
 int vp9b_parser_parse(vp9b_parser *p, const uint8_t *data, size_t size, const void **packed,
                       size_t *bytes, int *show_slot);
+/* Tile-column workers per frame (vp9_decodeframe.c:2919-3047 decode_tiles_mt): 1 (default, or the
+ * environment variable VP9B_PARSE_THREADS) parses every tile on the calling thread; n > 1 spreads the
+ * tile columns over n threads owned by the parser.  Worth it when there are fewer streams than host
+ * cores; the packed buffer is equivalent either way (records may be ordered differently). */
+int vp9b_parser_set_threads(vp9b_parser *p, int threads);
 /* Where the packed buffer is assembled: alloc(priv, bytes) returns the destination, e.g. the
  * page-locked upload buffer of a reconstruction context (vp9gpu_upload_buffer) so that the frame is
  * packed straight into the memory the H2D copy reads.  alloc == NULL (default) or a NULL return:
