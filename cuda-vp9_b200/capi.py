@@ -397,6 +397,13 @@ class Decoder:
                      pl[0].strides[0], pl[1].strides[0]))
         return True
 
+    def set_parse_threads(self, n):
+        """Tile-column parser threads of this decoder (vp9b_parser_set_threads on its parser)."""
+        self.L.vp9b_decoder_parser.restype = C.c_void_p
+        self.L.vp9b_decoder_parser.argtypes = [C.c_void_p]
+        self.L.vp9b_parser_set_threads.argtypes = [C.c_void_p, C.c_int]
+        self._chk(self.L.vp9b_parser_set_threads(self.L.vp9b_decoder_parser(self.d), int(n)))
+
     def set_frame_buffer_functions(self, get, release):
         """External output buffers (vpx_codec_set_frame_buffer_functions): get(min_size) -> (address, size, tag),
         release(tag).  Must be called before the first decode()."""

@@ -27,6 +27,14 @@
 #include "vp9_lf_sb.cuh"
 #include "vp9_lf_warp.cuh"
 
+// occupancy targets of the two register-hungry kernels (A/B builds override them)
+#ifndef VP9B_MC_MINB
+#define VP9B_MC_MINB 5
+#endif
+#ifndef VP9B_INTRA_MINB
+#define VP9B_INTRA_MINB 1
+#endif
+
 namespace vp9b {
 
 // ------------------------------------------------------------------------------------------
@@ -673,7 +681,7 @@ VP9B_DEV void mc_do_unit(const FrameParams &P, const Px *stage, const MiEntry *s
 }
 
 template <typename Px, typename FB>
-__global__ void __launch_bounds__(128, sizeof(Px) == 1 ? 5 : 3) k_inter_pred_sb(const __grid_constant__ FB B) {
+__global__ void __launch_bounds__(128, sizeof(Px) == 1 ? VP9B_MC_MINB : 3) k_inter_pred_sb(const __grid_constant__ FB B) {
   const FrameParams &P = B.f[blockIdx.z];
   if (!P.do_inter) return;
   const int sbc = blockIdx.x, sbr = blockIdx.y, tid = threadIdx.x;
@@ -1199,7 +1207,7 @@ template <typename Px> struct IntraTileGeom {
 };
 
 template <typename Px, typename PT, typename FB>
-__global__ void __launch_bounds__(kWaveWarps * 32) k_intra(const __grid_constant__ FB B) {
+__global__ void __launch_bounds__(kWaveWarps * 32, VP9B_INTRA_MINB) k_intra(const __grid_constant__ FB B) {
   const FrameParams &P = B.f[blockIdx.z];
   if (!P.do_intra) return;
   extern __shared__ __align__(16) unsigned char intra_smem[];

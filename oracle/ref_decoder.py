@@ -71,10 +71,12 @@ class RefRecon:
             self.c = None
 
 
-def decode_chunks(chunks, want="md5", stop_stage=0):
+def decode_chunks(chunks, want="md5", stop_stage=0, parse_threads=1):
     """Decode IVF chunks with (host parser -> oracle).  Yields one entry per shown frame."""
     import cuda_vp9_b200 as vb
     parser = vb.HostParser()
+    if parse_threads > 1:
+        parser.set_threads(parse_threads)
     rec = RefRecon()
     out = []
     for ch in chunks:

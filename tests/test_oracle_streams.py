@@ -17,6 +17,16 @@ def test_cpu_decode_matches_golden_md5(name):
     assert got == golden_md5(name)
 
 
+@pytest.mark.parametrize("name", ["tiles_rt", "bench_1440p", "bench_hbd1080", "intra_only", "aq", "scaled_rt"])
+@pytest.mark.parametrize("threads", [2, 4, 7])
+def test_tile_parallel_parse_matches_golden_md5(name, threads):
+    """Tile columns parsed by worker threads (vp9b_parser_set_threads): the merged packed buffer must
+    reconstruct to the same frames (per-worker record lists are concatenated and rebased)."""
+    _, _, chunks = vb.ivf_read(clip_path(name))
+    n = 6 if name.startswith("bench_") else len(chunks)
+    assert ref_decoder.decode_chunks(chunks[:n], want="md5", parse_threads=threads) == golden_md5(name)[:n]
+
+
 @pytest.mark.skipif(not vpx_oracle.available(), reason="libvpx .so not present")
 @pytest.mark.parametrize("name", ["odd_rt", "comp", "hbd10", "scaled"])
 def test_golden_md5_matches_live_libvpx(name):
