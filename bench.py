@@ -457,6 +457,9 @@ def run_ours(args, rank, world, local):
                 "host_parse_fps_1thread": rp.shown / rp.parse_s, "host_submit_ms_per_step": host_submit_ms,
                 "timed_region_s": ms * 1e-3}
     packed_bytes = sum(len(p) for p in rp.packed)
+    # bytes of the frames a pass hands out (frames of the scaled segment are smaller than the stream size)
+    shown_bytes = sum(int(hh.width * hh.height + 2 * ((hh.width + hh.ss_x) >> hh.ss_x) * ((hh.height + hh.ss_y) >> hh.ss_y)) * bps
+                      for hh in rp.hdrs if hh.show_frame)
     hdr0 = rp.hdrs[0]
     w, h, chunks, shown = rp.w, rp.h, rp.chunks, rp.shown
     rp.close()
@@ -558,7 +561,7 @@ def run_ours(args, rank, world, local):
         single = {"parse_threads_1": single_stream(1), "parse_threads_4": single_stream(4)} if rank == 0 else None
         e2e = {"value": n_e2e / e2e_s, "unit": "frames/s",
                "h2d_bytes_per_step": int(packed_bytes * E * world * e2e_passes / args.steps),
-               "d2h_bytes_per_step": int(shown * int(w * h * 1.5 * bps) * E * world * e2e_passes / args.steps),
+               "d2h_bytes_per_step": int(shown_bytes * E * world * e2e_passes / args.steps),
                "timed_region_s": e2e_s, "host_threads": E * world, "single_stream_fps": single,
                "what": "vp9b_decoder_decode (host parse + H2D + kernels) + vp9b_decoder_read_frame (D2H) per shown "
                        "frame into pinned host memory, %d host threads / streams per rank, %d clip passes each" % (E, e2e_passes)}

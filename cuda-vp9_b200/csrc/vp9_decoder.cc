@@ -66,7 +66,6 @@ int vp9b_decoder_decode(vp9b_decoder *d, const uint8_t *data, size_t size) {
     const void *packed = nullptr;
     size_t bytes = 0;
     int show = -1;
-    // a frame of size 1 with only the marker is a skipped frame in libvpx superframes
     nvtxRangePushA("vp9b: host parse (bool decoder, modes, tokens, masks)");
     int e = vp9b_parser_parse(d->parser, data + off, sizes[i], &packed, &bytes, &show);
     nvtxRangePop();

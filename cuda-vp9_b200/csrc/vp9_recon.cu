@@ -1,12 +1,16 @@
 // VP9 reconstruction kernels for sm_100a (B200) + the vp9gpu_* C ABI (include/vp9_b200.h).
 //
 // One packed buffer per frame is uploaded; reference frames stay resident in HBM.  Stages per
-// frame, all enqueued on the context stream:
-//   0  k_expand_blocks   block records -> dense per-8x8 motion map (L2 resident)
-//   1  k_inter_pred      8-tap sub-pel MC incl. compound + scaled refs   (a1-a3)
-//   2  k_residual        inverse transform + add for inter blocks          (a6-a7)
-//   3  k_intra           intra prediction + residual, superblock wavefront (a4-a7)
-//   4  k_loopfilter      lpf 4/8/16 in libvpx's normative superblock order (a9-a10)
+// frame (or per batch of frames of up to 32 contexts), all enqueued on the context stream:
+//   0  k_expand_blocks    block records -> dense per-8x8 motion map (L2 resident)
+//   1  k_inter_pred_sb    8-tap sub-pel MC incl. compound + scaled refs, one CTA per superblock,
+//                         reference windows staged by TMA                  (a1-a3)
+//   2  k_residual         inverse transform + add for inter blocks          (a6-a7)
+//   3  k_intra_residual   inverse transforms of intra blocks into residual planes
+//      k_intra            intra prediction + residual, superblock-row wavefront (a4-a7)
+//   4  k_lf_sb            lpf 4/8/16 in libvpx's normative order, one worker per superblock column,
+//                         launched programmatically behind k_intra and following it one superblock
+//                         row behind (a9-a10; k_lf_warp: packed-arithmetic variant, opt-in)
 // Integer byte work, HBM/L2 bound -- no tensor cores by design (bit exactness).
 #include <cuda.h>
 #include <cuda_runtime.h>
@@ -40,7 +44,6 @@ namespace vp9b {
 // ------------------------------------------------------------------------------------------
 // device-side constant tables
 __device__ int16_t d_scan[(16 + 64 + 256) * 3 + 1024];  // [4x4: def,row,col][8x8..][16x16..][32x32 def]
-__device__ int8_t d_filters[4 * 16 * 8];                 // taps fit int8 except 128 (stored as int16 below)
 __device__ int16_t d_filters16[4 * 16 * 8];
 
 __host__ __device__ inline int scan_offset(int tx_size, int tx_type) {
@@ -756,6 +759,63 @@ __global__ void __launch_bounds__(128, sizeof(Px) == 1 ? VP9B_MC_MINB : 3) k_int
     for (int pl = 1; pl < 3; pl++)
       mc_do_unit<Px, 8>(P, stage, s_mi, s_woff, pl, ((tid >> 4) << 3) | ((tid & 15) >> 1), sbr, sbc, sbc * 64 + (tid & 15) * 4, sbr * 64 + (tid >> 4) * 8);
   }
+}
+
+// ------------------------------------------------------------------------------------------
+// stage 1, flat variant (no staging): thread = one 4 x H unit anywhere in the plane, warp = 8 x 4
+// units, reference rows straight from global memory through L1.  All three planes in one launch:
+// luma tiles (32 x 128 samples) first, then the two chroma planes.  Kept next to k_inter_pred_sb as
+// the A/B baseline (VP9B_MC_FLAT=1).
+template <typename Px, int H>
+VP9B_DEV void inter_pred_flat_body(const FrameParams &P, int plane, int bx_, int by_) {
+  typedef typename McOut<Px>::T Row;
+  const int ss_x = plane ? P.ss_x : 0, ss_y = plane ? P.ss_y : 0;
+  const int pw = (P.mi_cols * 8) >> ss_x, ph = (P.mi_rows * 8) >> ss_y;
+  const int x = (bx_ * 8 + (threadIdx.x & 7)) * 4;
+  const int y = (by_ * 16 + (threadIdx.x >> 3)) * H;
+  if (x >= pw || y >= ph) return;
+  const int dstride = P.dst[plane].stride;
+  Px *dst = (Px *)P.dst[plane].ptr + (size_t)y * dstride + x;
+  const int mi_col = (x << ss_x) >> 3, mi_row = (y << ss_y) >> 3;
+  const MiEntry e = P.mi[(size_t)mi_row * P.mi_cols + mi_col];
+  if (!e.ref0) return;
+  McWin W;
+  W.off[0] = W.off[1] = -1;
+  W.bx = W.by = 0;
+  W.S = 0;
+  if (H == 8 && e.bsize < 3) {  // sub-8x8 block in an unsubsampled plane: two 4x4 units
+#pragma unroll 1
+    for (int half = 0; half < 2; half++) {
+      Row o[4];
+      mc_unit<Px, 4>(P, nullptr, W, plane, e, mi_row, mi_col, x, y + 4 * half, o);
+#pragma unroll
+      for (int i = 0; i < 4; i++) *(Row *)(dst + (size_t)(i + 4 * half) * dstride) = o[i];
+    }
+    return;
+  }
+  Row o[H];
+  mc_unit<Px, H>(P, nullptr, W, plane, e, mi_row, mi_col, x, y, o);
+#pragma unroll
+  for (int i = 0; i < H; i++) *(Row *)(dst + (size_t)i * dstride) = o[i];
+}
+
+template <typename Px, typename FB>
+__global__ void __launch_bounds__(128, sizeof(Px) == 1 ? 8 : 4) k_inter_pred_flat(const __grid_constant__ FB B) {
+  const FrameParams &P = B.f[blockIdx.z];
+  if (!P.do_inter) return;
+  const int pwy = P.mi_cols * 8, phy = P.mi_rows * 8, pwc = pwy >> P.ss_x, phc = phy >> P.ss_y;
+  const int gy_y = (phy + 127) / 128, gx_y = (pwy + 31) / 32, gx_c = (pwc + 31) / 32, gy_c = P.ss_x ? (phc + 63) / 64 : (phc + 127) / 128;
+  int by = blockIdx.y, plane = 0;
+  if (by >= gy_y) {
+    by -= gy_y;
+    plane = 1;
+    if (by >= gy_c) { by -= gy_c; plane = 2; }
+    if (by >= gy_c || (int)blockIdx.x >= gx_c) return;
+  } else if ((int)blockIdx.x >= gx_y) {
+    return;
+  }
+  if (plane && P.ss_x) inter_pred_flat_body<Px, 4>(P, plane, blockIdx.x, by);
+  else inter_pred_flat_body<Px, 8>(P, plane, blockIdx.x, by);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1741,6 +1801,7 @@ struct vp9gpu_ctx {
   uint64_t next_ticket = 1;
   int stop_stage = 0;
   bool lf_overlap = getenv("VP9B_LF_NO_OVERLAP") == nullptr;   // loop filter launched programmatically behind k_intra
+  bool mc_flat = getenv("VP9B_MC_FLAT") != nullptr;   // A/B: motion compensation without staging (k_inter_pred_flat)
   bool lf_warp = getenv("VP9B_LF_WARP") != nullptr;   // A/B: 8-bit 4:2:0 through k_lf_warp instead of k_lf_sb
   bool validate = true;           // record-level validation of host packed buffers (vp9gpu_set_validation)
   uint64_t launches = 0;
@@ -1786,7 +1847,6 @@ static int init_tables(vp9gpu_ctx *ctx) {
   CK(cudaMemcpyToSymbol(d_filters16, kSubpelFilters, sizeof(int16_t) * 4 * 16 * 8));
   int8_t f8[4 * 16 * 8];
   for (int i = 0; i < 4 * 16 * 8; i++) f8[i] = (int8_t)(kSubpelFilters[i] > 127 ? 127 : kSubpelFilters[i]);
-  CK(cudaMemcpyToSymbol(d_filters, f8, sizeof(f8)));
   uint32_t t4[4 * 16 * 2];
   for (int i = 0; i < 4 * 16; i++)
     for (int hhalf = 0; hhalf < 2; hhalf++) {
@@ -2091,7 +2151,18 @@ static int launch_batch(vp9gpu_ctx *const *ctxs, FB &B, int n) {
     ctx->launches++;
   }
   if (prof) cudaEventRecord(ctx->prof_ev[1], st);
-  if (g_mcx) {
+  if (g_mcx && ctx->mc_flat) {
+    int gx = 0, gy = 0;
+    for (int i = 0; i < n; i++) {
+      const FrameParams &P = B.f[i];
+      if (!P.do_inter) continue;
+      const int pwy = P.mi_cols * 8, phy = P.mi_rows * 8, phc = phy >> P.ss_y;
+      gx = std::max(gx, (pwy + 31) / 32);
+      gy = std::max(gy, (phy + 127) / 128 + 2 * (P.ss_x ? (phc + 63) / 64 : (phc + 127) / 128));
+    }
+    k_inter_pred_flat<Px, FB><<<dim3(gx, gy, n), 128, 0, st>>>(B);
+    ctx->launches++;
+  } else if (g_mcx) {
     const dim3 grid(g_mcx, g_mcy, n);   // one CTA per superblock
     const size_t smem = McStage<Px>::kBudget * sizeof(Px);
     const unsigned abit = (sizeof(Px) == 1 ? 64u : 128u) << abase;

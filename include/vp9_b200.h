@@ -137,7 +137,9 @@ typedef struct vp9b_lfm { /* 160 bytes. role of LOOP_FILTER_MASK, vp9_loopfilter
 /* ------------------------------------------------------------------ 1. reconstruction ctx --- */
 typedef struct vp9gpu_ctx vp9gpu_ctx;
 
-/* device < 0: current device.  Returns NULL on failure (no CUDA device). */
+/* device < 0: current device.  Returns NULL on failure (no CUDA device).  Side effect shared by every
+ * vp9gpu_* / vp9b_decoder_* call: the calling thread's current CUDA device is set to the context's
+ * device (cudaSetDevice) and left there. */
 vp9gpu_ctx *vp9gpu_create(int device);
 void vp9gpu_destroy(vp9gpu_ctx *ctx);
 const char *vp9gpu_last_error(vp9gpu_ctx *ctx);
