@@ -285,11 +285,13 @@ def stage_bytes(np, packed, hdrs):
 class Replay:
     """S reconstruction contexts replaying one clip's packed buffers from HBM, K streams per launch."""
 
-    def __init__(self, vb, torch, local, clip, S, K, stop_stage=0):
+    def __init__(self, vb, torch, local, clip, S, K, stop_stage=0, parsed=None):
         import numpy as np
         self.vb, self.torch, self.S = vb, torch, S
-        self.w, self.h, self.chunks = load_clip(clip)
-        self.packed, self.shown, self.parse_s = parse_clip(vb, self.chunks)
+        if parsed is None:
+            w, h, chunks = load_clip(clip)
+            parsed = (w, h, chunks) + parse_clip(vb, chunks)
+        self.w, self.h, self.chunks, self.packed, self.shown, self.parse_s = parsed
         hs = C.sizeof(vb.FrameHdr)
         self.hdrs = [vb.FrameHdr.from_buffer_copy(p[:hs]) for p in self.packed]
         self.n_coded = len(self.packed)
@@ -392,96 +394,21 @@ def run_ours(args, rank, world, local):
         torch.cuda.synchronize()
 
     S, P = args.streams, args.passes
-    rp = Replay(vb, torch, local, args.clip, S, args.batch, args.stop_stage)
-    args.batch = rp.K
-    sampler = ClockSampler(local)
-    ms, host_submit_ms, launches = rp.timed(args.steps, args.warmup, P, barrier, sampler)
-    clocks = sampler.finish()
-    if world > 1:
-        import torch.distributed as dist
-        t = torch.tensor([ms], device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
-        lt = torch.tensor([launches], device="cuda", dtype=torch.int64)
-        dist.all_reduce(lt)
-        launches = int(lt.item())
-    frames_total = rp.shown * S * P * args.steps * world
-    value = frames_total / (ms * 1e-3)
-
-    # ---- roofline: one launch group (K frames per launch) alone on the GPU, per-stage events
-    stage = rp.profile_batch()
-    K = rp.K
-    bps = 2 if rp.hdrs[0].bit_depth > 8 else 1
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-    except Exception:
-        pass
-    peak = float(peaks.get("hbm_gbs", 6650.0))
-    peak_src = "measured (MEASURED_PEAKS.json)" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
-    kernel_of = {"expand": "k_expand_blocks", "inter_pred": "k_inter_pred_sb", "inter_residual": "k_residual",
-                 "intra_residual": "k_intra_residual", "intra": "k_intra", "loop_filter": "k_lf_sb"}
-    n_launch = {k: max(1, sum(1 for f in rp.bytes_frame if f[k] > 0)) for k in kernel_of}
-    allk = {}
-    for k, name in kernel_of.items():
-        b = rp.bytes_tot[k] * K            # every launch covers K frames
-        allk[name] = {"ms_per_clip_pass": stage[k], "bytes_per_clip_pass": b, "launches_per_clip_pass": n_launch[k],
-                      "GBps": (b / (stage[k] * 1e-3) / 1e9 if stage[k] > 0 else 0.0)}
-    dom_stage = max(kernel_of, key=lambda k: stage[k])
-    dom = kernel_of[dom_stage]
-    d = allk[dom]
-    traffic, traffic_src = None, None
-    try:
-        tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-        ent = tr.get(CLIPS[args.clip], {}).get(dom)
-        if ent and ent.get("streams_per_launch") == K:
-            traffic, traffic_src = ent["dram_bytes_per_launch"], ent.get("source")
-    except Exception:
-        pass
-    roofline = {"bound": "hbm", "kernel": dom, "achieved": d["GBps"], "peak": peak, "unit": "GB/s",
-                "frac": d["GBps"] / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
-                "frames_per_launch": K,
-                "algorithmic_bytes_per_launch": d["bytes_per_clip_pass"] / d["launches_per_clip_pass"],
-                "avg_launch_ms": d["ms_per_clip_pass"] / d["launches_per_clip_pass"],
-                "how": "one launch group of %d streams alone on the GPU, CUDA events between the stages on the launching stream" % K,
-                "step_share": {kernel_of[k]: stage[k] / max(sum(stage.values()), 1e-9) for k in kernel_of},
-                "all": allk,
-                "aggregate_mc_lf_GBps_in_timed_region": (rp.bytes_tot["inter_pred"] + rp.bytes_tot["loop_filter"]) * S * P * args.steps
-                                                        / (ms * 1e-3) / 1e9}
-    config = make_config(args)
-    frame_bytes = int(rp.hdrs[0].mi_cols * 8 * rp.hdrs[0].mi_rows * 8 * 1.5 * bps)
-    run_info = {"coded_frames": rp.n_coded,
-                "parallelism": "independent streams, %d per GPU, %d per kernel launch, no collective" % (S, K),
-                "l2": ("working set %d MB per GPU (> 126 MB L2): %d streams x (frame pool + packed buffers)" %
-                       (S * (12 * frame_bytes + sum(len(p) for p in rp.packed)) >> 20, S)),
-                "host_parse_fps_1thread": rp.shown / rp.parse_s, "host_submit_ms_per_step": host_submit_ms,
-                "timed_region_s": ms * 1e-3}
-    packed_bytes = sum(len(p) for p in rp.packed)
+    # ---- the clip, parsed once on the host
+    w, h, chunks = load_clip(args.clip)
+    parsed = (w, h, chunks) + parse_clip(vb, chunks)
+    packed_all, shown = parsed[3], parsed[4]
+    hs = C.sizeof(vb.FrameHdr)
+    hdrs_all = [vb.FrameHdr.from_buffer_copy(p[:hs]) for p in packed_all]
+    hdr0 = hdrs_all[0]
+    bps = 2 if hdr0.bit_depth > 8 else 1
+    packed_bytes = sum(len(p) for p in packed_all)
     # bytes of the frames a pass hands out (frames of the scaled segment are smaller than the stream size)
     shown_bytes = sum(int(hh.width * hh.height + 2 * ((hh.width + hh.ss_x) >> hh.ss_x) * ((hh.height + hh.ss_y) >> hh.ss_y)) * bps
-                      for hh in rp.hdrs if hh.show_frame)
-    hdr0 = rp.hdrs[0]
-    w, h, chunks, shown = rp.w, rp.h, rp.chunks, rp.shown
-    rp.close()
-    del rp
+                      for hh in hdrs_all if hh.show_frame)
 
-    # ---- the other bench clips: same replay measurement, short
-    others = {}
-    if not args.no_others and world == 1:
-        for clip in CLIPS:
-            if clip == args.clip or not os.path.exists(clip_file(clip)):
-                continue
-            So = min(S, 8) if clip == "lossless" else min(S, 32)
-            r2 = Replay(vb, torch, local, clip, So, args.batch)
-            ms2, _, _ = r2.timed(3, 2, 1, barrier)
-            st2 = r2.profile_batch(1)
-            others[clip] = {"workload": WORKLOADS[clip], "value": r2.shown * So * 3 / (ms2 * 1e-3), "unit": "frames/s",
-                            "streams_per_gpu": So, "streams_per_launch": r2.K, "timed_region_s": ms2 * 1e-3,
-                            "stage_ms_per_clip_pass": st2}
-            r2.close()
-            del r2
-
-    # ---- e2e: compressed chunks in host memory -> frames in host memory, one thread per stream
+    # ---- e2e first (the host is the bottleneck of this leg: measure it before the long replay phases):
+    # compressed chunks in host memory -> frames in host memory, one thread per stream
     e2e = None
     if not args.no_e2e:
         E = args.e2e_streams or sharding.host_threads_for_rank(world)
@@ -565,6 +492,89 @@ def run_ours(args, rank, world, local):
                "timed_region_s": e2e_s, "host_threads": E * world, "single_stream_fps": single,
                "what": "vp9b_decoder_decode (host parse + H2D + kernels) + vp9b_decoder_read_frame (D2H) per shown "
                        "frame into pinned host memory, %d host threads / streams per rank, %d clip passes each" % (E, e2e_passes)}
+
+    # ---- recon-only replay
+    rp = Replay(vb, torch, local, args.clip, S, args.batch, args.stop_stage, parsed=parsed)
+    args.batch = rp.K
+    sampler = ClockSampler(local)
+    ms, host_submit_ms, launches = rp.timed(args.steps, args.warmup, P, barrier, sampler)
+    clocks = sampler.finish()
+    if world > 1:
+        import torch.distributed as dist
+        t = torch.tensor([ms], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        lt = torch.tensor([launches], device="cuda", dtype=torch.int64)
+        dist.all_reduce(lt)
+        launches = int(lt.item())
+    frames_total = rp.shown * S * P * args.steps * world
+    value = frames_total / (ms * 1e-3)
+
+    # ---- roofline: one launch group (K frames per launch) alone on the GPU, per-stage events
+    stage = rp.profile_batch()
+    K = rp.K
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json)" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    kernel_of = {"expand": "k_expand_blocks", "inter_pred": "k_inter_pred_sb", "inter_residual": "k_residual",
+                 "intra_residual": "k_intra_residual", "intra": "k_intra", "loop_filter": "k_lf_sb"}
+    n_launch = {k: max(1, sum(1 for f in rp.bytes_frame if f[k] > 0)) for k in kernel_of}
+    allk = {}
+    for k, name in kernel_of.items():
+        b = rp.bytes_tot[k] * K            # every launch covers K frames
+        allk[name] = {"ms_per_clip_pass": stage[k], "bytes_per_clip_pass": b, "launches_per_clip_pass": n_launch[k],
+                      "GBps": (b / (stage[k] * 1e-3) / 1e9 if stage[k] > 0 else 0.0)}
+    dom_stage = max(kernel_of, key=lambda k: stage[k])
+    dom = kernel_of[dom_stage]
+    d = allk[dom]
+    traffic, traffic_src = None, None
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        ent = tr.get(CLIPS[args.clip], {}).get(dom)
+        if ent and ent.get("streams_per_launch") == K:
+            traffic, traffic_src = ent["dram_bytes_per_launch"], ent.get("source")
+    except Exception:
+        pass
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": d["GBps"], "peak": peak, "unit": "GB/s",
+                "frac": d["GBps"] / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
+                "frames_per_launch": K,
+                "algorithmic_bytes_per_launch": d["bytes_per_clip_pass"] / d["launches_per_clip_pass"],
+                "avg_launch_ms": d["ms_per_clip_pass"] / d["launches_per_clip_pass"],
+                "how": "one launch group of %d streams alone on the GPU, CUDA events between the stages on the launching stream" % K,
+                "step_share": {kernel_of[k]: stage[k] / max(sum(stage.values()), 1e-9) for k in kernel_of},
+                "all": allk,
+                "aggregate_mc_lf_GBps_in_timed_region": (rp.bytes_tot["inter_pred"] + rp.bytes_tot["loop_filter"]) * S * P * args.steps
+                                                        / (ms * 1e-3) / 1e9}
+    config = make_config(args)
+    frame_bytes = int(rp.hdrs[0].mi_cols * 8 * rp.hdrs[0].mi_rows * 8 * 1.5 * bps)
+    run_info = {"coded_frames": rp.n_coded,
+                "parallelism": "independent streams, %d per GPU, %d per kernel launch, no collective" % (S, K),
+                "l2": ("working set %d MB per GPU (> 126 MB L2): %d streams x (frame pool + packed buffers)" %
+                       (S * (12 * frame_bytes + sum(len(p) for p in rp.packed)) >> 20, S)),
+                "host_parse_fps_1thread": rp.shown / rp.parse_s, "host_submit_ms_per_step": host_submit_ms,
+                "timed_region_s": ms * 1e-3}
+    rp.close()
+    del rp
+
+    # ---- the other bench clips: same replay measurement, short
+    others = {}
+    if not args.no_others and world == 1:
+        for clip in CLIPS:
+            if clip == args.clip or not os.path.exists(clip_file(clip)):
+                continue
+            So = min(S, 8) if clip == "lossless" else min(S, 32)
+            r2 = Replay(vb, torch, local, clip, So, args.batch)
+            ms2, _, _ = r2.timed(3, 2, 1, barrier)
+            st2 = r2.profile_batch(1)
+            others[clip] = {"workload": WORKLOADS[clip], "value": r2.shown * So * 3 / (ms2 * 1e-3), "unit": "frames/s",
+                            "streams_per_gpu": So, "streams_per_launch": r2.K, "timed_region_s": ms2 * 1e-3,
+                            "stage_ms_per_clip_pass": st2}
+            r2.close()
+            del r2
 
     out = {"metric": "decoded frames/sec", "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",

@@ -563,6 +563,79 @@ VP9B_DEV void tma_load_2d(void *dst, const CUtensorMap *map, int x, int y, uint6
                ::"r"(smem_u32(dst)), "l"(map), "r"(x), "r"(y), "r"(smem_u32(bar)) : "memory");
 }
 
+// Scaled reference, 8-bit, one 4 x H unit (vpx_scaled_2d == vpx_convolve8_c with x/y_step_q4 != 16,
+// vpx_dsp/vpx_convolve.c:22-82,153-203): the unit's own intermediate block -- every reference row
+// between the first and the last row the vertical pass touches, filtered horizontally at the four
+// columns' positions and phases, clipped -- goes to a per-thread column of shared memory (the
+// staging buffer, unused in frames with scaled references), then the vertical pass picks eight
+// consecutive intermediate rows per output row.  Same arithmetic as predict_sample(), but a reference
+// row is filtered once instead of once per vertical tap (8x fewer loads and horizontal MACs).
+// Returns false (caller takes the per-sample path) when the window leaves the reference or the
+// step is larger than the scratch allows.  pp = position of the BLOCK origin, (dx0, dy0) = the unit
+// inside the block.  scr: this thread's column, rows 128 words apart.
+constexpr int kScaledRows = 48;
+template <int H>
+VP9B_DEV bool mc_unit_scaled(const RefGeom &R, int plane, const PredPos &pp, int dx0, int dy0, int filter, uint32_t *scr,
+                             uint32_t *out) {
+  const int rw = R.w[plane], rh = R.h[plane], rstride = R.pl[plane].stride;
+  int ix[4], ph[4];
+#pragma unroll
+  for (int c = 0; c < 4; c++) {
+    const int xq = pp.sx + (dx0 + c) * pp.xs;
+    ix[c] = pp.x0 - 3 + (xq >> 4);
+    ph[c] = xq & 15;
+  }
+  const int yq0 = pp.sy + dy0 * pp.ys, yql = pp.sy + (dy0 + H - 1) * pp.ys;
+  const int iy0 = pp.y0 - 3 + (yq0 >> 4), nrows = (yql >> 4) - (yq0 >> 4) + 8;
+  if (nrows > kScaledRows || ix[0] < 0 || ix[3] + 8 > rw || iy0 < 0 || iy0 + nrows > rh) return false;
+  // horizontal pass: three aligned words per column and row (neighbouring lanes share them in L1)
+  uint32_t txl[4], txh[4];
+  int sh[4];
+  const uint8_t *col[4];
+#pragma unroll
+  for (int c = 0; c < 4; c++) {
+    txl[c] = d_taps4[(filter * 16 + ph[c]) * 2];
+    txh[c] = d_taps4[(filter * 16 + ph[c]) * 2 + 1];
+    sh[c] = (ix[c] & 3) * 8;
+    col[c] = (const uint8_t *)R.pl[plane].ptr + (ptrdiff_t)iy0 * rstride + (ix[c] & ~3);
+  }
+#pragma unroll 2
+  for (int j = 0; j < nrows; j++) {
+    int v[4];
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+      const uint32_t *p = (const uint32_t *)(col[c] + (ptrdiff_t)j * rstride);
+      const uint32_t a0 = __ldg(p), a1 = __ldg(p + 1), a2 = __ldg(p + 2);
+      const uint32_t lo = __funnelshift_r(a0, a1, sh[c]), hi = __funnelshift_r(a1, a2, sh[c]);
+      // phase 0 is the tap 128, stored as 127 in the packed table: add the centre sample once more
+      int sum = dp4a_us(lo, txl[c], dp4a_us(hi, txh[c], 64)) + (ph[c] ? 0 : (int)(lo >> 24));
+      v[c] = sum >> 7;
+    }
+    scr[j * 128] = pack_sat_u8x4(v[0], v[1], v[2], v[3]);
+  }
+  // vertical pass
+#pragma unroll
+  for (int r = 0; r < H; r++) {
+    const int yq = pp.sy + (dy0 + r) * pp.ys, jr = (yq >> 4) - (yq0 >> 4), py = yq & 15;
+    const uint32_t tyl = d_taps4[(filter * 16 + py) * 2], tyh = d_taps4[(filter * 16 + py) * 2 + 1];
+    uint32_t m[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) m[k] = scr[(jr + k) * 128];
+    // 4x4 byte transposes: m[0..3] / m[4..7] -> per column the four rows' samples
+    const uint32_t a0 = __byte_perm(m[0], m[1], 0x5140), a1 = __byte_perm(m[2], m[3], 0x5140);
+    const uint32_t a2 = __byte_perm(m[0], m[1], 0x7362), a3 = __byte_perm(m[2], m[3], 0x7362);
+    const uint32_t b0 = __byte_perm(m[4], m[5], 0x5140), b1 = __byte_perm(m[6], m[7], 0x5140);
+    const uint32_t b2 = __byte_perm(m[4], m[5], 0x7362), b3 = __byte_perm(m[6], m[7], 0x7362);
+    const uint32_t lo[4] = { __byte_perm(a0, a1, 0x5410), __byte_perm(a0, a1, 0x7632), __byte_perm(a2, a3, 0x5410), __byte_perm(a2, a3, 0x7632) };
+    const uint32_t hi[4] = { __byte_perm(b0, b1, 0x5410), __byte_perm(b0, b1, 0x7632), __byte_perm(b2, b3, 0x5410), __byte_perm(b2, b3, 0x7632) };
+    int v[4];
+#pragma unroll
+    for (int c = 0; c < 4; c++) v[c] = (dp4a_us(lo[c], tyl, dp4a_us(hi[c], tyh, 64)) + (py ? 0 : (int)(lo[c] >> 24))) >> 7;
+    out[r] = pack_sat_u8x4(v[0], v[1], v[2], v[3]);
+  }
+  return true;
+}
+
 // what a unit needs to know about its block's staged windows
 struct McWin {
   int off[2];     // offset (samples) of the unit's luma window in the staging buffer per reference, -1: not staged
@@ -626,11 +699,23 @@ VP9B_DEV void mc_unit(const FrameParams &P, const Px *stage, const McWin &W, int
       else
         mc_unit_fast16<H>((const uint16_t *)src, stride, xs, ys, smvc & 15, smvr & 15, e.filter, edge, R.w[plane], R.h[plane], maxv,
                           (uint2 *)pr);
-    } else {  // scaled reference: exact per-sample path
+    } else {  // scaled reference
+      bool done = false;
+      if (sizeof(Px) == 1 && stage && !P.tmaps) {
+        // the staging buffer is free in frames with scaled references: per-thread scratch column
+        const int bw8 = d_bw8[e.bsize], bh8 = d_bh8[e.bsize];
+        const int mi_col0 = mi_col & ~(bw8 - 1), mi_row0 = mi_row & ~(bh8 - 1);
+        const int bx = x - ((mi_col0 * 8) >> ss_x), by = y - ((mi_row0 * 8) >> ss_y);
+        const int xoff = sub8 ? (bx & ~3) : 0, yoff = sub8 ? (by & ~3) : 0;
+        const PredPos pp = pred_position(P, R, plane, mi_row0, mi_col0, bw8, bh8, xoff, yoff, mvr, mvc);
+        done = mc_unit_scaled<H>(R, plane, pp, bx - xoff, by - yoff, e.filter, (uint32_t *)const_cast<Px *>(stage) + threadIdx.x, (uint32_t *)pr);
+      }
+      if (!done) {   // exact per-sample path (frame edges, high bit depth, very large steps)
 #pragma unroll
-      for (int yy = 0; yy < H; yy++) {
-        if (sizeof(Px) == 1) ((uint32_t *)pr)[yy] = mc_row_slow(P, R, plane, e, mi_row, mi_col, x, y, yy, mvr, mvc);
-        else ((uint2 *)pr)[yy] = mc16_row_slow(P, R, plane, e, mi_row, mi_col, x, y, yy, mvr, mvc);
+        for (int yy = 0; yy < H; yy++) {
+          if (sizeof(Px) == 1) ((uint32_t *)pr)[yy] = mc_row_slow(P, R, plane, e, mi_row, mi_col, x, y, yy, mvr, mvc);
+          else ((uint2 *)pr)[yy] = mc16_row_slow(P, R, plane, e, mi_row, mi_col, x, y, yy, mvr, mvc);
+        }
       }
     }
 #pragma unroll
@@ -2443,6 +2528,9 @@ static int prepare_frame(vp9gpu_ctx *ctx, const uint8_t *d_packed, const vp9b_fr
   P.lfm = (const vp9b_lfm *)(d_packed + h->sec[VP9B_SEC_LFM].offset);
   P.mi = ctx->d_mi;
   P.tmaps = ctx->tma_ok ? ctx->d_tmaps : nullptr;
+  // frames with a scaled reference do not stage windows: their units use the staging buffer as scratch
+  for (int r = 0; r < 3 && !h->intra_only; r++)
+    if (P.ref[r].x_step_q4 != 16 || P.ref[r].y_step_q4 != 16) P.tmaps = nullptr;
   // progress counters: [0, 3*1024) intra (plane, row), [3072, 4096) loop filter.  Values are
   // prog_base + count with prog_base advancing by 2048 per frame; cleared only when it wraps.
   if (h->width > 16384 || h->height > 16384) { ctx->err = "frame too large"; return VP9B_ERR_UNSUP; }
