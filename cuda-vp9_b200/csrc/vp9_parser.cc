@@ -1678,7 +1678,9 @@ void TileCtx::build_lf_mask() {
   const int row_in_sb = mi_row & 7, col_in_sb = mi_col & 7;
   const int shift_y = col_in_sb + (row_in_sb << 3);
   const int shift_uv = (col_in_sb >> 1) + ((row_in_sb >> 1) << 2);
-  const int build_uv = kFirstBlockIn16x16[row_in_sb * 8 + col_in_sb];
+  // the 4:2:0 chroma masks; 4:4:4 filters chroma with the luma masks, 4:2:2 / 4:4:0 get their own
+  // masks from the finished mode info (Parser::build_lfm_non420)
+  const int build_uv = (P->ss_x_ == P->ss_y_) && kFirstBlockIn16x16[row_in_sb * 8 + col_in_sb];
   {
     int index = shift_y;
     for (int i = 0; i < bh; i++) {
@@ -1915,6 +1917,51 @@ void Parser::adapt_mv_probs() {
 }
 
 // vp9_adjust_mask (vp9_loopfilter.c:766-878) applied to every superblock before upload.
+// Chroma masks of a 4:2:2 / 4:4:0 frame: the mask construction of vp9_filter_block_plane_non420
+// (vp9_loopfilter.c:1080-1239) for every superblock, from the finished mode info; the frame-edge rules
+// of the two filter passes (left-most column, top row, last odd row) are folded in.
+void Parser::build_lfm_non420() {
+  const int ss_x = ss_x_, ss_y = ss_y_, row_step = 1 << ss_y, col_step = 1 << ss_x;
+  vp9b_lfm_uv z;
+  memset(&z, 0, sizeof(z));
+  out_lfm_uv_.assign((size_t)sb_cols_ * sb_rows_, z);
+  for (int sbr = 0; sbr < sb_rows_; sbr++)
+    for (int sbc = 0; sbc < sb_cols_; sbc++) {
+      vp9b_lfm_uv &m = out_lfm_uv_[(size_t)sbr * sb_cols_ + sbc];
+      const int mi_row = sbr * 8, mi_col = sbc * 8;
+      for (int r = 0; r < 8 && mi_row + r < mi_rows_; r += row_step) {
+        for (int c = 0; c < 8 && mi_col + c < mi_cols_; c += col_step) {
+          const BlockInfo &mi = blocks_[grid_[(size_t)(mi_row + r) * mi_cols_ + mi_col + c]];
+          const int sb_type = mi.sb_type;
+          const bool skip_this = mi.skip && mi.ref_frame[0] > INTRA_FRAME;
+          // left / top edge of the unit is a block edge -> not skipped
+          const bool edge_left = kNum4x4Wide[sb_type] > 1 ? !(c & (kNum8x8Wide[sb_type] - 1)) : true;
+          const bool edge_above = kNum4x4High[sb_type] > 1 ? !(r & (kNum8x8High[sb_type] - 1)) : true;
+          const bool skip_c = skip_this && !edge_left, skip_r = skip_this && !edge_above;
+          const int tx = kUvTxSize[((sb_type * 4 + mi.tx_size) * 2 + ss_x) * 2 + ss_y];
+          const bool border_c = ss_x && mi_col + c == mi_cols_ - 1, border_r = ss_y && mi_row + r == mi_rows_ - 1;
+          const int level = lf_lvl_[mi.segment_id][mi.ref_frame[0] < 0 ? 0 : mi.ref_frame[0]][kModeLfLut[mi.mode]];
+          const uint8_t bit = (uint8_t)(1u << (c >> ss_x));
+          m.lfl[(r << 3) + (c >> ss_x)] = (uint8_t)level;
+          if (!level) continue;
+          if (tx == TX_32X32 || tx == TX_16X16) {
+            const int al = tx == TX_32X32 ? 3 : 1;
+            if (!skip_c && ((c >> ss_x) & al) == 0) (border_c ? m.v8 : m.v16)[r] |= bit;
+            if (!skip_r && ((r >> ss_y) & al) == 0) (border_r ? m.h8 : m.h16)[r] |= bit;
+          } else {
+            if (!skip_c) ((tx == TX_8X8 || ((c >> ss_x) & 3) == 0) ? m.v8 : m.v4)[r] |= bit;   // 8x8 filter on 32x32 boundaries
+            if (!skip_r) ((tx == TX_8X8 || ((r >> ss_y) & 3) == 0) ? m.h8 : m.h4)[r] |= bit;
+            if (!skip_this && tx < TX_8X8 && !border_c) m.v4i[r] |= bit;
+          }
+        }
+        // horizontal pass: its inner edges are the same mask minus the last odd row; no top edge in frame row 0
+        m.h4i[r] = (ss_y && mi_row + r == mi_rows_ - 1) ? 0 : m.v4i[r];
+        if (mi_row + r == 0) m.h16[r] = m.h8[r] = m.h4[r] = 0;
+        if (mi_col == 0) { m.v16[r] &= 0xfe; m.v8[r] &= 0xfe; m.v4[r] &= 0xfe; }   // left-most column of the frame
+      }
+    }
+}
+
 void Parser::finish_lfm() {
   const uint64_t left_border = 0x1111111111111111ULL, above_border = 0x000000ff000000ffULL;
   const uint16_t left_border_uv = 0x1111, above_border_uv = 0x000f;
@@ -2058,6 +2105,7 @@ void Parser::pack() {
   set(VP9B_SEC_SB_INTRA, sizeof(vp9b_sbrange), out_sb_intra_.size());
   set(VP9B_SEC_COEF, coef_elem, n_coef);
   if (lf_.filter_level) set(VP9B_SEC_LFM, sizeof(vp9b_lfm), out_lfm_.size());
+  if (!out_lfm_uv_.empty()) set(VP9B_SEC_LFM_UV, sizeof(vp9b_lfm_uv), out_lfm_uv_.size());
   size_t off = (sizeof(h) + 15) & ~(size_t)15;
   for (int i = 0; i < VP9B_SEC_COUNT; i++) {
     h.sec[i].offset = (uint32_t)off;
@@ -2119,6 +2167,8 @@ void Parser::pack() {
             dr[p * nsb + sbr * sb_cols_ + sbc].start += (uint32_t)intra_base[p * nw + sb_worker_[sbc]];
     }
     if (lf_.filter_level) memcpy(dst + h.sec[VP9B_SEC_LFM].offset, out_lfm_.data(), out_lfm_.size() * sizeof(vp9b_lfm));
+    if (!out_lfm_uv_.empty())
+      memcpy(dst + h.sec[VP9B_SEC_LFM_UV].offset, out_lfm_uv_.data(), out_lfm_uv_.size() * sizeof(vp9b_lfm_uv));
   }
 }
 
@@ -2170,8 +2220,6 @@ int Parser::parse(const uint8_t *data, size_t size) {
     last_height_ = height_;
     return VP9B_OK;
   }
-  if (!(ss_x_ == 1 && ss_y_ == 1) && !(ss_x_ == 0 && ss_y_ == 0))
-    return fail(VP9B_ERR_UNSUP, "only 4:2:0 and 4:4:4 are supported");
   if (hdr_bytes + first_partition_size > size) return fail(VP9B_ERR_CORRUPT, "truncated packet or corrupt header length");
   use_prev_frame_mvs_ = !error_res_ && width_ == last_width_ && height_ == last_height_ &&
                         !last_intra_only_ && last_show_frame_ && prev_mvs_valid_;
@@ -2283,6 +2331,8 @@ int Parser::parse(const uint8_t *data, size_t size) {
     else job();
   }
   if (lf_.filter_level) finish_lfm();
+  out_lfm_uv_.clear();
+  if (lf_.filter_level && ss_x_ != ss_y_) build_lfm_non420();
   pack();
   // swap_frame_buffers (vp9_decoder.c:334-367) + tail of vp9_receive_compressed_data
   SlotInfo &s = slots_[new_slot_];

@@ -195,6 +195,7 @@ class Parser {
   void adapt_mode_probs();
   void adapt_mv_probs();
   void finish_lfm();
+  void build_lfm_non420();
   void pack();
   struct TileJob { const uint8_t *data; size_t size; int tr, tc; };
   void run_tile_column(TileOut *o, const TileJob *jobs, int n_jobs);
@@ -253,6 +254,7 @@ class Parser {
   std::vector<uint8_t> sb_worker_;                       // superblock column -> worker that parsed it
   std::vector<vp9b_sbrange> out_sb_intra_;  // [3][sb_rows*sb_cols], start = index in the owning worker's list
   std::vector<vp9b_lfm> out_lfm_;
+  std::vector<vp9b_lfm_uv> out_lfm_uv_;      // 4:2:2 / 4:4:0 frames only
   std::vector<uint8_t> packed_;
 };
 

@@ -54,6 +54,7 @@ enum {
   VP9B_SEC_SB_INTRA = 6, /* vp9b_sbrange[3][sb_rows*sb_cols]  per-plane range into TXB_INTRA_* */
   VP9B_SEC_COEF = 7,     /* int16 (8-bit) or int32 (HBD) dequantised coefs, scan order, eob each */
   VP9B_SEC_LFM = 8,      /* vp9b_lfm[sb_rows*sb_cols]  final (adjusted) loop-filter masks     */
+  VP9B_SEC_LFM_UV = 9,   /* vp9b_lfm_uv[sb_rows*sb_cols]  chroma masks of 4:2:2 / 4:4:0 frames only */
   VP9B_SEC_COUNT = 12
 };
 
@@ -133,6 +134,18 @@ typedef struct vp9b_lfm { /* 160 bytes. role of LOOP_FILTER_MASK, vp9_loopfilter
   uint16_t pad[3];
   uint8_t lfl_y[64];
 } vp9b_lfm;
+
+/* Chroma loop-filter masks of a superblock when ss_x != ss_y (4:2:2, 4:4:0): what
+ * vp9_filter_block_plane_non420 (vp9_loopfilter.c:1080-1239) derives from the mode info, frame-edge
+ * rules already applied.  Index r = mi row inside the superblock (only every (1 << ss_y)-th entry is
+ * used), bit = mi column >> ss_x.  v*: vertical edges of the 8-sample-row band, h*: its top edge
+ * (and inner edge), by filter size 16 / 8 / 4 / inner 4x4.  (In those frames the uv fields of
+ * vp9b_lfm are zero.) */
+typedef struct vp9b_lfm_uv { /* 128 bytes */
+  uint8_t v16[8], v8[8], v4[8], v4i[8];
+  uint8_t h16[8], h8[8], h4[8], h4i[8];
+  uint8_t lfl[64]; /* filter level at [(r << 3) + (c >> ss_x)] */
+} vp9b_lfm_uv;
 
 /* ------------------------------------------------------------------ 1. reconstruction ctx --- */
 typedef struct vp9gpu_ctx vp9gpu_ctx;
@@ -355,5 +368,6 @@ VP9B_STATIC_ASSERT(sizeof(vp9b_submv) == 40, "vp9b_submv is 40 bytes");
 VP9B_STATIC_ASSERT(sizeof(vp9b_txb) == 12, "vp9b_txb is 12 bytes");
 VP9B_STATIC_ASSERT(sizeof(vp9b_sbrange) == 8, "vp9b_sbrange is 8 bytes");
 VP9B_STATIC_ASSERT(sizeof(vp9b_lfm) == 160, "vp9b_lfm is 160 bytes");
+VP9B_STATIC_ASSERT(sizeof(vp9b_lfm_uv) == 128, "vp9b_lfm_uv is 128 bytes");
 VP9B_STATIC_ASSERT(sizeof(vp9b_frame_hdr) == 416, "vp9b_frame_hdr is 416 bytes");
 #endif /* VP9_B200_H_ */

@@ -72,6 +72,10 @@ def encode_clip(path, w, h, n, seed=1234, bit_depth=8, scale_at=None, detail=0.0
     if enc_kw.get("chroma444"):  # full-resolution chroma planes
         frames = [[f[0], np.repeat(np.repeat(f[1], 2, 0), 2, 1)[:h, :w], np.repeat(np.repeat(f[2], 2, 0), 2, 1)[:h, :w]]
                   for f in frames]
+    elif enc_kw.get("chroma") == "422":  # full-height chroma
+        frames = [[f[0], np.repeat(f[1], 2, 0)[:h], np.repeat(f[2], 2, 0)[:h]] for f in frames]
+    elif enc_kw.get("chroma") == "440":  # full-width chroma
+        frames = [[f[0], np.repeat(f[1], 2, 1)[:, :w], np.repeat(f[2], 2, 1)[:, :w]] for f in frames]
     if two_pass:  # first pass collects stats (vpxenc.c two-pass loop)
         e1 = vo.Encoder(w, h, bit_depth=bit_depth, g_pass=1, **enc_kw)
         for f in frames:

@@ -541,9 +541,17 @@ static int inter_predict_frame(vp9ref_ctx *c, const vp9b_frame_hdr *h, const uin
           int k = 0;
           for (int y = 0; y < nh; y++)
             for (int x = 0; x < nw; x++, k++) {
+              /* average_split_mvs (vp9_reconinter.c:90-113 / dec_build_inter_predictors_sb): the block
+               * index is the running count k of the plane's own 4x4 grid; 4:2:2 averages blocks k, k+1,
+               * 4:4:0 blocks k, k+2 (mi_mv_pred_q2), 4:2:0 all four (q4, precomputed), 4:4:4 none */
               int mr, mc;
               if (ss_x && ss_y) { mr = s->chroma[r][0]; mc = s->chroma[r][1]; }
-              else { mr = s->luma[k][r][0]; mc = s->luma[k][r][1]; }
+              else if (ss_x || ss_y) {
+                const int k2 = k + (ss_x ? 1 : 2);
+                const int sr = s->luma[k][r][0] + s->luma[k2][r][0], sc = s->luma[k][r][1] + s->luma[k2][r][1];
+                mr = (sr < 0 ? sr - 1 : sr + 1) / 2;
+                mc = (sc < 0 ? sc - 1 : sc + 1) / 2;
+              } else { mr = s->luma[k][r][0]; mc = s->luma[k][r][1]; }
               predict_block(h, dst, rf, rd, plane, b->mi_row, b->mi_col, n4w_x4, n4h_x4, 4 * x, 4 * y, 4, 4, mr, mc,
                             b->filter, r, mb_to_left, mb_to_right, mb_to_top, mb_to_bottom, vis_w - 4 * x, vis_h - 4 * y);
             }
@@ -967,19 +975,58 @@ static void filter_block_plane_ss11(const vp9b_frame_hdr *h, uint16_t *buf, int 
   }
 }
 
+/* filter_selectively_vert (vp9_loopfilter.c:652-681, high bit depth :683-714): one 8-row band */
+static void filter_selectively_vert(uint16_t *s, int pitch, unsigned m16, unsigned m8, unsigned m4, unsigned m4i,
+                                    const vp9b_frame_hdr *h, const uint8_t *lfl) {
+  unsigned mask;
+  for (mask = m16 | m8 | m4 | m4i; mask; mask >>= 1) {
+    if (mask & 1) {
+      if (m16 & 1) lf_edge(s, pitch, 1, 16, 8, h, *lfl);
+      else if (m8 & 1) lf_edge(s, pitch, 1, 8, 8, h, *lfl);
+      else if (m4 & 1) lf_edge(s, pitch, 1, 4, 8, h, *lfl);
+    }
+    if (m4i & 1) lf_edge(s + 4, pitch, 1, 4, 8, h, *lfl);
+    s += 8;
+    lfl += 1;
+    m16 >>= 1; m8 >>= 1; m4 >>= 1; m4i >>= 1;
+  }
+}
+
+/* the two filter passes of vp9_filter_block_plane_non420 (vp9_loopfilter.c:1180-1239); the masks
+ * were built by the packer (vp9b_lfm_uv), frame-edge rules included */
+static void filter_block_plane_non420(const vp9b_frame_hdr *h, uint16_t *buf, int pitch, int mi_row, const vp9b_lfm_uv *m) {
+  const int row_step = 1 << h->ss_y;
+  uint16_t *b = buf;
+  int r;
+  for (r = 0; r < 8 && mi_row + r < (int)h->mi_rows; r += row_step) {
+    filter_selectively_vert(b, pitch, m->v16[r], m->v8[r], m->v4[r], m->v4i[r], h, &m->lfl[r << 3]);
+    b += 8 * pitch;
+  }
+  b = buf;
+  for (r = 0; r < 8 && mi_row + r < (int)h->mi_rows; r += row_step) {
+    filter_selectively_horiz(b, pitch, m->h16[r], m->h8[r], m->h4[r], m->h4i[r], h, &m->lfl[r << 3]);
+    b += 8 * pitch;
+  }
+}
+
 /* loop_filter_rows (vp9_loopfilter.c:1424-1469): superblocks in raster order, masks already
  * adjusted (vp9_adjust_mask) by the packer. */
 static int loop_filter_frame(vp9ref_ctx *c, const vp9b_frame_hdr *h, const uint8_t *base) {
   if (!h->lf_level) return 0;
-  if (!((h->ss_x == 1 && h->ss_y == 1) || (h->ss_x == 0 && h->ss_y == 0))) return VP9B_ERR_UNSUP;
+  const int non420 = h->ss_x != h->ss_y;   /* LF_PATH_SLOW: luma ss00, chroma non420 */
+  if (non420 && h->sec[VP9B_SEC_LFM_UV].count != h->sb_rows * h->sb_cols) return VP9B_ERR_INVALID;
   vp9ref_frame *f = &c->slot[h->dst_slot];
   const vp9b_lfm *lfm = (const vp9b_lfm *)(base + h->sec[VP9B_SEC_LFM].offset);
+  const vp9b_lfm_uv *lfm_uv = (const vp9b_lfm_uv *)(base + h->sec[VP9B_SEC_LFM_UV].offset);
   for (uint32_t sbr = 0; sbr < h->sb_rows; sbr++)
     for (uint32_t sbc = 0; sbc < h->sb_cols; sbc++) {
       const vp9b_lfm *m = &lfm[sbr * h->sb_cols + sbc];
       filter_block_plane_ss00(h, f->plane[0] + (size_t)sbr * 64 * f->stride[0] + sbc * 64, f->stride[0], sbr * 8, m);
       for (int p = 1; p < 3; p++) {
-        if (h->ss_x)
+        if (non420)
+          filter_block_plane_non420(h, f->plane[p] + (size_t)sbr * (64 >> h->ss_y) * f->stride[p] + sbc * (64 >> h->ss_x),
+                                    f->stride[p], sbr * 8, &lfm_uv[sbr * h->sb_cols + sbc]);
+        else if (h->ss_x)
           filter_block_plane_ss11(h, f->plane[p] + (size_t)sbr * 32 * f->stride[p] + sbc * 32, f->stride[p], sbr * 8, m);
         else
           filter_block_plane_ss00(h, f->plane[p] + (size_t)sbr * 64 * f->stride[p] + sbc * 64, f->stride[p], sbr * 8, m);

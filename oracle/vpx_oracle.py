@@ -77,6 +77,8 @@ VPX_IMG_FMT_I420 = 0x102
 VPX_IMG_FMT_HIGHBITDEPTH = 0x800
 VPX_IMG_FMT_I42016 = VPX_IMG_FMT_I420 | VPX_IMG_FMT_HIGHBITDEPTH
 VPX_IMG_FMT_I444 = 0x106
+VPX_IMG_FMT_I422 = 0x105
+VPX_IMG_FMT_I440 = 0x107
 
 # control ids (vpx/vp8dx.h:58-146, vpx/vp8cx.h:131-720)
 VP9_SET_SKIP_LOOP_FILTER = 265
@@ -242,7 +244,7 @@ class Encoder:
                  tile_rows_log2=0, lossless=0, cq_level=None, bitrate=None, min_q=0, max_q=63,
                  kf_max_dist=9999, error_resilient=0, frame_parallel=0, threads=4, aq_mode=0,
                  end_usage=None, resize_allowed=0, sharpness=None, g_pass=0, stats=None,
-                 arnr_maxframes=None, arnr_strength=None, chroma444=False):
+                 arnr_maxframes=None, arnr_strength=None, chroma444=False, chroma=None):
         L = lib()
         self.L, self.w, self.h, self.bd = L, w, h, bit_depth
         iface = C.c_void_p(L.vpx_codec_vp9_cx())
@@ -261,7 +263,9 @@ class Encoder:
             cfg.g_profile = 2
             cfg.g_bit_depth = bit_depth
             cfg.g_input_bit_depth = bit_depth
-        if chroma444:  # profile 1 (8 bit) / 3 (high bit depth): non-4:2:0 sampling
+        if chroma444:
+            chroma = "444"
+        if chroma:  # profile 1 (8 bit) / 3 (high bit depth): non-4:2:0 sampling ("444", "422", "440")
             cfg.g_profile = 3 if bit_depth > 8 else 1
         if end_usage is not None:
             cfg.rc_end_usage = end_usage
@@ -302,7 +306,7 @@ class Encoder:
         if arnr_strength is not None:
             self.ctrl(VP8E_SET_ARNR_STRENGTH, arnr_strength)
         self.stats_out = []
-        fmt = VPX_IMG_FMT_I444 if chroma444 else VPX_IMG_FMT_I420
+        fmt = {"444": VPX_IMG_FMT_I444, "422": VPX_IMG_FMT_I422, "440": VPX_IMG_FMT_I440}.get(chroma, VPX_IMG_FMT_I420)
         if bit_depth > 8:
             fmt |= VPX_IMG_FMT_HIGHBITDEPTH
         self.img_p = L.vpx_img_alloc(None, fmt, w, h, 32)

@@ -49,6 +49,12 @@ PARITY = {
     # profile 1 / 3: 4:4:4 sampling (vp9_filter_block_plane_non420, full-size chroma MC / intra)
     "p444": dict(w=176, h=144, n=5, chroma444=True, deadline=1, cpu_used=5, bitrate=300),
     "p444_hbd": dict(w=144, h=112, n=4, chroma444=True, bit_depth=10, deadline=1, cpu_used=5, bitrate=300),
+    # profile 1 / 3 with 4:2:2 and 4:4:0 sampling: vp9_filter_block_plane_non420 for chroma, non-square
+    # chroma blocks in MC / intra, q2 averages of sub-8x8 motion vectors (odd sizes, sub-8x8 partitions)
+    "p422": dict(w=200, h=152, n=6, chroma="422", cpu_used=1, bitrate=900, end_usage=0, min_q=4, max_q=40, force_lf=True),
+    "p440": dict(w=184, h=136, n=6, chroma="440", cpu_used=1, bitrate=900, end_usage=0, min_q=4, max_q=40, force_lf=True),
+    "p422_hbd": dict(w=176, h=144, n=5, chroma="422", bit_depth=10, deadline=1, cpu_used=5, bitrate=300),
+    "p440_rt": dict(w=352, h=288, n=8, chroma="440", deadline=1, cpu_used=5, bitrate=300, tile_cols_log2=1),
     # a forced key frame rewritten as a hidden intra-only frame, then shown with
     # show_existing_frame (bitstream edits in oracle/synth.py).  frame_parallel: without backward
     # adaptation the frames after the edit do not depend on last_frame_type == KEY_FRAME
