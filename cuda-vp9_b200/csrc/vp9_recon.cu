@@ -92,6 +92,7 @@ struct FrameParams {
   const vp9b_sbrange *sb_intra;  // [3][nsb]
   const void *coef;
   const vp9b_lfm *lfm;
+  const vp9b_lfm_uv *lfm_uv;    // chroma masks of 4:2:2 / 4:4:0 frames (nullptr otherwise)
   MiEntry *mi;
   const CUtensorMap *tmaps;     // [slot][plane][class] TMA descriptors of the frame pool (nullptr: no staging)
   uint32_t *prog_intra;         // [3][sb_rows] progress counters: prog_base + superblocks done in the row
@@ -661,11 +662,19 @@ VP9B_DEV void mc_unit(const FrameParams &P, const Px *stage, const McWin &W, int
     const RefGeom &R = P.ref[(r ? e.ref1 : e.ref0) - 1];
     int mvr, mvc;
     if (sub8) {
+      // average_split_mvs (vp9_reconinter.c:90-113): the block index is the running count of the
+      // plane's own 4x4 grid inside the 8x8 block (dec_build_inter_predictors_sb, dfc:702-718)
       const vp9b_submv &sm = P.submv[e.aux];
       if (ss_x && ss_y) { mvr = sm.chroma[r][0]; mvc = sm.chroma[r][1]; }
       else {
-        const int k = (((y << ss_y) & 7) >> 2) * 2 + (((x << ss_x) & 7) >> 2);
+        const int k = ((y & ((8 >> ss_y) - 1)) >> 2) * (2 >> ss_x) + ((x & ((8 >> ss_x) - 1)) >> 2);
         mvr = sm.luma[k][r][0]; mvc = sm.luma[k][r][1];
+        if (ss_x | ss_y) {     // 4:2:2: blocks k, k+1; 4:4:0: blocks k, k+2 (mi_mv_pred_q2)
+          const int k2 = k + (ss_x ? 1 : 2);
+          const int sr = mvr + sm.luma[k2][r][0], sc = mvc + sm.luma[k2][r][1];
+          mvr = (sr < 0 ? sr - 1 : sr + 1) / 2;
+          mvc = (sc < 0 ? sc - 1 : sc + 1) / 2;
+        }
       }
     } else {
       mvr = e.mv[r][0];
@@ -834,15 +843,27 @@ __global__ void __launch_bounds__(128, sizeof(Px) == 1 ? VP9B_MC_MINB : 3) k_int
     else mbar_arrive(&s_bar);
   }
   mbar_wait(&s_bar, 0);     // every staged window has landed; s_woff is visible (arrive = release, wait = acquire)
-  // ---- luma: 16 x 8 units of 4 x 8; chroma 4:2:0: 8 x 8 units of 4 x 4 per plane, 4:4:4: like luma
+  // ---- luma: 16 x 8 units of 4 x 8
   mc_do_unit<Px, 8>(P, stage, s_mi, s_woff, 0, ((tid >> 4) << 3) | ((tid & 15) >> 1), sbr, sbc, sbc * 64 + (tid & 15) * 4, sbr * 64 + (tid >> 4) * 8);
-  if (P.ss_x) {
-    const int pl = 1 + (tid >> 6), i = tid & 63;
-    mc_do_unit<Px, 4>(P, stage, s_mi, s_woff, pl, i, sbr, sbc, sbc * 32 + (i & 7) * 4, sbr * 32 + (i >> 3) * 4);
-  } else {
+  // ---- chroma: units of 4 x 4 when the plane is vertically subsampled, else 4 x 8 (a unit never
+  // straddles two 8x8 luma cells).  Horizontally subsampled planes are 32 samples wide per superblock:
+  // 64 units per plane, the plane comes from the thread index; full-width planes have 128 units and
+  // a thread takes one of each plane.
+  const int per_thread = P.ss_x ? 1 : 2;
+  if (P.ss_y) {     // 4:2:0, 4:4:0
 #pragma unroll 1
-    for (int pl = 1; pl < 3; pl++)
-      mc_do_unit<Px, 8>(P, stage, s_mi, s_woff, pl, ((tid >> 4) << 3) | ((tid & 15) >> 1), sbr, sbc, sbc * 64 + (tid & 15) * 4, sbr * 64 + (tid >> 4) * 8);
+    for (int it = 0; it < per_thread; it++) {
+      const int pl = P.ss_x ? 1 + (tid >> 6) : 1 + it, i = P.ss_x ? (tid & 63) : tid;
+      const int ux = P.ss_x ? (i & 7) : (i & 15), uy = P.ss_x ? (i >> 3) : (i >> 4);     // unit column / row in the superblock
+      mc_do_unit<Px, 4>(P, stage, s_mi, s_woff, pl, uy * 8 + (P.ss_x ? ux : (ux >> 1)), sbr, sbc, sbc * (64 >> P.ss_x) + ux * 4, sbr * 32 + uy * 4);
+    }
+  } else {          // 4:4:4, 4:2:2
+#pragma unroll 1
+    for (int it = 0; it < per_thread; it++) {
+      const int pl = P.ss_x ? 1 + (tid >> 6) : 1 + it, i = P.ss_x ? (tid & 63) : tid;
+      const int ux = P.ss_x ? (i & 7) : (i & 15), uy = P.ss_x ? (i >> 3) : (i >> 4);
+      mc_do_unit<Px, 8>(P, stage, s_mi, s_woff, pl, uy * 8 + (P.ss_x ? ux : (ux >> 1)), sbr, sbc, sbc * (64 >> P.ss_x) + ux * 4, sbr * 64 + uy * 8);
+    }
   }
 }
 
@@ -1376,7 +1397,8 @@ __global__ void __launch_bounds__(kWaveWarps * 32, VP9B_INTRA_MINB) k_intra(cons
   // units are ordered row-major so that a row's dependency (row-1, same plane) has a lower index
   const int sbr = unit / 3, plane = unit % 3;
   const int nsb = P.sb_cols * P.sb_rows;
-  const int n = (plane && P.ss_x) ? 32 : 64;  // superblock size in this plane
+  const int n = (plane && P.ss_x) ? 32 : 64;    // superblock width in this plane
+  const int nh = (plane && P.ss_y) ? 32 : 64;   // and its height (4:2:2 / 4:4:0: not square)
   const int stride = P.dst[plane].stride;
   Px *gplane = (Px *)P.dst[plane].ptr;
   uint32_t *prog = P.prog_intra + plane * P.sb_rows;
@@ -1411,9 +1433,9 @@ __global__ void __launch_bounds__(kWaveWarps * 32, VP9B_INTRA_MINB) k_intra(cons
       }
       left_in_smem = false;
     }
-    Px *g = gplane + (size_t)(sbr * n) * stride + sbc * n;
+    Px *g = gplane + (size_t)(sbr * nh) * stride + sbc * n;
     // interior rows can be fetched before the dependency wait (nobody else writes them)
-    const int vpr = n >> 3, vsh = n == 64 ? 3 : 2, nvec = n * vpr;
+    const int vpr = n >> 3, vsh = n == 64 ? 3 : 2, nvec = nh * vpr;
     // all loads of the tile are issued before the first one is consumed (one L2 round trip); they
     // were already issued at the end of the previous superblock when that one ran in this loop
     if (pf_sbc != sbc) {
@@ -1429,7 +1451,7 @@ __global__ void __launch_bounds__(kWaveWarps * 32, VP9B_INTRA_MINB) k_intra(cons
       if (i < nvec) *(Vec *)(T0 + (i >> vsh) * TS + (i & (vpr - 1)) * 8) = tmp[k];
     }
     if (sbc > 0 && !left_in_smem)
-      for (int r = lane; r < n; r += 32) T0[r * TS - 1] = __ldcg((const Px *)(g + (size_t)r * stride - 1));
+      for (int r = lane; r < nh; r += 32) T0[r * TS - 1] = __ldcg((const Px *)(g + (size_t)r * stride - 1));
     if (sbr > 0) {
       if (lane == 0) wait_progress(prog + sbr - 1, P.prog_base, min(sbc + 1, P.sb_cols));
       __syncwarp();
@@ -1439,7 +1461,7 @@ __global__ void __launch_bounds__(kWaveWarps * 32, VP9B_INTRA_MINB) k_intra(cons
     }
     __syncwarp();
     const vp9b_txb *list = P.txb_intra[plane] + rg.start;
-    const int px0 = sbc * n, py0 = sbr * n;
+    const int px0 = sbc * n, py0 = sbr * nh;
     typedef typename ResidT<Px>::T R;
     const R *rplane = (const R *)P.resid[plane];
     const int maxv = (1 << P.bd) - 1;
@@ -1475,7 +1497,7 @@ __global__ void __launch_bounds__(kWaveWarps * 32, VP9B_INTRA_MINB) k_intra(cons
     // The row below only ever reads this superblock's bottom row (its "above" samples): store
     // that row first and publish -- the release then waits for 64 samples, not for the whole tile
     for (int v = lane; v < vpr; v += 32)
-      __stcg((Vec *)(g + (size_t)(n - 1) * stride + v * 8), *(const Vec *)(T0 + (n - 1) * TS + v * 8));
+      __stcg((Vec *)(g + (size_t)(nh - 1) * stride + v * 8), *(const Vec *)(T0 + (nh - 1) * TS + v * 8));
     __syncwarp();
     if (lane == 0) st_release(prog + sbr, P.prog_base + (uint32_t)(sbc + 1));
     published = sbc + 1;
@@ -1483,7 +1505,7 @@ __global__ void __launch_bounds__(kWaveWarps * 32, VP9B_INTRA_MINB) k_intra(cons
     // rest of this tile is written back
     if (todo) {
       pf_sbc = c0 + __ffs(todo) - 1;
-      const Px *gn = gplane + (size_t)(sbr * n) * stride + pf_sbc * n;
+      const Px *gn = gplane + (size_t)(sbr * nh) * stride + pf_sbc * n;
 #pragma unroll
       for (int k = 0; k < kPer; k++) {
         const int i = lane + 32 * k;
@@ -1495,7 +1517,7 @@ __global__ void __launch_bounds__(kWaveWarps * 32, VP9B_INTRA_MINB) k_intra(cons
     for (int i = lane; i < nvec - vpr; i += 32)
       __stcg((Vec *)(g + (size_t)(i >> vsh) * stride + (i & (vpr - 1)) * 8), *(const Vec *)(T0 + (i >> vsh) * TS + (i & (vpr - 1)) * 8));
     __syncwarp();
-    for (int r = lane; r < n; r += 32) T0[r * TS - 1] = T0[r * TS + n - 1];
+    for (int r = lane; r < nh; r += 32) T0[r * TS - 1] = T0[r * TS + n - 1];
     left_in_smem = true;
     __syncwarp();
     if (lane == 0) st_release(done + sbr, P.prog_base + (uint32_t)(sbc + 1));   // the whole tile is out
@@ -1816,6 +1838,76 @@ __global__ void __launch_bounds__(32, 16) k_lf_warp(const __grid_constant__ FB B
       lfw_phase_fetch(C.tile, g, C.stride, C.has_next, lane);
     }
   }
+}
+
+// ------------------------------------------------------------------------------------------
+// stage 4b, 4:2:2 / 4:4:0 only: loop filter of the two chroma planes (LF_PATH_SLOW:
+// vp9_filter_block_plane_non420, vp9_loopfilter.c:1180-1239).  These samplings are rare; the kernel
+// is the reference order itself -- superblocks in raster order, per superblock all vertical edges
+// (thread = sample row, filter_selectively_vert :652-714) then all horizontal edges (thread = sample
+// column, filter_selectively_horiz :453-650) -- one CTA per plane, working in global memory.  The luma
+// plane of such frames goes through k_lf_sb with empty chroma masks.
+template <typename Px, typename FB>
+__global__ void __launch_bounds__(64) k_lf_uv_non420(const __grid_constant__ FB B) {
+  const FrameParams &P = B.f[blockIdx.z];
+  if (!P.do_lf || !P.lfm_uv) return;
+  const int plane = 1 + blockIdx.x, tid = threadIdx.x;
+  const int ss_x = P.ss_x, ss_y = P.ss_y, nw = 64 >> ss_x, nh = 64 >> ss_y, stride = P.dst[plane].stride;
+  Px *const base = (Px *)P.dst[plane].ptr;
+  __shared__ vp9b_lfm s_lvl;      // only lfl_y is used: levels compacted to [band][block column] for lf_h_unit
+  __shared__ vp9b_lfm_uv s_m;
+  for (int sbr = 0; sbr < P.sb_rows; sbr++)
+    for (int sbc = 0; sbc < P.sb_cols; sbc++) {
+      __syncthreads();             // previous superblock finished (its samples and the staged masks)
+      if (tid < 32) ((uint32_t *)&s_m)[tid] = __ldg((const uint32_t *)&P.lfm_uv[sbr * P.sb_cols + sbc] + tid);
+      __syncthreads();
+      {
+        const int b = tid >> 3, c = tid & 7;     // band b = mask row b << ss_y
+        s_lvl.lfl_y[tid] = (b << ss_y) < 8 ? s_m.lfl[((b << ss_y) << 3) + c] : 0;
+      }
+      Px *const sb = base + (size_t)(sbr * nh) * stride + sbc * nw;
+      // vertical edges: thread = sample row of the superblock
+      if (tid < nh) {
+        const int r = (tid >> 3) << ss_y;        // mask row of this band
+        if (sbr * 8 + r < P.mi_rows) {
+          uint32_t m16 = s_m.v16[r], m8 = s_m.v8[r], m4 = s_m.v4[r], m4i = s_m.v4i[r];
+          Px *s = sb + (size_t)tid * stride;
+          const uint8_t *lfl = &s_m.lfl[r << 3];
+          for (uint32_t mask = m16 | m8 | m4 | m4i; mask; mask >>= 1) {
+            const int lvl = *lfl;
+            if (m16 & 1) lf_px<Px>(s, 1, 16, P.lf_mblim[lvl], P.lf_lim[lvl], lvl >> 4, P.bd);
+            else if (m8 & 1) lf_px<Px>(s, 1, 8, P.lf_mblim[lvl], P.lf_lim[lvl], lvl >> 4, P.bd);
+            else if (m4 & 1) lf_px<Px>(s, 1, 4, P.lf_mblim[lvl], P.lf_lim[lvl], lvl >> 4, P.bd);
+            if (m4i & 1) lf_px<Px>(s + 4, 1, 4, P.lf_mblim[lvl], P.lf_lim[lvl], lvl >> 4, P.bd);
+            s += 8;
+            lfl += 1;
+            m16 >>= 1; m8 >>= 1; m4 >>= 1; m4i >>= 1;
+          }
+        }
+      }
+      __syncthreads();
+      // horizontal edges: thread = sample column; masks compacted to one row of 8 bits per band
+      if (tid < nw) {
+        LfHMasks H;
+        H.a16 = H.a8 = H.a4 = H.ai = 0;
+        H.rsh = 3; H.lstep = 1; H.nrow = 8;
+        for (int b = 0; b < (8 >> ss_y); b++) {
+          const int r = b << ss_y;
+          if (sbr * 8 + r >= P.mi_rows) break;
+          H.a16 |= (uint64_t)s_m.h16[r] << (8 * b);
+          H.a8 |= (uint64_t)s_m.h8[r] << (8 * b);
+          H.a4 |= (uint64_t)s_m.h4[r] << (8 * b);
+          H.ai |= (uint64_t)s_m.h4i[r] << (8 * b);
+        }
+        const int c = tid >> 3;
+        uint64_t todo = ((H.a16 | H.a8 | H.a4 | H.ai) >> c) & 0x0101010101010101ull;
+        while (todo) {
+          const int bit0 = (todo & 0xffffffffu) ? __ffs((uint32_t)todo) - 1 : 32 + __ffs((uint32_t)(todo >> 32)) - 1;
+          todo &= todo - 1;
+          lf_h_unit<Px>(H, s_lvl, tid, bit0 >> 3, sb + tid, stride, P.lf_lim, P.lf_mblim, P.bd);
+        }
+      }
+    }
 }
 
 // output path: 16-bit samples -> 8 bits (truncating shift, highbd_img_downshift in tools_common.c)
@@ -2221,7 +2313,7 @@ static int launch_batch(vp9gpu_ctx *const *ctxs, FB &B, int n) {
     if (P.do_lf) g_lf = std::max(g_lf, P.sb_cols);
   }
   // 8-bit 4:2:0 can take the warp-per-column loop filter (VP9B_LF_WARP=1)
-  const bool lf_warp = sizeof(Px) == 1 && B.f[0].ss_x != 0 && ctx->lf_warp;
+  const bool lf_warp = sizeof(Px) == 1 && B.f[0].ss_x != 0 && B.f[0].ss_y != 0 && ctx->lf_warp;
   // tickets: every participating frame's counter advances by the number of CTAs launched for it
   for (int i = 0; i < n; i++) {
     FrameParams &P = B.f[i];
@@ -2236,7 +2328,7 @@ static int launch_batch(vp9gpu_ctx *const *ctxs, FB &B, int n) {
     ctx->launches++;
   }
   if (prof) cudaEventRecord(ctx->prof_ev[1], st);
-  if (g_mcx && ctx->mc_flat) {
+  if (g_mcx && ctx->mc_flat && B.f[0].ss_x == B.f[0].ss_y) {
     int gx = 0, gy = 0;
     for (int i = 0; i < n; i++) {
       const FrameParams &P = B.f[i];
@@ -2287,7 +2379,9 @@ static int launch_batch(vp9gpu_ctx *const *ctxs, FB &B, int n) {
     for (int i = 0; i < n; i++) max_rows = std::max(max_rows, B.f[i].sb_rows);
     const size_t plan_bytes = ((size_t)max_rows * 49 + 15) & ~(size_t)15;   // per superblock: 24 dependent sets + chain flag
     // opt-in shared-memory limit, once per device and kernel variant: two tiles + the plan of the tallest frame (16384 / 64 rows)
-    const bool sub = B.f[0].ss_x != 0;
+    // 4:2:2 / 4:4:0: the luma plane goes through the 4:2:0 kernel (its chroma masks are empty and its
+    // 32x32 chroma tiles stay inside the planes); the chroma planes follow in k_lf_uv_non420
+    const bool sub = B.f[0].ss_x != 0 || B.f[0].ss_y != 0;
     const size_t tiles = 2 * (sub ? LfGeom<Px, true>::kTileBytes : LfGeom<Px, false>::kTileBytes);
     const unsigned abit = ((sizeof(Px) == 1 ? 4u : 8u) << (sub ? 2 : 0)) << abase;
     if (!(ctx->attr_done & abit)) {
@@ -2316,6 +2410,10 @@ static int launch_batch(vp9gpu_ctx *const *ctxs, FB &B, int n) {
       else CK(cudaLaunchKernelEx(&cfg, k_lf_sb<Px, false, FB>, B));
     }
     ctx->launches++;
+    if (B.f[0].ss_x != B.f[0].ss_y) {   // 4:2:2 / 4:4:0: the chroma planes, after the luma pass has finished
+      k_lf_uv_non420<Px, FB><<<dim3(2, 1, n), 64, 0, st>>>(B);
+      ctx->launches++;
+    }
   }
   if (prof) {
     cudaEventRecord(ctx->prof_ev[6], st);
@@ -2334,16 +2432,13 @@ static int launch_batch(vp9gpu_ctx *const *ctxs, FB &B, int n) {
 static int check_header(vp9gpu_ctx *ctx, const vp9b_frame_hdr *h) {
   if (h->magic != VP9B_MAGIC) { ctx->err = "bad packed buffer magic"; return VP9B_ERR_INVALID; }
   if (h->dst_slot < 0 || h->dst_slot >= VP9B_NUM_SLOTS) { ctx->err = "bad dst slot"; return VP9B_ERR_INVALID; }
-  if (!((h->ss_x == 1 && h->ss_y == 1) || (h->ss_x == 0 && h->ss_y == 0))) {
-    ctx->err = "only 4:2:0 / 4:4:4 supported";
-    return VP9B_ERR_UNSUP;
-  }
+  if (h->ss_x > 1 || h->ss_y > 1) { ctx->err = "bad chroma subsampling"; return VP9B_ERR_INVALID; }
   {
     // the header is the only part of a packed buffer the host can check cheaply: every section
     // must lie inside the buffer and the per-superblock tables must have the frame's geometry
     static const uint32_t elem[VP9B_SEC_COUNT] = { sizeof(vp9b_block), sizeof(vp9b_submv), sizeof(vp9b_txb), sizeof(vp9b_txb),
                                                    sizeof(vp9b_txb), sizeof(vp9b_txb), sizeof(vp9b_sbrange), 0,
-                                                   sizeof(vp9b_lfm), 0, 0, 0 };
+                                                   sizeof(vp9b_lfm), sizeof(vp9b_lfm_uv), 0, 0 };
     const uint32_t coef_elem = h->bit_depth > 8 ? 4 : 2;
     for (int i = 0; i < VP9B_SEC_COUNT; i++) {
       const uint64_t bytes = (uint64_t)h->sec[i].count * (i == VP9B_SEC_COEF ? coef_elem : elem[i]);
@@ -2355,7 +2450,8 @@ static int check_header(vp9gpu_ctx *ctx, const vp9b_frame_hdr *h) {
     const uint32_t nsb = h->sb_cols * h->sb_rows;
     if (h->sb_cols != (h->mi_cols + 7) / 8 || h->sb_rows != (h->mi_rows + 7) / 8 || h->mi_cols != (h->width + 7) / 8 ||
         h->mi_rows != (h->height + 7) / 8 || h->sec[VP9B_SEC_SB_INTRA].count != 3 * nsb ||
-        (h->lf_level && h->sec[VP9B_SEC_LFM].count != nsb) || (h->bit_depth != 8 && h->bit_depth != 10 && h->bit_depth != 12)) {
+        (h->lf_level && h->sec[VP9B_SEC_LFM].count != nsb) ||
+        (h->lf_level && h->ss_x != h->ss_y && h->sec[VP9B_SEC_LFM_UV].count != nsb) || (h->bit_depth != 8 && h->bit_depth != 10 && h->bit_depth != 12)) {
       ctx->err = "packed buffer: inconsistent frame geometry";
       return VP9B_ERR_INVALID;
     }
@@ -2408,7 +2504,7 @@ static int validate_records(const uint8_t *p, const vp9b_frame_hdr *h, std::stri
   for (int pl = 0; pl < 3; pl++) {
     const vp9b_txb *t = (const vp9b_txb *)(p + h->sec[VP9B_SEC_TXB_INTRA_Y + pl].offset);
     const uint32_t cnt = h->sec[VP9B_SEC_TXB_INTRA_Y + pl].count;
-    const int n4 = (pl && h->ss_x) ? 8 : 16;       // superblock size in 4-sample units
+    const int n4 = (pl && h->ss_x) ? 8 : 16, n4y = (pl && h->ss_y) ? 8 : 16;       // superblock size in 4-sample units
     for (uint32_t sb = 0; sb < nsb; sb++) {
       const vp9b_sbrange &r = rg[(size_t)pl * nsb + sb];
       if ((uint64_t)r.start + r.count > cnt) return bad("packed buffer: intra range out of bounds");
@@ -2417,8 +2513,8 @@ static int validate_records(const uint8_t *p, const vp9b_frame_hdr *h, std::stri
         const int bs4 = 1 << (t[i].tx & 3);
         // the wavefront kernel reconstructs a superblock inside a shared-memory tile: every record of
         // the range has to lie inside that superblock
-        if (!check_txb(t[i], pl, true) || t[i].x4 < sbc * n4 || t[i].x4 + bs4 > (sbc + 1) * n4 || t[i].y4 < sbr * n4 ||
-            t[i].y4 + bs4 > (sbr + 1) * n4)
+        if (!check_txb(t[i], pl, true) || t[i].x4 < sbc * n4 || t[i].x4 + bs4 > (sbc + 1) * n4 || t[i].y4 < sbr * n4y ||
+            t[i].y4 + bs4 > (sbr + 1) * n4y)
           return bad("packed buffer: intra transform record out of range");
       }
     }
@@ -2428,6 +2524,16 @@ static int validate_records(const uint8_t *p, const vp9b_frame_hdr *h, std::stri
     for (uint32_t sb = 0; sb < nsb; sb++)
       for (int i = 0; i < 64; i++)
         if (m[sb].lfl_y[i] > 63) return bad("packed buffer: loop-filter level out of range");
+    if (h->ss_x != h->ss_y) {
+      const vp9b_lfm_uv *mu = (const vp9b_lfm_uv *)(p + h->sec[VP9B_SEC_LFM_UV].offset);
+      for (uint32_t sb = 0; sb < nsb; sb++) {
+        for (int i = 0; i < 64; i++)
+          if (mu[sb].lfl[i] > 63) return bad("packed buffer: loop-filter level out of range");
+        // 4:2:2 / 4:4:0 chroma is filtered by its own kernel: the 4:2:0 chroma masks must be empty
+        for (int i = 0; i < 4; i++)
+          if (m[sb].left_uv[i] | m[sb].above_uv[i] | m[sb].int_4x4_uv) return bad("packed buffer: 4:2:0 chroma masks in a non-4:2:0 frame");
+      }
+    }
   }
   return 0;
 }
@@ -2526,11 +2632,13 @@ static int prepare_frame(vp9gpu_ctx *ctx, const uint8_t *d_packed, const vp9b_fr
   P.sb_intra = (const vp9b_sbrange *)(d_packed + h->sec[VP9B_SEC_SB_INTRA].offset);
   P.coef = d_packed + h->sec[VP9B_SEC_COEF].offset;
   P.lfm = (const vp9b_lfm *)(d_packed + h->sec[VP9B_SEC_LFM].offset);
+  P.lfm_uv = (h->ss_x != h->ss_y) ? (const vp9b_lfm_uv *)(d_packed + h->sec[VP9B_SEC_LFM_UV].offset) : nullptr;
   P.mi = ctx->d_mi;
   P.tmaps = ctx->tma_ok ? ctx->d_tmaps : nullptr;
   // frames with a scaled reference do not stage windows: their units use the staging buffer as scratch
   for (int r = 0; r < 3 && !h->intra_only; r++)
     if (P.ref[r].x_step_q4 != 16 || P.ref[r].y_step_q4 != 16) P.tmaps = nullptr;
+  if (h->ss_x != h->ss_y) P.tmaps = nullptr;   // 4:2:2 / 4:4:0: chroma windows are not square, no staging
   // progress counters: [0, 3*1024) intra (plane, row), [3072, 4096) loop filter.  Values are
   // prog_base + count with prog_base advancing by 2048 per frame; cleared only when it wraps.
   if (h->width > 16384 || h->height > 16384) { ctx->err = "frame too large"; return VP9B_ERR_UNSUP; }
