@@ -30,6 +30,7 @@ struct vp9b_packer {
   std::vector<uint32_t> intra_sb[3];     // superblock index of every intra record (call order)
   std::vector<int32_t> coef;             // widened; narrowed at finish for 8-bit streams
   std::vector<vp9b_lfm> lfm;
+  std::vector<vp9b_lfm_uv> lfm_uv;       // 4:2:2 / 4:4:0 frames only
   std::vector<uint8_t> out;
   int fail(const char *m) { err = m; return VP9B_ERR_INVALID; }
 };
@@ -60,6 +61,8 @@ extern "C" int vp9b_packer_begin(vp9b_packer *p, const vp9b_frame_hdr *in) {
     for (int i = 0; i < 3; i++) { p->txb_intra[i].clear(); p->intra_sb[i].clear(); }
     p->lfm.assign(h.lf_level ? (size_t)h.sb_cols * h.sb_rows : 0, vp9b_lfm());
     if (!p->lfm.empty()) memset(p->lfm.data(), 0, p->lfm.size() * sizeof(vp9b_lfm));
+    p->lfm_uv.assign((h.lf_level && h.ss_x != h.ss_y) ? (size_t)h.sb_cols * h.sb_rows : 0, vp9b_lfm_uv());
+    if (!p->lfm_uv.empty()) memset(p->lfm_uv.data(), 0, p->lfm_uv.size() * sizeof(vp9b_lfm_uv));
     p->open = true;
     return VP9B_OK;
   } catch (const std::bad_alloc &) {
@@ -158,6 +161,15 @@ extern "C" int vp9b_packer_set_lfm(vp9b_packer *p, int sb_row, int sb_col, const
   return VP9B_OK;
 }
 
+extern "C" int vp9b_packer_set_lfm_uv(vp9b_packer *p, int sb_row, int sb_col, const vp9b_lfm_uv *m) {
+  if (!p || !m || !p->open) return VP9B_ERR_INVALID;
+  const vp9b_frame_hdr &h = p->hdr;
+  if (p->lfm_uv.empty()) return VP9B_OK;      // only 4:2:2 / 4:4:0 frames with the filter on carry the section
+  if (sb_row < 0 || sb_col < 0 || sb_row >= (int)h.sb_rows || sb_col >= (int)h.sb_cols) return p->fail("loop-filter mask outside the frame");
+  p->lfm_uv[(size_t)sb_row * h.sb_cols + sb_col] = *m;
+  return VP9B_OK;
+}
+
 extern "C" int vp9b_packer_finish(vp9b_packer *p, const void **packed, size_t *bytes) {
   if (!p || !packed || !bytes || !p->open) return VP9B_ERR_INVALID;
   try {
@@ -197,6 +209,7 @@ extern "C" int vp9b_packer_finish(vp9b_packer *p, const void **packed, size_t *b
     if (h.coef_bytes == 2) src[VP9B_SEC_COEF] = { coef16.data(), 2, coef16.size() };
     else src[VP9B_SEC_COEF] = { p->coef.data(), 4, p->coef.size() };
     src[VP9B_SEC_LFM] = { p->lfm.data(), sizeof(vp9b_lfm), p->lfm.size() };
+    src[VP9B_SEC_LFM_UV] = { p->lfm_uv.data(), sizeof(vp9b_lfm_uv), p->lfm_uv.size() };
     uint64_t off = (sizeof(vp9b_frame_hdr) + 15) & ~(size_t)15;
     for (int i = 0; i < VP9B_SEC_COUNT; i++) {
       h.sec[i].offset = (uint32_t)off;

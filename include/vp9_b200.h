@@ -260,6 +260,10 @@ int vp9b_packer_add_txb(vp9b_packer *p, int plane, int inter, int x4, int y4, in
                         const int16_t *scan, int eob);
 /* Final loop-filter mask of one superblock (after vp9_adjust_mask, vp9_loopfilter.c:766-878). */
 int vp9b_packer_set_lfm(vp9b_packer *p, int sb_row, int sb_col, const vp9b_lfm *m);
+/* 4:2:2 / 4:4:0 frames only: the chroma masks of one superblock (what vp9_filter_block_plane_non420
+ * derives from the mode info, vp9_loopfilter.c:1080-1178, with its frame-edge rules applied); the uv
+ * fields of the vp9b_lfm passed to vp9b_packer_set_lfm must then be zero.  Ignored for other frames. */
+int vp9b_packer_set_lfm_uv(vp9b_packer *p, int sb_row, int sb_col, const vp9b_lfm_uv *m);
 /* Close the frame: *packed (packer-owned, valid until the next begin) is ready for
  * vp9gpu_frame_submit. */
 int vp9b_packer_finish(vp9b_packer *p, const void **packed, size_t *bytes);

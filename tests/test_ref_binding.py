@@ -23,8 +23,7 @@ VPXDEC = os.path.join(ROOT, "oracle", "_ref", "vpxdec_ref")
 # the reference tree is configured without --enable-vp9-highbitdepth (the fork's HBD transform
 # functions do not match their prototypes): 8-bit clips only
 HBD = {"hbd10", "hbd12", "p444_hbd", "scaled_hbd", "bench_hbd1080", "p422_hbd"}
-# 4:2:2 / 4:4:0: the shim does not build the vp9b_lfm_uv section yet (the reference C decoder handles them)
-NON420 = {"p422", "p440", "p440_rt"}
+NON420 = set()
 SMALL = [n for n in clip_names() if n not in HBD and not n.startswith("bench_")]
 SMALL_GPU = [n for n in SMALL if n not in NON420]
 ALL8 = [n for n in clip_names() if n not in HBD and n not in NON420]
