@@ -38,6 +38,9 @@
 #ifndef VP9B_INTRA_MINB
 #define VP9B_INTRA_MINB 1
 #endif
+#ifndef VP9B_LF_MINB
+#define VP9B_LF_MINB 5
+#endif
 
 namespace vp9b {
 
@@ -1372,8 +1375,11 @@ template <typename Px> struct IntraTileGeom {
   static constexpr size_t kWarpBytes = (kTileBytes + 32 * 33 * sizeof(int) + sizeof(IntraEdge) + 15) & ~(size_t)15;
 };
 
-template <typename Px, typename PT, typename FB>
-__global__ void __launch_bounds__(kWaveWarps * 32, VP9B_INTRA_MINB) k_intra(const __grid_constant__ FB B) {
+// MINB = CTAs per SM the kernel is compiled for: 1 (255 registers, fastest single warp) or 4 (128
+// registers, no spills): the second variant is launched when a batch brings more CTAs than fit at
+// 255 registers (2 per SM), i.e. for large batches of large 8-bit frames (4K, 32 per launch: +4 %).
+template <typename Px, typename PT, typename FB, int MINB>
+__global__ void __launch_bounds__(kWaveWarps * 32, MINB) k_intra(const __grid_constant__ FB B) {
   const FrameParams &P = B.f[blockIdx.z];
   if (!P.do_intra) return;
   extern __shared__ __align__(16) unsigned char intra_smem[];
@@ -1547,7 +1553,7 @@ VP9B_DEV unsigned long long gtime() { unsigned long long t; asm volatile("mov.u6
 // Producer: all threads store (st.cg), block barrier, one thread fence + st.release.gpu.
 // Consumer (worker c+1): one thread polls (relaxed, then one ld.acquire.gpu), block barrier, ld.cg.
 template <typename Px, bool SUB, typename FB>
-__global__ void __launch_bounds__(LfGeom<Px, SUB>::NT, SUB ? 6 : 3) k_lf_sb(const __grid_constant__ FB B) {
+__global__ void __launch_bounds__(LfGeom<Px, SUB>::NT, SUB ? VP9B_LF_MINB : 3) k_lf_sb(const __grid_constant__ FB B) {
   const FrameParams &P = B.f[blockIdx.z];
   if (!P.do_lf) return;
   typedef LfGeom<Px, SUB> G;
@@ -2359,15 +2365,18 @@ static int launch_batch(vp9gpu_ctx *const *ctxs, FB &B, int n) {
   if (g_intra) {
     const size_t ismem = IntraTileGeom<Px>::kWarpBytes * kWaveWarps;
     // opt-in shared memory size: per device, so remembered per context (one context = one device)
+    const bool dense = sizeof(Px) == 1 && (g_intra * n > 2 * ctx->num_sms || VP9B_INTRA_MINB > 1);
     const unsigned abit = (sizeof(Px) == 1 ? 1u : 2u) << abase;
     if (!(ctx->attr_done & abit)) {
-      CK(cudaFuncSetAttribute(k_intra<Px, PT, FB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ismem));
+      CK(cudaFuncSetAttribute((k_intra<Px, PT, FB, 1>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ismem));
+      CK(cudaFuncSetAttribute((k_intra<Px, PT, FB, 4>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ismem));
       ctx->attr_done |= abit;
     }
     k_intra_residual<Px, PT, FB><<<dim3(g_ires, 1, n), kResWarps * 32, 0, st>>>(B);
     ctx->launches++;
     if (prof) cudaEventRecord(ctx->prof_ev[4], st);
-    k_intra<Px, PT, FB><<<dim3(g_intra, 1, n), kWaveWarps * 32, ismem, st>>>(B);
+    if (dense) k_intra<Px, PT, FB, 4><<<dim3(g_intra, 1, n), kWaveWarps * 32, ismem, st>>>(B);
+    else k_intra<Px, PT, FB, 1><<<dim3(g_intra, 1, n), kWaveWarps * 32, ismem, st>>>(B);
     ctx->launches++;
   } else if (prof) {
     cudaEventRecord(ctx->prof_ev[4], st);
