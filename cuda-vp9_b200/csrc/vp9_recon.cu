@@ -116,8 +116,8 @@ struct FrameParams {
 
 // Frames of up to kMaxBatch different contexts that go through one launch per stage: the hardware
 // has 32 work queues, so more than 32 concurrent streams need several frames per launch.
-constexpr int kMaxBatch = VP9B_MAX_BATCH;   // 32 x 728 bytes of kernel parameters (limit: 32764)
-// Two parameter-block sizes: a launch copies the whole block (728 bytes per frame), and 23 KB of
+constexpr int kMaxBatch = VP9B_MAX_BATCH;   // 32 x 736 bytes of kernel parameters (limit: 32764)
+// Two parameter-block sizes: a launch copies the whole block (736 bytes per frame), and 23 KB of
 // parameters cost ~10 us of host time per launch -- single frames and pairs use the small block.
 template <int NB> struct FrameBatchT {
   static constexpr int kN = NB;
