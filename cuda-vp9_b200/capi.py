@@ -298,6 +298,15 @@ class GpuRecon:
         self.sync()
         return pl
 
+    def get_frame_scaled(self, slot, dst_w, dst_h, bd):
+        """Shown 4:2:0 frame scaled to dst_w x dst_h on the GPU (vpxdec --scale)."""
+        pl = _alloc_planes(dst_w, dst_h, bd, 1, 1)
+        self.L.vp9gpu_get_frame_scaled_async.argtypes = [C.c_void_p, C.c_int, C.c_uint32, C.c_uint32] + [C.c_void_p] * 3 + [C.c_int] * 2
+        self._chk(self.L.vp9gpu_get_frame_scaled_async(self.ctx, slot, dst_w, dst_h, pl[0].ctypes.data, pl[1].ctypes.data,
+                                                       pl[2].ctypes.data, pl[0].strides[0], pl[1].strides[0]))
+        self.sync()
+        return pl
+
     def set_frame(self, slot, planes, bd, sx, sy):
         y, u, v = [np.ascontiguousarray(p) for p in planes]
         self._chk(self.L.vp9gpu_set_frame(self.ctx, slot, y.shape[1], y.shape[0], bd, sx, sy, y.ctypes.data,

@@ -112,6 +112,16 @@ int vp9b_decoder_read_frame_async(vp9b_decoder *d, const vp9b_image *img, uint8_
   return e;
 }
 
+// vpxdec --scale (vpxdec.c:910-949): the shown frame scaled to a display size on the GPU
+int vp9b_decoder_read_frame_scaled(vp9b_decoder *d, const vp9b_image *img, uint32_t dst_w, uint32_t dst_h, uint8_t *y,
+                                   uint8_t *u, uint8_t *v, int y_stride, int uv_stride) {
+  if (!d || !img) return VP9B_ERR_INVALID;
+  int e = vp9gpu_get_frame_scaled_async(d->gpu, img->slot, dst_w, dst_h, y, u, v, y_stride, uv_stride);
+  if (!e) e = vp9gpu_sync(d->gpu);
+  if (e) d->err = vp9gpu_last_error(d->gpu);
+  return e;
+}
+
 int vp9b_decoder_sync(vp9b_decoder *d) {
   if (!d) return VP9B_ERR_INVALID;
   const int e = vp9gpu_sync(d->gpu);

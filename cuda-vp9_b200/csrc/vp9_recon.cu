@@ -1916,6 +1916,55 @@ __global__ void __launch_bounds__(64) k_lf_uv_non420(const __grid_constant__ FB 
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// output path: scaling of a shown 4:2:0 frame to the display size (vpxdec --scale: vpx_image_scale ->
+// libyuv I420Scale / I420Scale_16 with kFilterBox, vpxdec.c:910-949).  For every size change within
+// a factor of two libyuv reduces the box filter to its bilinear paths (ScaleFilterReduce,
+// scale_common.cc:1162-1203); those two are reproduced bit-exactly, one thread per output sample:
+//   up   (ScalePlaneBilinearUp, scale.cc:1128-1262): rows yi and yi+1 are filtered horizontally
+//        (ScaleFilterCols_C: a + ((f >> 9) * (b - a) + 64 >> 7), 16-bit samples: full 16-bit fraction),
+//        then blended vertically (InterpolateRow_C: (a * (256 - yf) + b * yf + 128) >> 8; the 16-bit
+//        row function does not round, except for yf == 128);
+//   down (ScalePlaneBilinearDown, :928-1034): vertical blend first, then the horizontal filter.
+// Positions are libyuv's 16.16 steps (ScaleSlope, scale_common.cc:1218-1288), computed on the host.
+struct ScalePlan {
+  int x0, dx, y0, dy;   // 16.16
+  int up;               // ScalePlaneBilinearUp (dst_height > src_height) or ...Down
+  int linear;           // kFilterLinear: no vertical blend
+};
+
+template <typename Px>
+VP9B_DEV int scale_hblend(int a, int b, int f) {
+  if (sizeof(Px) == 1) return a + ((((f >> 9) * (b - a)) + 0x40) >> 7);
+  return a + (int)((((long long)f * (b - a)) + 0x8000) >> 16);
+}
+template <typename Px>
+VP9B_DEV int scale_vblend(int a, int b, int yf) {
+  if (yf == 0) return a;
+  if (yf == 128) return (a + b + 1) >> 1;
+  if (sizeof(Px) == 1) return (a * (256 - yf) + b * yf + 128) >> 8;
+  return (a * (256 - yf) + b * yf) >> 8;
+}
+
+template <typename Px>
+__global__ void k_scale_plane(const Px *__restrict__ src, int sstride, int sh, Px *__restrict__ dst, int dstride, int dw, int dh,
+                              ScalePlan pl) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y;
+  if (k >= dw || j >= dh) return;
+  const long long max_y = (long long)(sh - 1) << 16;
+  long long y = (long long)pl.y0 + (long long)j * pl.dy;
+  if (y > max_y) y = max_y;
+  const long long x = (long long)pl.x0 + (long long)k * pl.dx;
+  const int yi = (int)(y >> 16), yf = pl.linear ? 0 : (int)(y >> 8) & 255;
+  const int xi = (int)(x >> 16), f = (int)(x & 0xffff);
+  const Px *r0 = src + (size_t)yi * sstride + xi, *r1 = r0 + (yf ? sstride : 0);
+  const int a0 = r0[0], b0 = r0[1], a1 = r1[0], b1 = r1[1];
+  int v;
+  if (pl.up) v = scale_vblend<Px>(scale_hblend<Px>(a0, b0, f), scale_hblend<Px>(a1, b1, f), yf);
+  else v = scale_hblend<Px>(scale_vblend<Px>(a0, a1, yf), scale_vblend<Px>(b0, b1, yf), f);
+  dst[(size_t)j * dstride + k] = (Px)v;
+}
+
 // output path: 16-bit samples -> 8 bits (truncating shift, highbd_img_downshift in tools_common.c)
 __global__ void k_downshift(const uint16_t *__restrict__ src, int sstride, uint8_t *__restrict__ dst, int dstride, int w,
                             int h, int shift) {
@@ -2140,6 +2189,80 @@ extern "C" int vp9gpu_get_frame_8bit_async(vp9gpu_ctx *ctx, int slot, uint8_t *y
     ctx->launches++;
     CK(cudaMemcpy2DAsync(out[p], p ? uv_stride : y_stride, ctx->d_out8 + off[p], ps[p], pw[p], ph[p], cudaMemcpyDeviceToHost,
                          ctx->stream));
+  }
+  CK(cudaGetLastError());
+  return 0;
+}
+
+// libyuv's choice of algorithm and 16.16 steps for one plane (ScaleFilterReduce + ScalePlane's dispatch
+// + ScaleSlope); false: a path that is not reproduced here (box kernels of the 3/4, 1/2, 3/8, 1/4 and
+// < 1/2 ratios, height-only changes, one-sample planes)
+static bool scale_plan(int sw, int sh, int dw, int dh, ScalePlan &p) {
+  memset(&p, 0, sizeof(p));
+  if (sw < 2 || sh < 1 || dw < 1 || dh < 1) return false;
+  if (!(dw * 2 >= sw && dh * 2 >= sh)) return false;             // stays kFilterBox: ScalePlaneBox
+  bool linear = sh == 1 || dh == sh || dh * 3 == sh;
+  if (linear && (dw == sw || dw * 3 == sw)) return false;        // reduced to kFilterNone
+  if (dw == sw) return false;                                     // ScalePlaneVertical
+  if (dw <= sw && dh <= sh) {
+    if ((4 * dw == 3 * sw && 4 * dh == 3 * sh) || (2 * dw == sw && 2 * dh == sh) || (8 * dw == 3 * sw && 8 * dh == 3 * sh)) return false;
+  }
+  auto fixed_div = [](int num, int div) { return (int)(((int64_t)num << 16) / div); };
+  auto fixed_div1 = [](int num, int div) { return (int)((((int64_t)num << 16) - 0x00010001) / (div - 1)); };
+  if (dw <= sw) { p.dx = fixed_div(sw, dw); p.x0 = (p.dx >> 1) - 32768; }
+  else if (dw > 1) { p.dx = fixed_div1(sw, dw); p.x0 = 0; }
+  if (linear) { p.dy = fixed_div(sh, dh); p.y0 = p.dy >> 1; }
+  else if (dh <= sh) { p.dy = fixed_div(sh, dh); p.y0 = (p.dy >> 1) - 32768; }
+  else if (dh > 1) { p.dy = fixed_div1(sh, dh); p.y0 = 0; }
+  p.linear = linear;
+  p.up = dh > sh;
+  // both paths clamp y to the last row only from above; a negative start cannot happen (dy >= 65536 when centred)
+  return true;
+}
+
+extern "C" int vp9gpu_get_frame_scaled_async(vp9gpu_ctx *ctx, int slot, uint32_t dst_w, uint32_t dst_h, uint8_t *y, uint8_t *u,
+                                             uint8_t *v, int y_stride, int uv_stride) {
+  if (!ctx || slot < 0 || slot >= VP9B_NUM_SLOTS || !ctx->slot[slot].valid || !dst_w || !dst_h) return VP9B_ERR_INVALID;
+  const DevFrame &f = ctx->slot[slot];
+  if (f.width == dst_w && f.height == dst_h) return vp9gpu_get_frame_async(ctx, slot, y, u, v, y_stride, uv_stride);
+  if (!(f.ss_x == 1 && f.ss_y == 1)) { ctx->err = "output scaling: 4:2:0 only (as vpxdec's libyuv_scale)"; return VP9B_ERR_UNSUP; }
+  CK(cudaSetDevice(ctx->device));
+  ScalePlan plan[3];
+  int sw[3], sh[3], dw[3], dh[3], ps[3];
+  size_t off[3], total = 0;
+  for (int p = 0; p < 3; p++) {
+    sw[p] = p ? (int)((f.width + 1) >> 1) : (int)f.width;
+    sh[p] = p ? (int)((f.height + 1) >> 1) : (int)f.height;
+    dw[p] = p ? (int)((dst_w + 1) >> 1) : (int)dst_w;
+    dh[p] = p ? (int)((dst_h + 1) >> 1) : (int)dst_h;
+    if (!scale_plan(sw[p], sh[p], dw[p], dh[p], plan[p])) {
+      ctx->err = "output scaling: this size ratio takes one of libyuv's box kernels, which are not implemented";
+      return VP9B_ERR_UNSUP;
+    }
+    ps[p] = (dw[p] * f.bps + 127) & ~127;
+    off[p] = total;
+    total += (size_t)ps[p] * dh[p];
+  }
+  if (ctx->out8_bytes < total) {     // shares the staging buffer of the 8-bit output path
+    CK(cudaStreamSynchronize(ctx->stream));
+    cudaFree(ctx->d_out8);
+    ctx->d_out8 = nullptr;
+    ctx->out8_bytes = 0;
+    CK(cudaMalloc(&ctx->d_out8, total));
+    ctx->out8_bytes = total;
+  }
+  uint8_t *out[3] = { y, u, v };
+  for (int p = 0; p < 3; p++) {
+    const dim3 blk(128), grd((dw[p] + 127) / 128, dh[p]);
+    if (f.bps == 1)
+      k_scale_plane<uint8_t><<<grd, blk, 0, ctx->stream>>>((const uint8_t *)f.pl[p].ptr, f.pl[p].stride, sh[p], ctx->d_out8 + off[p], ps[p],
+                                                             dw[p], dh[p], plan[p]);
+    else
+      k_scale_plane<uint16_t><<<grd, blk, 0, ctx->stream>>>((const uint16_t *)f.pl[p].ptr, f.pl[p].stride, sh[p],
+                                                              (uint16_t *)(ctx->d_out8 + off[p]), ps[p] / 2, dw[p], dh[p], plan[p]);
+    ctx->launches++;
+    CK(cudaMemcpy2DAsync(out[p], p ? uv_stride : y_stride, ctx->d_out8 + off[p], ps[p], (size_t)dw[p] * f.bps, dh[p],
+                         cudaMemcpyDeviceToHost, ctx->stream));
   }
   CK(cudaGetLastError());
   return 0;

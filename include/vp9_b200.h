@@ -201,6 +201,14 @@ int vp9gpu_get_frame_async(vp9gpu_ctx *ctx, int slot, uint8_t *y, uint8_t *u, ui
  * is identical to it. */
 int vp9gpu_get_frame_8bit_async(vp9gpu_ctx *ctx, int slot, uint8_t *y, uint8_t *u, uint8_t *v, int y_stride,
                                 int uv_stride);
+/* Output scaled to a display size (vpxdec --scale: vpx_image_scale -> libyuv I420Scale[_16] with
+ * kFilterBox, vpxdec.c:910-949), done on the GPU before the copy; dst_w x dst_h luma samples, 4:2:0
+ * only (as in vpxdec).  Bit-exact with libyuv's C paths for every change within a factor of two that
+ * libyuv handles with its bilinear code (any resize of a VP9 stream scaled back to its first size);
+ * the ratios it gives to box kernels (exactly 3/4, 1/2, 3/8, below 1/2, height-only) return
+ * VP9B_ERR_UNSUP.  Asynchronous like vp9gpu_get_frame_async; same size = plain copy. */
+int vp9gpu_get_frame_scaled_async(vp9gpu_ctx *ctx, int slot, uint32_t dst_w, uint32_t dst_h, uint8_t *y, uint8_t *u,
+                                  uint8_t *v, int y_stride, int uv_stride);
 /* Tickets: vp9gpu_mark() records a point on the ctx stream (e.g. right after a get_frame_async),
  * vp9gpu_wait() blocks until that point has been reached.  Lets a host thread wait for the frame
  * it handed out N frames ago instead of draining the stream.  Up to 64 tickets may be pending. */
@@ -319,6 +327,10 @@ int vp9b_decoder_read_frame(vp9b_decoder *d, const vp9b_image *img, uint8_t *y, 
 /* Asynchronous variant (see vp9gpu_get_frame_async) and the matching wait. */
 int vp9b_decoder_read_frame_async(vp9b_decoder *d, const vp9b_image *img, uint8_t *y, uint8_t *u, uint8_t *v,
                                   int y_stride, int uv_stride);
+/* The shown frame scaled to dst_w x dst_h (vpxdec --scale; see vp9gpu_get_frame_scaled_async);
+ * synchronous. */
+int vp9b_decoder_read_frame_scaled(vp9b_decoder *d, const vp9b_image *img, uint32_t dst_w, uint32_t dst_h, uint8_t *y,
+                                   uint8_t *u, uint8_t *v, int y_stride, int uv_stride);
 int vp9b_decoder_sync(vp9b_decoder *d);
 /* Ticket of everything enqueued so far / wait for a ticket (see vp9gpu_mark, vp9gpu_wait). */
 int vp9b_decoder_mark(vp9b_decoder *d, uint64_t *ticket);
