@@ -79,6 +79,17 @@ class BoolReader {
   }
   inline void fill() {
     int shift = 64 - 8 - (count_ + 8);
+    if (end_ - buf_ >= 8 && shift >= 0) {   // whole bytes from one big-endian 64-bit load
+      uint64_t w;
+      memcpy(&w, buf_, 8);
+      w = __builtin_bswap64(w);
+      const int nbytes = (shift >> 3) + 1;            // 1..8 bytes fit
+      const int nbits = nbytes * 8;
+      value_ |= (w >> (64 - nbits)) << (shift + 8 - nbits);
+      buf_ += nbytes;
+      count_ += nbits;
+      return;
+    }
     while (shift >= 0) {
       uint64_t b = 0;
       if (buf_ < end_) b = *buf_++; else overrun_++;
@@ -86,6 +97,9 @@ class BoolReader {
       value_ |= b << shift;
       shift -= 8;
     }
+  }
+  static inline int norm_shift(uint32_t range) {
+    return __builtin_clz(range) - 24;   // range is 1..255 (LZCNT; the table of bitreader.c costs a load)
   }
   inline int read(int prob) {
     const uint32_t split = (range_ * (uint32_t)prob + (256 - (uint32_t)prob)) >> 8;
@@ -100,11 +114,27 @@ class BoolReader {
       range_ = split;
       bit = 0;
     }
-    const int shift = kVpxNorm[range_];
+    const int shift = norm_shift(range_);
     range_ <<= shift;
     value_ <<= shift;
     count_ -= shift;
     return bit;
+  }
+  // Same arithmetic without a data-dependent branch: for symbols whose value only feeds arithmetic
+  // (signs, the extra bits of the category tokens) -- a coin-flip branch there costs more than the
+  // select.
+  inline int read_nb(int prob) {
+    const uint32_t split = (range_ * (uint32_t)prob + (256 - (uint32_t)prob)) >> 8;
+    if (count_ < 0) fill();
+    const uint64_t bigsplit = (uint64_t)split << 56;
+    const uint64_t m = (uint64_t)0 - (uint64_t)(value_ >= bigsplit);
+    range_ = split + ((range_ - 2 * split) & (uint32_t)m);
+    value_ -= bigsplit & m;
+    const int shift = norm_shift(range_);
+    range_ <<= shift;
+    value_ <<= shift;
+    count_ -= shift;
+    return (int)(m & 1);
   }
   inline int read_bit() { return read(128); }
   inline int read_literal(int bits) {
@@ -692,6 +722,8 @@ struct TileCtx {
   void append_sub8x8_mvs_for_idx(const int8_t *search, int b_mode, int block, int ref, Mv *best);
   int get_mode_context(const int8_t *search);
   int decode_block_tokens(int plane, int x, int y, int tx_size, int tx_type, uint32_t *coef_off);
+  template <bool HBD, bool COUNTS>
+  int decode_block_tokens_t(int plane, int x, int y, int tx_size, int tx_type, uint32_t *coef_off);
   void residual_and_record();
   void build_lf_mask();
   bool seg_active(int seg, int feat) const {
@@ -1470,6 +1502,16 @@ void TileCtx::read_inter_frame_mode_info() {
 // decode_coefs + vp9_decode_block_tokens (vp9_detokenize.c:115-333).  Coefficients are written
 // to the packed stream in scan order (positions 0..eob-1) already dequantised.
 int TileCtx::decode_block_tokens(int plane, int x, int y, int tx_size, int tx_type, uint32_t *coef_off) {
+  // four copies of the token loop: sample width and "collect counts" are frame constants
+  const bool hbd = P->bit_depth_ > 8;
+  if (P->do_counts_)
+    return hbd ? decode_block_tokens_t<true, true>(plane, x, y, tx_size, tx_type, coef_off)
+               : decode_block_tokens_t<false, true>(plane, x, y, tx_size, tx_type, coef_off);
+  return hbd ? decode_block_tokens_t<true, false>(plane, x, y, tx_size, tx_type, coef_off)
+             : decode_block_tokens_t<false, false>(plane, x, y, tx_size, tx_type, coef_off);
+}
+template <bool HBD, bool COUNTS>
+int TileCtx::decode_block_tokens_t(int plane, int x, int y, int tx_size, int tx_type, uint32_t *coef_off) {
   const int ss_x = plane ? P->ss_x_ : 0, ss_y = plane ? P->ss_y_ : 0;
   uint8_t *a = &P->above_ctx_[plane][((mi_col * 2) >> ss_x) + x];
   uint8_t *l = &left_ctx[plane][(((mi_row * 2) & 15) >> ss_y) + y];
@@ -1508,14 +1550,14 @@ int TileCtx::decode_block_tokens(int plane, int x, int y, int tx_size, int tx_ty
   const uint8_t(*coef_probs)[6][3] = P->fc_.coef[tx_size][type][ref];
   uint32_t(*coef_counts)[6][4] = O->counts.coef[tx_size][type][ref];
   uint32_t(*eob_branch)[6] = O->counts.eob_branch[tx_size][type][ref];
-  const bool counts = P->do_counts_;
+  constexpr bool counts = COUNTS;
   const uint8_t *band_translate = tx_size == TX_4X4 ? kCoefBand4x4 : kCoefBand8x8Plus;
   const int dq_shift = (tx_size == TX_32X32);
   const int16_t *dq = plane ? P->uv_dequant_[mi->segment_id] : P->y_dequant_[mi->segment_id];
   const int bd = P->bit_depth_;
   const uint8_t *cat6_prob = bd == 12 ? kCat6ProbHigh12 : (bd == 10 ? kCat6ProbHigh12 + 2 : kCat6Prob);
   const int cat6_bits = bd == 12 ? 18 : (bd == 10 ? 16 : 14);
-  const bool hbd = bd > 8;
+  constexpr bool hbd = HBD;
   // coefficient stream: grow geometrically, write through raw pointers (no per-block zero fill)
   size_t base;
   if (hbd) {
@@ -1534,7 +1576,7 @@ int TileCtx::decode_block_tokens(int plane, int x, int y, int tx_size, int tx_ty
   const uint8_t *prob;
   auto read_coeff = [&](const uint8_t *probs, int nbits) {
     int val = 0;
-    for (int i = 0; i < nbits; ++i) val = (val << 1) | r.read(probs[i]);
+    for (int i = 0; i < nbits; ++i) val = (val << 1) | r.read_nb(probs[i]);
     return val;
   };
   while (c < max_eob) {
@@ -1594,7 +1636,10 @@ int TileCtx::decode_block_tokens(int plane, int x, int y, int tx_size, int tx_ty
       token_cache[scan[c]] = 1;
       v = dqv >> dq_shift;
     }
-    if (r.read_bit()) v = -v;
+    {
+      const int sgn = -r.read_nb(128);
+      v = (v ^ sgn) - sgn;
+    }
     if (hbd) o32[c] = v; else o16[c] = (int16_t)v;
     ++c;
     ctx = (1 + token_cache[nb[2 * c]] + token_cache[nb[2 * c + 1]]) >> 1;

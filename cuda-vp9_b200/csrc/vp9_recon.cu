@@ -931,26 +931,91 @@ __global__ void __launch_bounds__(128, sizeof(Px) == 1 ? 8 : 4) k_inter_pred_fla
 // stages 2/3: inverse transform + add, one warp per transform block.  Rows then columns
 // (vpx_idctNxN_add_c), final shift 4/5/6/6, clip to the pixel range.  tbuf: per-warp shared
 // scratch of N*(N+1) ints.
-// where the samples of an inverse transform go: added to the prediction in place, or stored as a
-// residual plane for the intra wavefront (which then only predicts and adds)
-template <typename Px> struct SinkAdd {
-  Px *d; int stride, maxv;
-  VP9B_DEV void put(int r, int c, int v) const {
-    Px *q = d + (size_t)r * stride + c;
-    *q = (Px)clampi((int)*q + v, 0, maxv);
-  }
-};
-template <typename R> struct SinkRaw {
-  R *d; int stride;
-  VP9B_DEV void put(int r, int c, int v) const { d[(size_t)r * stride + c] = (R)v; }
-};
+// Four consecutive samples of a row: residuals added to the prediction in place (one 32-/64-bit
+// read-modify-write), or stored as a residual plane for the intra wavefront (which then only
+// predicts and adds).
+VP9B_DEV void add4_clip(uint8_t *p, int v0, int v1, int v2, int v3, int) {
+  const uint32_t w = *(const uint32_t *)p;
+  const int r0 = clampi((int)(w & 0xff) + v0, 0, 255), r1 = clampi((int)((w >> 8) & 0xff) + v1, 0, 255);
+  const int r2 = clampi((int)((w >> 16) & 0xff) + v2, 0, 255), r3 = clampi((int)(w >> 24) + v3, 0, 255);
+  *(uint32_t *)p = (uint32_t)r0 | ((uint32_t)r1 << 8) | ((uint32_t)r2 << 16) | ((uint32_t)r3 << 24);
+}
+VP9B_DEV void add4_clip(uint16_t *p, int v0, int v1, int v2, int v3, int maxv) {
+  const uint2 w = *(const uint2 *)p;
+  const int r0 = clampi((int)(w.x & 0xffff) + v0, 0, maxv), r1 = clampi((int)(w.x >> 16) + v1, 0, maxv);
+  const int r2 = clampi((int)(w.y & 0xffff) + v2, 0, maxv), r3 = clampi((int)(w.y >> 16) + v3, 0, maxv);
+  *(uint2 *)p = make_uint2((uint32_t)r0 | ((uint32_t)r1 << 16), (uint32_t)r2 | ((uint32_t)r3 << 16));
+}
+VP9B_DEV void put4_raw(int16_t *p, int v0, int v1, int v2, int v3) {
+  *(uint2 *)p = make_uint2(((uint32_t)v0 & 0xffff) | ((uint32_t)v1 << 16), ((uint32_t)v2 & 0xffff) | ((uint32_t)v3 << 16));
+}
+VP9B_DEV void put4_raw(int32_t *p, int v0, int v1, int v2, int v3) { *(int4 *)p = make_int4(v0, v1, v2, v3); }
 template <typename Px> struct ResidT { typedef int16_t T; };
 template <> struct ResidT<uint16_t> { typedef int32_t T; };
 
-template <typename PT, int N, typename Sink>
-VP9B_DEV void warp_itx(int *tbuf, const void *coef_base, int coef_bytes, const vp9b_txb &t, const Sink &sink,
-                       int lossless, int lane) {
+// Rows then columns of the blocks a warp holds in shared memory (tb = this lane's block, N + 1 ints
+// per row, lane l = row / column l), in place: afterwards tb[r * S + c] is the final residual
+// (vpx_idctNxN_add_c: final shift 4/5/6/6).  xf = this lane takes part; lead = warp-uniform eob class.
+template <typename PT, int N>
+VP9B_DEV void itx_2d_inplace(int *tb, int l, bool xf, int lead, bool row_adst, bool col_adst) {
   constexpr int S = N + 1;
+  constexpr int shift = (N == 4) ? 4 : (N == 8 ? 5 : 6);
+#pragma unroll 1
+  for (int pass = 0; pass < 2; pass++) {   // one copy of the butterflies for both passes
+    if (xf && (pass || l < lead)) {        // rows lead.. are zero and stay zero
+      int out[N];
+      itx_line_lead<PT, N>(tb + l * (pass ? 1 : S), pass ? S : 1, pass ? col_adst : row_adst, lead, out);
+      if (pass == 0) {
+#pragma unroll
+        for (int j = 0; j < N; j++) tb[l * S + j] = out[j];
+      } else {
+#pragma unroll
+        for (int j = 0; j < N; j++) tb[j * S + l] = (out[j] + (1 << (shift - 1))) >> shift;
+      }
+    }
+    __syncwarp();
+  }
+}
+// vpx_iwht4x4_16_add_c (inv_txfm.c:18-66), same convention
+VP9B_DEV void iwht_2d_inplace(int *tb, int l, bool xf) {
+  constexpr int S = 5;
+  int o[4];
+  if (xf) {
+    iwht4(tb[l * S + 0] >> 2, tb[l * S + 1] >> 2, tb[l * S + 2] >> 2, tb[l * S + 3] >> 2, o);
+    for (int j = 0; j < 4; j++) tb[l * S + j] = o[j];
+  }
+  __syncwarp();
+  if (xf) {
+    iwht4(tb[0 * S + l], tb[1 * S + l], tb[2 * S + l], tb[3 * S + l], o);
+    for (int j = 0; j < 4; j++) tb[j * S + l] = o[j];
+  }
+  __syncwarp();
+}
+template <int N>
+VP9B_DEV void scatter_coefs(int *tb, const void *coef_base, int coef_bytes, uint32_t coef_off, int eob, const int16_t *scan,
+                            int l, int step) {
+  constexpr int S = N + 1;
+  if (coef_bytes == 2) {
+    const int16_t *c = (const int16_t *)coef_base + coef_off;
+    for (int i = l; i < eob; i += step) {
+      const int pos = scan[i];
+      tb[(pos / N) * S + (pos % N)] = c[i];
+    }
+  } else {
+    const int32_t *c = (const int32_t *)coef_base + coef_off;
+    for (int i = l; i < eob; i += step) {
+      const int pos = scan[i];
+      tb[(pos / N) * S + (pos % N)] = c[i];
+    }
+  }
+}
+
+// inverse transform of one intra block into the residual plane (one warp per block); rows of the
+// plane are written as 4-sample vectors
+template <typename PT, int N, typename R>
+VP9B_DEV void warp_itx(int *tbuf, const void *coef_base, int coef_bytes, const vp9b_txb &t, R *dst, int stride,
+                       int lossless, int lane) {
+  constexpr int S = N + 1, Q = N / 4;     // quads per row
   const int tx_size = t.tx & 3, tx_type = lossless ? 0 : ((t.tx >> 2) & 3);
   const int eob = t.eob;
   if (eob == 1 && tx_type == 0 && !lossless) {  // DC only: vpx_idctNxN_1_add_c
@@ -958,91 +1023,49 @@ VP9B_DEV void warp_itx(int *tbuf, const void *coef_base, int coef_bytes, const v
     const int dc = coef_bytes == 2 ? (int)((const int16_t *)coef_base)[t.coef_off] : ((const int32_t *)coef_base)[t.coef_off];
     const int v1 = rs14<PT>((PT)dc * (PT)c16);
     const int a1 = (rs14<PT>((PT)v1 * (PT)c16) + (1 << (sh - 1))) >> sh;
-    for (int p = lane; p < N * N; p += 32) sink.put(p / N, p % N, a1);
-    __syncwarp();
+    for (int q = lane; q < N * Q; q += 32) put4_raw(dst + (size_t)(q / Q) * stride + (q % Q) * 4, a1, a1, a1, a1);
     return;
   }
   for (int i = lane; i < N * S; i += 32) tbuf[i] = 0;
   __syncwarp();
-  const int16_t *scan = d_scan + scan_offset(tx_size, tx_type);
-  if (coef_bytes == 2) {
-    const int16_t *c = (const int16_t *)coef_base + t.coef_off;
-    for (int i = lane; i < eob; i += 32) {
-      const int pos = scan[i];
-      tbuf[(pos / N) * S + (pos % N)] = c[i];
-    }
+  scatter_coefs<N>(tbuf, coef_base, coef_bytes, t.coef_off, eob, d_scan + scan_offset(tx_size, tx_type), lane, 32);
+  __syncwarp();
+  if (N == 4 && lossless) {
+    iwht_2d_inplace(tbuf, lane, lane < 4);
   } else {
-    const int32_t *c = (const int32_t *)coef_base + t.coef_off;
-    for (int i = lane; i < eob; i += 32) {
-      const int pos = scan[i];
-      tbuf[(pos / N) * S + (pos % N)] = c[i];
-    }
+    const bool row_adst = (N < 32) && (tx_type & 2), col_adst = (N < 32) && (tx_type & 1);
+    itx_2d_inplace<PT, N>(tbuf, lane, lane < N, eob_lead<N>(tx_type, eob), row_adst, col_adst);
   }
-  __syncwarp();
-  if (lossless) {  // vpx_iwht4x4_16_add_c (inv_txfm.c:18-66)
-    if (N == 4) {
-      int o[4];
-      if (lane < 4) {
-        iwht4(tbuf[lane * S + 0] >> 2, tbuf[lane * S + 1] >> 2, tbuf[lane * S + 2] >> 2, tbuf[lane * S + 3] >> 2, o);
-        for (int j = 0; j < 4; j++) tbuf[lane * S + j] = o[j];
-      }
-      __syncwarp();
-      if (lane < 4) {
-        iwht4(tbuf[0 * S + lane], tbuf[1 * S + lane], tbuf[2 * S + lane], tbuf[3 * S + lane], o);
-        for (int j = 0; j < 4; j++) sink.put(j, lane, o[j]);
-      }
-    }
-    __syncwarp();
-    return;
-  }
-  const bool row_adst = (N < 32) && (tx_type & 2), col_adst = (N < 32) && (tx_type & 1);
-  // rows: lane r transforms row r (all-zero rows stay zero)
-  if (lane < N) {
-    int in[N], out[N];
-    int any = 0;
-#pragma unroll
-    for (int j = 0; j < N; j++) { in[j] = tbuf[lane * S + j]; any |= in[j]; }
-    if (any) {
-      txfm1d<PT, N>(in, out, row_adst);
-#pragma unroll
-      for (int j = 0; j < N; j++) tbuf[lane * S + j] = out[j];
-    }
-  }
-  __syncwarp();
-  // columns
-  constexpr int shift = (N == 4) ? 4 : (N == 8 ? 5 : 6);
-  if (lane < N) {
-    int in[N], out[N];
-#pragma unroll
-    for (int j = 0; j < N; j++) in[j] = tbuf[j * S + lane];
-    txfm1d<PT, N>(in, out, col_adst);
-#pragma unroll
-    for (int j = 0; j < N; j++) sink.put(j, lane, (out[j] + (1 << (shift - 1))) >> shift);
+  for (int q = lane; q < N * Q; q += 32) {
+    const int r = q / Q, c4 = (q % Q) * 4;
+    const int *tv = tbuf + r * S + c4;
+    put4_raw(dst + (size_t)r * stride + c4, tv[0], tv[1], tv[2], tv[3]);
   }
   __syncwarp();
 }
 
-// inverse transform of one intra block into the residual plane
 template <typename Px, typename PT>
 VP9B_DEV void warp_intra_residual(const FrameParams &P, int *tbuf, const vp9b_txb &t, int plane, int lane) {
   typedef typename ResidT<Px>::T R;
   const int stride = P.dst[plane].stride;
-  const SinkRaw<R> sink = { (R *)P.resid[plane] + (size_t)t.y4 * 4 * stride + t.x4 * 4, stride };
+  R *dst = (R *)P.resid[plane] + (size_t)t.y4 * 4 * stride + t.x4 * 4;
   const int cb = sizeof(Px) == 1 ? 2 : 4;
   switch (t.tx & 3) {
-    case 0: warp_itx<PT, 4>(tbuf, P.coef, cb, t, sink, P.lossless, lane); break;
-    case 1: warp_itx<PT, 8>(tbuf, P.coef, cb, t, sink, 0, lane); break;
-    case 2: warp_itx<PT, 16>(tbuf, P.coef, cb, t, sink, 0, lane); break;
-    default: warp_itx<PT, 32>(tbuf, P.coef, cb, t, sink, 0, lane); break;
+    case 0: warp_itx<PT, 4>(tbuf, P.coef, cb, t, dst, stride, P.lossless, lane); break;
+    case 1: warp_itx<PT, 8>(tbuf, P.coef, cb, t, dst, stride, 0, lane); break;
+    case 2: warp_itx<PT, 16>(tbuf, P.coef, cb, t, dst, stride, 0, lane); break;
+    default: warp_itx<PT, 32>(tbuf, P.coef, cb, t, dst, stride, 0, lane); break;
   }
 }
 
+// Inter residuals: a warp takes 32 / N blocks of size N (lane = (block, row / column)), transforms
+// them in shared memory and adds them to the prediction row-wise, four samples per access.
 template <typename Px, typename PT, int N>
 VP9B_DEV void group_itx_add(int *tbuf, const FrameParams &P, int first, int count, int lane) {
-  constexpr int S = N + 1;
+  constexpr int S = N + 1, Q = N / 4, QB = N * Q, NSUB = 32 / N;
   const int sub = lane / N, l = lane % N;
   int *tb = tbuf + sub * (N * S);
-  bool active = sub < count;
+  const bool active = sub < count;
   vp9b_txb t;
   t.coef_off = 0; t.x4 = t.y4 = 0; t.eob = 0; t.tx = 0; t.aux = 0;
   if (active) t = P.txb_inter[first + sub];
@@ -1057,73 +1080,34 @@ VP9B_DEV void group_itx_add(int *tbuf, const FrameParams &P, int first, int coun
   // DC-only DCT blocks (more than half of all inter blocks): both passes reduce to one value
   // (vpx_idctNxN_1_add_c, inv_txfm.c:159-173 and the 8/16/32 twins)
   const bool dc_only = active && eob == 1 && tx_type == 0 && !lossless;
+  int fill = 0;
   if (dc_only) {
     const int dc = sizeof(Px) == 1 ? (int)((const int16_t *)P.coef)[t.coef_off] : ((const int32_t *)P.coef)[t.coef_off];
     const int v1 = rs14<PT>((PT)dc * (PT)c16);
-    const int a1 = (rs14<PT>((PT)v1 * (PT)c16) + (1 << (shift - 1))) >> shift;
-#pragma unroll 4
-    for (int j = 0; j < N; j++) {
-      Px *p = dst + (size_t)j * stride + l;
-      *p = (Px)clampi((int)*p + a1, 0, maxv);
-    }
+    fill = (rs14<PT>((PT)v1 * (PT)c16) + (1 << (shift - 1))) >> shift;
   }
-  active = active && !dc_only;
+  const bool xf = active && !dc_only;
   if (active)
-    for (int i = l; i < N * S; i += N) tb[i] = 0;
+    for (int i = l; i < N * S; i += N) tb[i] = fill;
   __syncwarp();
-  if (active) {
-    const int16_t *scan = d_scan + scan_offset(t.tx & 3, tx_type);
-    if (sizeof(Px) == 1) {
-      const int16_t *c = (const int16_t *)P.coef + t.coef_off;
-      for (int i = l; i < eob; i += N) {
-        const int pos = scan[i];
-        tb[(pos / N) * S + (pos % N)] = c[i];
-      }
-    } else {
-      const int32_t *c = (const int32_t *)P.coef + t.coef_off;
-      for (int i = l; i < eob; i += N) {
-        const int pos = scan[i];
-        tb[(pos / N) * S + (pos % N)] = c[i];
-      }
-    }
-  }
+  if (xf) scatter_coefs<N>(tb, P.coef, sizeof(Px) == 1 ? 2 : 4, t.coef_off, eob, d_scan + scan_offset(t.tx & 3, tx_type), l, N);
   __syncwarp();
-  if (N == 4 && lossless) {  // vpx_iwht4x4_16_add_c (inv_txfm.c:18-66)
-    int o[4];
-    if (active) {
-      iwht4(tb[l * S + 0] >> 2, tb[l * S + 1] >> 2, tb[l * S + 2] >> 2, tb[l * S + 3] >> 2, o);
-      for (int j = 0; j < 4; j++) tb[l * S + j] = o[j];
-    }
-    __syncwarp();
-    if (active) {
-      iwht4(tb[0 * S + l], tb[1 * S + l], tb[2 * S + l], tb[3 * S + l], o);
-      for (int j = 0; j < 4; j++) dst[j * stride + l] = (Px)clampi((int)dst[j * stride + l] + o[j], 0, maxv);
-    }
-    __syncwarp();
-    return;
+  if (N == 4 && lossless) {
+    iwht_2d_inplace(tb, l, xf);
+  } else {
+    // eob class: the blocks of a warp take the widest one among them so that the warp stays converged
+    const int lead = __reduce_max_sync(0xffffffffu, xf ? eob_lead<N>(tx_type, eob) : 0);
+    if (lead) itx_2d_inplace<PT, N>(tb, l, xf, lead, (N < 32) && (tx_type & 2), (N < 32) && (tx_type & 1));
   }
-  const bool row_adst = (N < 32) && (tx_type & 2), col_adst = (N < 32) && (tx_type & 1);
-  if (active) {  // rows: lane l transforms row l (all-zero rows stay zero)
-    int in[N], out[N];
-    int any = 0;
+  // add: quad q of the warp = (block, row, 4 columns); the block's destination comes from its first lane
 #pragma unroll
-    for (int j = 0; j < N; j++) { in[j] = tb[l * S + j]; any |= in[j]; }
-    if (any) {
-      txfm1d<PT, N>(in, out, row_adst);
-#pragma unroll
-      for (int j = 0; j < N; j++) tb[l * S + j] = out[j];
-    }
-  }
-  __syncwarp();
-  if (active) {  // columns
-    int in[N], out[N];
-#pragma unroll
-    for (int j = 0; j < N; j++) in[j] = tb[j * S + l];
-    txfm1d<PT, N>(in, out, col_adst);
-#pragma unroll
-    for (int j = 0; j < N; j++) {
-      Px *p = dst + (size_t)j * stride + l;
-      *p = (Px)clampi((int)*p + ((out[j] + (1 << (shift - 1))) >> shift), 0, maxv);
+  for (int q = lane; q < NSUB * QB; q += 32) {
+    const int sb = q / QB, r = (q % QB) / Q, c4 = (q % Q) * 4;
+    const unsigned long long dp = __shfl_sync(0xffffffffu, active ? (unsigned long long)dst : 0ull, sb * N);
+    const int st = __shfl_sync(0xffffffffu, stride, sb * N);
+    if (dp) {
+      const int *tv = tbuf + sb * (N * S) + r * S + c4;
+      add4_clip((Px *)dp + (size_t)r * st + c4, tv[0], tv[1], tv[2], tv[3], maxv);
     }
   }
   __syncwarp();
@@ -1131,7 +1115,7 @@ VP9B_DEV void group_itx_add(int *tbuf, const FrameParams &P, int first, int coun
 
 constexpr int kResWarps = 4;
 template <typename Px, typename PT, typename FB>
-__global__ void __launch_bounds__(kResWarps * 32) k_residual(const __grid_constant__ FB B) {
+__global__ void __launch_bounds__(kResWarps * 32, 8) k_residual(const __grid_constant__ FB B) {
   const FrameParams &P = B.f[blockIdx.z];
   if (!P.do_res) return;
   __shared__ int tbuf[kResWarps][32 * 33];
@@ -1158,7 +1142,7 @@ __global__ void __launch_bounds__(kResWarps * 32) k_residual(const __grid_consta
 // so it is taken off the intra wavefront's dependency chain and computed here, one warp per block,
 // into a residual plane; the wavefront (k_intra) then only predicts and adds.
 template <typename Px, typename PT, typename FB>
-__global__ void __launch_bounds__(kResWarps * 32) k_intra_residual(const __grid_constant__ FB B) {
+__global__ void __launch_bounds__(kResWarps * 32, 8) k_intra_residual(const __grid_constant__ FB B) {
   const FrameParams &P = B.f[blockIdx.z];
   if (!P.do_intra) return;
   __shared__ int tbuf[kResWarps][32 * 33];

@@ -283,6 +283,37 @@ VP9B_DEV void txfm1d(const int *in, int *out, bool adst) {
   }
 }
 
+// eob classes of the DCT (vp9_idct.c:119-204: vpx_idct8x8_12, idct16x16_10 / _38, idct32x32_34 / _135):
+// with the default scan the first eob coefficients of a block lie in its top-left K x K corner, so
+// both passes only see K leading inputs.  eob_lead = that K (N when the block is not DCT_DCT or is
+// dense).  The reduced transforms are the full butterflies with literal zeros for the inputs K..N-1:
+// the compiler folds away every operation that only sees zeros, the surviving arithmetic and its
+// rounding are those of the full transform.
+template <int N>
+VP9B_DEV int eob_lead(int tx_type, int eob) {
+  if (tx_type != 0) return N;
+  if (N == 8) return eob <= 12 ? 4 : 8;
+  if (N == 16) return eob <= 10 ? 4 : (eob <= 38 ? 8 : 16);
+  if (N == 32) return eob <= 34 ? 8 : (eob <= 135 ? 16 : 32);
+  return N;
+}
+// one line (row or column) of a block held in shared memory: element j at tb[j * sj]; K leading
+// entries are read, the rest are zero
+template <typename PT, int N, int K>
+VP9B_DEV void itx_line(const int *tb, int sj, bool adst, int *out) {
+  int in[N];
+#pragma unroll
+  for (int j = 0; j < N; j++) in[j] = j < K ? tb[j * sj] : 0;
+  txfm1d<PT, N>(in, out, K < N ? false : adst);
+}
+// dispatch on the (warp-uniform) number of leading entries
+template <typename PT, int N>
+VP9B_DEV void itx_line_lead(const int *tb, int sj, bool adst, int lead, int *out) {
+  if (N >= 8 && lead <= N / 4) itx_line<PT, N, (N >= 8 ? N / 4 : N)>(tb, sj, adst, out);
+  else if (N >= 8 && lead <= N / 2) itx_line<PT, N, (N >= 8 ? N / 2 : N)>(tb, sj, adst, out);
+  else itx_line<PT, N, N>(tb, sj, adst, out);
+}
+
 // one 1-D pass of the 4-point inverse Walsh-Hadamard transform (lossless path)
 VP9B_DEV void iwht4(int a1, int c1_, int d1, int b1, int *o) {
   a1 += c1_;
