@@ -32,6 +32,9 @@
 #include "vp9_lf_warp.cuh"
 
 // occupancy targets of the two register-hungry kernels (A/B builds override them)
+#ifndef VP9B_IRES_MINB
+#define VP9B_IRES_MINB 8
+#endif
 #ifndef VP9B_MC_MINB
 #define VP9B_MC_MINB 5
 #endif
@@ -1142,7 +1145,7 @@ __global__ void __launch_bounds__(kResWarps * 32, 8) k_residual(const __grid_con
 // so it is taken off the intra wavefront's dependency chain and computed here, one warp per block,
 // into a residual plane; the wavefront (k_intra) then only predicts and adds.
 template <typename Px, typename PT, typename FB>
-__global__ void __launch_bounds__(kResWarps * 32, 8) k_intra_residual(const __grid_constant__ FB B) {
+__global__ void __launch_bounds__(kResWarps * 32, VP9B_IRES_MINB) k_intra_residual(const __grid_constant__ FB B) {
   const FrameParams &P = B.f[blockIdx.z];
   if (!P.do_intra) return;
   __shared__ int tbuf[kResWarps][32 * 33];
