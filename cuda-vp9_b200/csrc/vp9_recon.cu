@@ -937,14 +937,15 @@ __global__ void __launch_bounds__(128, sizeof(Px) == 1 ? 8 : 4) k_inter_pred_fla
 // Four consecutive samples of a row: residuals added to the prediction in place (one 32-/64-bit
 // read-modify-write), or stored as a residual plane for the intra wavefront (which then only
 // predicts and adds).
-VP9B_DEV void add4_clip(uint8_t *p, int v0, int v1, int v2, int v3, int) {
-  const uint32_t w = *(const uint32_t *)p;
+template <typename Px> struct Quad;                         // four samples of a row as one load
+template <> struct Quad<uint8_t> { typedef uint32_t T; };
+template <> struct Quad<uint16_t> { typedef uint2 T; };
+VP9B_DEV void add4_clip(uint8_t *p, uint32_t w, int v0, int v1, int v2, int v3, int) {
   const int r0 = clampi((int)(w & 0xff) + v0, 0, 255), r1 = clampi((int)((w >> 8) & 0xff) + v1, 0, 255);
   const int r2 = clampi((int)((w >> 16) & 0xff) + v2, 0, 255), r3 = clampi((int)(w >> 24) + v3, 0, 255);
   *(uint32_t *)p = (uint32_t)r0 | ((uint32_t)r1 << 8) | ((uint32_t)r2 << 16) | ((uint32_t)r3 << 24);
 }
-VP9B_DEV void add4_clip(uint16_t *p, int v0, int v1, int v2, int v3, int maxv) {
-  const uint2 w = *(const uint2 *)p;
+VP9B_DEV void add4_clip(uint16_t *p, uint2 w, int v0, int v1, int v2, int v3, int maxv) {
   const int r0 = clampi((int)(w.x & 0xffff) + v0, 0, maxv), r1 = clampi((int)(w.x >> 16) + v1, 0, maxv);
   const int r2 = clampi((int)(w.y & 0xffff) + v2, 0, maxv), r3 = clampi((int)(w.y >> 16) + v3, 0, maxv);
   *(uint2 *)p = make_uint2((uint32_t)r0 | ((uint32_t)r1 << 16), (uint32_t)r2 | ((uint32_t)r3 << 16));
@@ -994,22 +995,38 @@ VP9B_DEV void iwht_2d_inplace(int *tb, int l, bool xf) {
   }
   __syncwarp();
 }
+// Coefficients of a block -> their positions in the shared-memory block (scan order in the packed
+// stream).  Two phases so that the global loads are in flight while the block is being cleared:
+// coef_preload() issues the first two rounds of loads, coef_scatter() stores them and walks the rest.
+struct CoefPre { int pos[2], val[2]; };
+VP9B_DEV int coef_at(const void *coef_base, int coef_bytes, uint32_t i) {
+  return coef_bytes == 2 ? (int)((const int16_t *)coef_base)[i] : ((const int32_t *)coef_base)[i];
+}
+VP9B_DEV CoefPre coef_preload(const void *coef_base, int coef_bytes, uint32_t coef_off, int eob, const int16_t *scan, int l, int step,
+                              bool on) {
+  CoefPre c;
+#pragma unroll
+  for (int k = 0; k < 2; k++) {
+    const int i = l + k * step;
+    c.pos[k] = -1;
+    c.val[k] = 0;
+    if (on && i < eob) {
+      c.pos[k] = scan[i];
+      c.val[k] = coef_at(coef_base, coef_bytes, coef_off + i);
+    }
+  }
+  return c;
+}
 template <int N>
-VP9B_DEV void scatter_coefs(int *tb, const void *coef_base, int coef_bytes, uint32_t coef_off, int eob, const int16_t *scan,
-                            int l, int step) {
+VP9B_DEV void coef_scatter(int *tb, const CoefPre &c, const void *coef_base, int coef_bytes, uint32_t coef_off, int eob,
+                           const int16_t *scan, int l, int step) {
   constexpr int S = N + 1;
-  if (coef_bytes == 2) {
-    const int16_t *c = (const int16_t *)coef_base + coef_off;
-    for (int i = l; i < eob; i += step) {
-      const int pos = scan[i];
-      tb[(pos / N) * S + (pos % N)] = c[i];
-    }
-  } else {
-    const int32_t *c = (const int32_t *)coef_base + coef_off;
-    for (int i = l; i < eob; i += step) {
-      const int pos = scan[i];
-      tb[(pos / N) * S + (pos % N)] = c[i];
-    }
+#pragma unroll
+  for (int k = 0; k < 2; k++)
+    if (c.pos[k] >= 0) tb[(c.pos[k] / N) * S + (c.pos[k] % N)] = c.val[k];
+  for (int i = l + 2 * step; i < eob; i += step) {
+    const int pos = scan[i];
+    tb[(pos / N) * S + (pos % N)] = coef_at(coef_base, coef_bytes, coef_off + i);
   }
 }
 
@@ -1029,9 +1046,11 @@ VP9B_DEV void warp_itx(int *tbuf, const void *coef_base, int coef_bytes, const v
     for (int q = lane; q < N * Q; q += 32) put4_raw(dst + (size_t)(q / Q) * stride + (q % Q) * 4, a1, a1, a1, a1);
     return;
   }
+  const int16_t *scan = d_scan + scan_offset(tx_size, tx_type);
+  const CoefPre cp = coef_preload(coef_base, coef_bytes, t.coef_off, eob, scan, lane, 32, true);
   for (int i = lane; i < N * S; i += 32) tbuf[i] = 0;
   __syncwarp();
-  scatter_coefs<N>(tbuf, coef_base, coef_bytes, t.coef_off, eob, d_scan + scan_offset(tx_size, tx_type), lane, 32);
+  coef_scatter<N>(tbuf, cp, coef_base, coef_bytes, t.coef_off, eob, scan, lane, 32);
   __syncwarp();
   if (N == 4 && lossless) {
     iwht_2d_inplace(tbuf, lane, lane < 4);
@@ -1090,10 +1109,25 @@ VP9B_DEV void group_itx_add(int *tbuf, const FrameParams &P, int first, int coun
     fill = (rs14<PT>((PT)v1 * (PT)c16) + (1 << (shift - 1))) >> shift;
   }
   const bool xf = active && !dc_only;
+  // the prediction under the blocks: quad q of the warp = (block, row, 4 columns), the block's
+  // destination comes from its first lane.  Loaded now, used after the transforms (one L2 / HBM
+  // round trip hidden behind them).
+  typedef typename Quad<Px>::T QT;
+  constexpr int NQ = NSUB * QB / 32;
+  QT pq[NQ];
+#pragma unroll
+  for (int k = 0; k < NQ; k++) {
+    const int q = lane + 32 * k, sb = q / QB, r = (q % QB) / Q, c4 = (q % Q) * 4;
+    const unsigned long long dp = __shfl_sync(0xffffffffu, active ? (unsigned long long)dst : 0ull, sb * N);
+    const int st = __shfl_sync(0xffffffffu, stride, sb * N);
+    if (dp) pq[k] = *(const QT *)((Px *)dp + (size_t)r * st + c4);
+  }
+  const int16_t *scan = d_scan + scan_offset(t.tx & 3, tx_type);
+  const CoefPre cp = coef_preload(P.coef, sizeof(Px) == 1 ? 2 : 4, t.coef_off, eob, scan, l, N, xf);
   if (active)
     for (int i = l; i < N * S; i += N) tb[i] = fill;
   __syncwarp();
-  if (xf) scatter_coefs<N>(tb, P.coef, sizeof(Px) == 1 ? 2 : 4, t.coef_off, eob, d_scan + scan_offset(t.tx & 3, tx_type), l, N);
+  if (xf) coef_scatter<N>(tb, cp, P.coef, sizeof(Px) == 1 ? 2 : 4, t.coef_off, eob, scan, l, N);
   __syncwarp();
   if (N == 4 && lossless) {
     iwht_2d_inplace(tb, l, xf);
@@ -1102,15 +1136,15 @@ VP9B_DEV void group_itx_add(int *tbuf, const FrameParams &P, int first, int coun
     const int lead = __reduce_max_sync(0xffffffffu, xf ? eob_lead<N>(tx_type, eob) : 0);
     if (lead) itx_2d_inplace<PT, N>(tb, l, xf, lead, (N < 32) && (tx_type & 2), (N < 32) && (tx_type & 1));
   }
-  // add: quad q of the warp = (block, row, 4 columns); the block's destination comes from its first lane
+  // add the residuals to the prediction loaded above
 #pragma unroll
-  for (int q = lane; q < NSUB * QB; q += 32) {
-    const int sb = q / QB, r = (q % QB) / Q, c4 = (q % Q) * 4;
+  for (int k = 0; k < NQ; k++) {
+    const int q = lane + 32 * k, sb = q / QB, r = (q % QB) / Q, c4 = (q % Q) * 4;
     const unsigned long long dp = __shfl_sync(0xffffffffu, active ? (unsigned long long)dst : 0ull, sb * N);
     const int st = __shfl_sync(0xffffffffu, stride, sb * N);
     if (dp) {
       const int *tv = tbuf + sb * (N * S) + r * S + c4;
-      add4_clip((Px *)dp + (size_t)r * st + c4, tv[0], tv[1], tv[2], tv[3], maxv);
+      add4_clip((Px *)dp + (size_t)r * st + c4, pq[k], tv[0], tv[1], tv[2], tv[3], maxv);
     }
   }
   __syncwarp();
@@ -1118,7 +1152,7 @@ VP9B_DEV void group_itx_add(int *tbuf, const FrameParams &P, int first, int coun
 
 constexpr int kResWarps = 4;
 template <typename Px, typename PT, typename FB>
-__global__ void __launch_bounds__(kResWarps * 32, 8) k_residual(const __grid_constant__ FB B) {
+__global__ void __launch_bounds__(kResWarps * 32, sizeof(Px) == 1 ? 8 : 6) k_residual(const __grid_constant__ FB B) {
   const FrameParams &P = B.f[blockIdx.z];
   if (!P.do_res) return;
   __shared__ int tbuf[kResWarps][32 * 33];
@@ -1238,7 +1272,8 @@ VP9B_DEV void warp_intra_predict(const FrameParams &P, IntraEdge &E, const vp9b_
     if (have_left) { for (int i = lane; i < bs; i += 32) s += l[i]; cnt += bs; }
 #pragma unroll
     for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    dc = cnt ? (s + (cnt >> 1)) / cnt : base;
+    // cnt is bs or 2 * bs: the division of dc_predictor (intrapred.c) is a shift
+    dc = cnt ? (s + (cnt >> 1)) >> (2 + tx_size + (have_top & have_left)) : base;
   }
 #define AT(i) ((i) < 0 ? tl : a[i])   /* above with above[-1] = top-left */
 #define LT(i) ((i) < 0 ? tl : l[i])   /* left with left[-1] = top-left  */
