@@ -171,7 +171,7 @@ template <typename Px, bool SUB> struct LfCtx {
   int stride[3];            // plane strides in samples
   const vp9b_lfm *M, *Mn;   // masks of this superblock and of the next one in the row
   const uint8_t *lf_lim, *lf_mblim;
-  uint16_t *dset;           // [3][8] per plane, per 8-row band: vertical operations (bit k: x = 4k) that depend on the left edge
+  uint16_t *dset;           // [3][8] per plane, per 8-row band: vertical operations that depend on the left edge (lf_plan_unit)
   int sbr, sbc, sb_cols, mi_rows, bd;
   bool has_next, has_top;
 };
@@ -362,7 +362,14 @@ LF_HD bool lf_plan_unit(const vp9b_lfm &M, bool has_left, int u, uint16_t *dset)
   uint32_t m16, m8, m4, m4i;
   lf_band_masks_v(M, uvsub, band, m16, m8, m4, m4i);
   const uint32_t d = lf_dependent_set(m16, m8, m4, m4i, nb, has_left);
-  dset[plane * 8 + band] = (uint16_t)d;
+  // stored per block column: low byte = 8-aligned edges, high byte = inner edges (the phase functions
+  // of every sample row of the band read it: split once here, not once per row and phase)
+  uint32_t de = 0, di = 0;
+  for (int c = 0; c < 8; c++) {
+    de |= ((d >> (2 * c)) & 1) << c;
+    di |= ((d >> (2 * c + 1)) & 1) << c;
+  }
+  dset[plane * 8 + band] = (uint16_t)(de | (di << 8));
   return (d >> (2 * nb - 2)) != 0;
 }
 template <typename Px, bool SUB> struct LfPlanUnits { static constexpr int value = 8 + 2 * (LfGeom<Px, SUB>::nC >> 3); };
@@ -438,11 +445,7 @@ LF_HD void lf_phase_vertical(const LfCtx<Px, SUB> &C, int tid, bool dependent) {
   const bool uvsub = p && SUB;
   if (!lf_row_valid(uvsub, y, C.sbr * 8, C.mi_rows)) return;
   const uint32_t d = C.dset[p * 8 + (y >> 3)];
-  uint32_t de = 0, di = 0;   // dependent set split into 8-aligned / inner edges per block column
-  for (int c = 0; c < 8; c++) {
-    de |= ((d >> (2 * c)) & 1) << c;
-    di |= ((d >> (2 * c + 1)) & 1) << c;
-  }
+  const uint32_t de = d & 0xff, di = d >> 8;   // dependent set: 8-aligned / inner edges per block column
   const uint32_t se = (dependent ? de : ~de) & 0xfe, si = (dependent ? di : ~di) & 0xff;
   lf_v_row<Px>(*C.M, uvsub, y, lf_tile_at(C, p, y, 0), se, si, C.lf_lim, C.lf_mblim, C.bd);
 }

@@ -417,11 +417,7 @@ LF_HD void lfw_phase_vertical(const LfwCtx &C, int lane, bool dependent) {
   const bool uvsub = p != 0;
   if (!lf_row_valid(uvsub, y, C.sbr * 8, C.mi_rows)) return;
   const uint32_t d = C.dset[p * 8 + (y >> 3)];
-  uint32_t de = 0, di = 0;
-  for (int c = 0; c < 8; c++) {
-    de |= ((d >> (2 * c)) & 1) << c;
-    di |= ((d >> (2 * c + 1)) & 1) << c;
-  }
+  const uint32_t de = d & 0xff, di = d >> 8;
   const uint32_t se = (dependent ? de : ~de) & 0xfe, si = (dependent ? di : ~di) & 0xff;
   lfw_v_rows(*C.M, uvsub, y, lfw_at(C, p, y, 0), p ? LfwGeom::pitchC : LfwGeom::pitchY, se, si, C.lf_lim, C.lf_mblim);
 }
@@ -473,7 +469,7 @@ LF_HD void lfw_phase_horizontal(const LfwCtx &C, int lane, int part) {
 LF_HD bool lfw_plan_deep(const uint16_t *dset) {
   uint32_t any = 0;
   for (int i = 0; i < 24; i++) any |= dset[i];
-  return (any >> 2) != 0;
+  return (any & 0xfefe) != 0;   // low byte: 8-aligned edges, high byte: inner edges, one bit per block column
 }
 
 // Stores (same split as lf_phase_store): part 0 = last block column of every plane (rows r0 .. n-1-keep)

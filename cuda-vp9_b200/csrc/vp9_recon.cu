@@ -41,6 +41,9 @@
 #ifndef VP9B_INTRA_MINB
 #define VP9B_INTRA_MINB 1
 #endif
+#ifndef VP9B_INTRA_DENSE
+#define VP9B_INTRA_DENSE 4      // CTAs per SM of the k_intra variant used for large batches
+#endif
 #ifndef VP9B_LF_MINB
 #define VP9B_LF_MINB 5
 #endif
@@ -1377,7 +1380,9 @@ VP9B_DEV uint32_t ld_relaxed(const uint32_t *p) {
   return v;
 }
 VP9B_DEV void wait_progress(const uint32_t *p, uint32_t base, int need) {
-  // poll with relaxed loads (no L1 invalidation per poll), then one acquire to order the data reads
+  // usually satisfied on arrival: one acquire load (a single L2 round trip) decides; otherwise poll
+  // with relaxed loads (no L1 invalidation per poll), then one acquire to order the data reads
+  if ((int)(ld_acquire(p) - base) >= need) return;
   while ((int)(ld_relaxed(p) - base) < need) __nanosleep(20);
   (void)ld_acquire(p);
 }
@@ -2514,13 +2519,13 @@ static int launch_batch(vp9gpu_ctx *const *ctxs, FB &B, int n) {
     const unsigned abit = (sizeof(Px) == 1 ? 1u : 2u) << abase;
     if (!(ctx->attr_done & abit)) {
       CK(cudaFuncSetAttribute((k_intra<Px, PT, FB, 1>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ismem));
-      CK(cudaFuncSetAttribute((k_intra<Px, PT, FB, 4>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ismem));
+      CK(cudaFuncSetAttribute((k_intra<Px, PT, FB, VP9B_INTRA_DENSE>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ismem));
       ctx->attr_done |= abit;
     }
     k_intra_residual<Px, PT, FB><<<dim3(g_ires, 1, n), kResWarps * 32, 0, st>>>(B);
     ctx->launches++;
     if (prof) cudaEventRecord(ctx->prof_ev[4], st);
-    if (dense) k_intra<Px, PT, FB, 4><<<dim3(g_intra, 1, n), kWaveWarps * 32, ismem, st>>>(B);
+    if (dense) k_intra<Px, PT, FB, VP9B_INTRA_DENSE><<<dim3(g_intra, 1, n), kWaveWarps * 32, ismem, st>>>(B);
     else k_intra<Px, PT, FB, 1><<<dim3(g_intra, 1, n), kWaveWarps * 32, ismem, st>>>(B);
     ctx->launches++;
   } else if (prof) {

@@ -13,6 +13,12 @@
 
 using namespace vp9b;
 
+// threads of one phase (between two barriers) run in index order, or -- schedule bit 30 -- in reverse
+// order: a phase whose threads touch disjoint samples must not care (this is what catches a wrong
+// split of a luma row / column between its two threads)
+static bool g_rev = false;
+#define FOR_TID for (int t_ = 0, tid = 0; t_ < G::NT && ((tid = g_rev ? G::NT - 1 - t_ : t_), true); t_++)
+
 template <typename Px, bool SUB>
 struct Worker {
   typedef LfGeom<Px, SUB> G;
@@ -48,6 +54,8 @@ static int run(const vp9b_frame_hdr *h, const uint8_t *base, uint16_t *const pla
   std::vector<Worker<Px, SUB>> W(sb_cols);
   std::vector<int> edge_done(sb_cols, 0);     // rows whose F_edge this worker has published
   *n_chain = 0;
+  g_rev = (schedule >> 30) & 1;
+  schedule &= ~(1u << 30);
   auto set_row = [&](Worker<Px, SUB> &w, int r) {
     LfCtx<Px, SUB> &C = w.C;
     C.tile = w.buf[r & 1].data();
@@ -74,7 +82,7 @@ static int run(const vp9b_frame_hdr *h, const uint8_t *base, uint16_t *const pla
     }
     // prologue: the first superblock is fetched and committed before the loop
     set_row(w, 0);
-    for (int tid = 0; tid < G::NT; tid++) {
+    FOR_TID {
       Vec(&pre)[G::kPre] = *(Vec(*)[G::kPre]) & w.pre[(size_t)tid * G::kPre];
       lf_phase_prefetch<Px, SUB>(C.g, C.stride, C.has_next, tid, pre);
       lf_phase_commit<Px, SUB>(C, tid, pre);
@@ -82,7 +90,7 @@ static int run(const vp9b_frame_hdr *h, const uint8_t *base, uint16_t *const pla
   }
   auto dependent = [&](Worker<Px, SUB> &w) {
     if (w.C.sbc == 0) return;
-    for (int tid = 0; tid < G::NT; tid++) { lf_phase_merge_left(w.C, tid); lf_phase_vertical(w.C, tid, true); }
+    FOR_TID { lf_phase_merge_left(w.C, tid); lf_phase_vertical(w.C, tid, true); }
   };
   // one step of a worker; returns false if its wait is not satisfied yet
   auto step = [&](int c) -> bool {
@@ -101,29 +109,29 @@ static int run(const vp9b_frame_hdr *h, const uint8_t *base, uint16_t *const pla
       if (next_row) {      // fetch of the next superblock is issued first
         Px *g[3];
         for (int p = 0; p < 3; p++) g[p] = w.base[p] + (size_t)(w.r + 1) * (p ? G::nC : 64) * stride[p];
-        for (int tid = 0; tid < G::NT; tid++)
+        FOR_TID
           lf_phase_prefetch<Px, SUB>(g, C.stride, C.has_next, tid, *(Vec(*)[G::kPre]) & w.pre[(size_t)tid * G::kPre]);
       }
-      for (int tid = 0; tid < G::NT; tid++) lf_phase_vertical(C, tid, false);
+      FOR_TID lf_phase_vertical(C, tid, false);
       if (w.chain) dependent(w);
-      for (int tid = 0; tid < G::NT; tid++) lf_phase_horizontal(C, tid, 0);
+      FOR_TID lf_phase_horizontal(C, tid, 0);
       if (C.has_next)
-        for (int tid = 0; tid < G::NT; tid++) lf_phase_next_left_edge(C, tid);
-      for (int tid = 0; tid < G::NT; tid++) lf_phase_store(C, tid, 0, keep);
+        FOR_TID lf_phase_next_left_edge(C, tid);
+      FOR_TID lf_phase_store(C, tid, 0, keep);
       edge_done[c] = w.r + 1;
       w.part = 1;
       return true;
     }
     if (!w.chain && c > 0 && edge_done[c - 1] <= w.r) return false;
     if (!w.chain) dependent(w);
-    for (int tid = 0; tid < G::NT; tid++) lf_phase_horizontal(C, tid, 1);
-    for (int tid = 0; tid < G::NT; tid++) lf_phase_store(C, tid, 1, keep);
+    FOR_TID lf_phase_horizontal(C, tid, 1);
+    FOR_TID lf_phase_store(C, tid, 1, keep);
     if (next_row) {
       Px *nt = w.buf[(w.r + 1) & 1].data();
-      for (int tid = 0; tid < G::NT; tid++) lf_phase_carry(C, nt, tid);
+      FOR_TID lf_phase_carry(C, nt, tid);
       LfCtx<Px, SUB> N = C;
       N.tile = nt;
-      for (int tid = 0; tid < G::NT; tid++) lf_phase_commit<Px, SUB>(N, tid, *(Vec(*)[G::kPre]) & w.pre[(size_t)tid * G::kPre]);
+      FOR_TID lf_phase_commit<Px, SUB>(N, tid, *(Vec(*)[G::kPre]) & w.pre[(size_t)tid * G::kPre]);
     }
     w.part = 0;
     w.r++;

@@ -16,6 +16,10 @@ import synth_packed as sp
 from conftest import ROOT, clip_path
 
 _LIB = None
+# schedule bit 30: the threads of every phase run in reverse index order (the second thread of a luma
+# row / column before the first one): a split of a row between two threads that is not independent
+# would show
+REV = 1 << 30
 
 
 def emu():
@@ -89,7 +93,7 @@ def run_stream(name, max_frames=4, emu_fn=None):
                 a.set_frame(s, b.get_frame(s, w, h, bd, sx, sy), bd, sx, sy)
             a.submit(packed, stop_stage=3)
             if hdr.lf_level:
-                check_frame(packed, raw_planes(a, hdr.dst_slot), raw_planes(b, hdr.dst_slot), (0, 1, 7), "%s frame %d" % (name, n), emu_fn)
+                check_frame(packed, raw_planes(a, hdr.dst_slot), raw_planes(b, hdr.dst_slot), (0, 1, 7, REV | 0, REV | 5), "%s frame %d" % (name, n), emu_fn)
                 n += 1
             if n >= max_frames:
                 return n
@@ -158,7 +162,7 @@ def random_mask_case(bd, ss, w, h, density, emu_fn=None):
         pre = raw_planes(a, 3)
         post = raw_planes(b, 3)
         changed += sum(int((x != y).sum()) for x, y in zip(pre, post))
-        chains.append(check_frame(packed, pre, post, (0, 1, 11, 12), "random bd%d ss%d %dx%d d%.2f seed %d" % (bd, ss, w, h, density, seed), emu_fn))
+        chains.append(check_frame(packed, pre, post, (0, 1, 11, 12, REV | 0, REV | 13), "random bd%d ss%d %dx%d d%.2f seed %d" % (bd, ss, w, h, density, seed), emu_fn))
     assert changed > 1000            # the filters really did something
     if density > 1.0:
         assert max(chains) > 0      # all-4x4 masks: every superblock takes the serialised (chain) path
