@@ -52,6 +52,7 @@ using std::max;
 using std::min;
 inline int lf_ffs(uint32_t v) { return v ? __builtin_ctz(v) + 1 : 0; }
 inline int lf_clz(uint32_t v) { return v ? __builtin_clz(v) : 32; }
+inline int lf_absd(int a, int b) { return a < b ? b - a : a - b; }
 template <typename V> inline V lf_ldg(const void *p) { V v; memcpy(&v, p, sizeof(V)); return v; }
 template <typename V> inline void lf_stg(void *p, const V &v) { memcpy(p, &v, sizeof(V)); }
 }  // namespace vp9b
@@ -62,6 +63,11 @@ typedef uint2 lf_u2;
 typedef uint4 lf_u4;
 LF_HD int lf_ffs(uint32_t v) { return __ffs(v); }
 LF_HD int lf_clz(uint32_t v) { return __clz(v); }
+#ifdef VP9B_LF_NOSAD
+LF_HD int lf_absd(int a, int b) { return a < b ? b - a : a - b; }
+#else
+LF_HD int lf_absd(int a, int b) { return (int)__sad(a, b, 0u); }   // |a - b| in one instruction
+#endif
 template <typename V> LF_HD V lf_ldg(const void *p) { return __ldcg((const V *)p); }   // L2: written by other SMs
 template <typename V> LF_HD void lf_stg(void *p, const V &v) { __stcg((V *)p, v); }
 }  // namespace vp9b
@@ -85,18 +91,18 @@ LF_HD void lf_px(Px *s, int step, int size, int blimit, int limit, int thresh, i
   const int q0 = s[0], q1 = s[step], q2 = s[2 * step], q3 = s[3 * step];
   const int lim16 = limit << sh, blim16 = blimit << sh, one = 1 << sh;
   // masks as max chains: no short-circuit branches, |p1-p0| and |q1-q0| shared by all of them
-  const int d10p = lf_abs(p1 - p0), d10q = lf_abs(q1 - q0);
-  const int dmax = max(max(max(lf_abs(p3 - p2), lf_abs(p2 - p1)), max(lf_abs(q2 - q1), lf_abs(q3 - q2))), max(d10p, d10q));
-  const bool fm = dmax <= lim16 && lf_abs(p0 - q0) * 2 + (lf_abs(p1 - q1) >> 1) <= blim16;
+  const int d10p = lf_absd(p1, p0), d10q = lf_absd(q1, q0);
+  const int dmax = max(max(max(lf_absd(p3, p2), lf_absd(p2, p1)), max(lf_absd(q2, q1), lf_absd(q3, q2))), max(d10p, d10q));
+  const bool fm = dmax <= lim16 && lf_absd(p0, q0) * 2 + (lf_absd(p1, q1) >> 1) <= blim16;
   if (!fm) return;  // filter_mask == 0: every variant leaves the samples untouched
   bool flat = false;
   if (size >= 8)
-    flat = max(max(max(d10p, d10q), max(lf_abs(p2 - p0), lf_abs(q2 - q0))), max(lf_abs(p3 - p0), lf_abs(q3 - q0))) <= one;
+    flat = max(max(max(d10p, d10q), max(lf_absd(p2, p0), lf_absd(q2, q0))), max(lf_absd(p3, p0), lf_absd(q3, q0))) <= one;
   if (size == 16 && flat) {
     const int p7 = s[-8 * step], p6 = s[-7 * step], p5 = s[-6 * step], p4 = s[-5 * step];
     const int q4 = s[4 * step], q5 = s[5 * step], q6 = s[6 * step], q7 = s[7 * step];
-    const bool flat2 = max(max(max(lf_abs(p4 - p0), lf_abs(q4 - q0)), max(lf_abs(p5 - p0), lf_abs(q5 - q0))),
-                           max(max(lf_abs(p6 - p0), lf_abs(q6 - q0)), max(lf_abs(p7 - p0), lf_abs(q7 - q0)))) <= one;
+    const bool flat2 = max(max(max(lf_absd(p4, p0), lf_absd(q4, q0)), max(lf_absd(p5, p0), lf_absd(q5, q0))),
+                           max(max(lf_absd(p6, p0), lf_absd(q6, q0)), max(lf_absd(p7, p0), lf_absd(q7, q0)))) <= one;
     if (flat2) {
       // 15-tap [1,1,1,1,1,1,1,2,1,1,1,1,1,1,1] with edge replication, evaluated from prefix
       // sums so that the 14 outputs are independent of each other (short dependency chain)
@@ -260,6 +266,26 @@ LF_HD void lf_v_row(const vp9b_lfm &M, bool uvsub, int y, Px *row, uint32_t sel_
   uint64_t lv_own, lv_pair;
   memcpy(&lv_own, &M.lfl_y[lrow * 8], 8);
   memcpy(&lv_pair, &M.lfl_y[prow * 8], 8);
+#ifndef VP9B_LF_MULTICALL
+  while (all) {
+    const int c = lf_ffs(all) - 1;
+    all &= all - 1;
+    const int lo = (int)(lv_own >> (c * lsh)) & 0xff;
+    const int lv16 = ((m16n >> c) & 1) ? ((int)(lv_pair >> (c * lsh)) & 0xff) : lo;
+    Px *s = row + c * 8;
+    // the operations of this block column in the reference's order (16, 8, 4, inner) through ONE
+    // inlined copy of the filter (rows of different bands reconverge in it; a third less code than a copy
+    // per size at the same speed; VP9B_LF_MULTICALL keeps the copies for A/B)
+    uint32_t ops = ((m16 >> c) & 1) | (((m8 >> c) & 1) << 1) | (((m4 >> c) & 1) << 2) | (((m4i >> c) & 1) << 3);
+#pragma unroll 1
+    while (ops) {
+      const int k = lf_ffs(ops) - 1;
+      ops &= ops - 1;
+      const int lv = k == 0 ? lv16 : lo;
+      lf_px<Px>(s + (k == 3 ? 4 : 0), 1, k == 0 ? 16 : (k == 1 ? 8 : 4), lf_mblim[lv], lf_lim[lv], lv >> 4, bd);
+    }
+  }
+#else
   while (all) {
     const int c = lf_ffs(all) - 1;
     all &= all - 1;
@@ -273,6 +299,7 @@ LF_HD void lf_v_row(const vp9b_lfm &M, bool uvsub, int y, Px *row, uint32_t sel_
     if ((m4 >> c) & 1) lf_px<Px>(s, 1, 4, lf_mblim[lo], lf_lim[lo], lo >> 4, bd);
     if ((m4i >> c) & 1) lf_px<Px>(s + 4, 1, 4, lf_mblim[lo], lf_lim[lo], lo >> 4, bd);
   }
+#endif
 }
 // is the band pair of sample row y inside the frame (the vertical pass walks band pairs)
 LF_HD bool lf_row_valid(bool uvsub, int y, int mi_row, int mi_rows) {
@@ -317,6 +344,24 @@ LF_HD void lf_h_unit(const LfHMasks &H, const vp9b_lfm &M, int x, int r, Px *col
   Px *s = col + r * 8 * ts;
   const uint8_t *lfl = &M.lfl_y[(r * H.lstep) * 8];
   const int lvl = lfl[c * H.lstep];
+#ifndef VP9B_LF_MULTICALL
+  int lv = lvl, size = k16 ? 16 : (k8 ? 8 : (k4 ? 4 : 0));
+  if (k16) {
+    const uint32_t row16 = (uint32_t)(H.a16 >> (r << H.rsh)) & 0xff;
+    const uint32_t below = ~row16 & ((1u << c) - 1);          // zero bits below c
+    const int run = below ? c - 1 - (31 - lf_clz(below)) : c;
+    if (run & 1) lv = lfl[(c - 1) * H.lstep];
+  }
+  // edge, then the inner edge (unless 16-wide), through one inlined copy of the filter
+  uint32_t ops = (size ? 1u : 0u) | ((!k16 && ki) ? 2u : 0u);
+#pragma unroll 1
+  while (ops) {
+    const int k = lf_ffs(ops) - 1;
+    ops &= ops - 1;
+    const int l = k ? lvl : lv;
+    lf_px<Px>(s + (k ? 4 * ts : 0), ts, k ? 4 : size, lf_mblim[l], lf_lim[l], l >> 4, bd);
+  }
+#else
   if (k16) {
     const uint32_t row16 = (uint32_t)(H.a16 >> (r << H.rsh)) & 0xff;
     const uint32_t below = ~row16 & ((1u << c) - 1);          // zero bits below c
@@ -329,6 +374,7 @@ LF_HD void lf_h_unit(const LfHMasks &H, const vp9b_lfm &M, int x, int r, Px *col
     lf_px<Px>(s, ts, 4, lf_mblim[lvl], lf_lim[lvl], lvl >> 4, bd);
   }
   if (!k16 && ki) lf_px<Px>(s + 4 * ts, ts, 4, lf_mblim[lvl], lf_lim[lvl], lvl >> 4, bd);
+#endif
 }
 // one thread walks a whole sample column: only the block rows that have an edge are visited
 template <typename Px>
