@@ -285,7 +285,7 @@ def stage_bytes(np, packed, hdrs):
 class Replay:
     """S reconstruction contexts replaying one clip's packed buffers from HBM, K streams per launch."""
 
-    def __init__(self, vb, torch, local, clip, S, K, stop_stage=0, parsed=None, stagger=True):
+    def __init__(self, vb, torch, local, clip, S, K, stop_stage=0, parsed=None):
         import numpy as np
         self.vb, self.torch, self.S = vb, torch, S
         if parsed is None:
@@ -304,35 +304,9 @@ class Replay:
         K = max(1, min(K, S, vb.MAX_BATCH))
         self.K = K
         self.groups = [list(range(g, min(g + K, S))) for g in range(0, S, K)]
-        # Launch groups are independent sets of streams: they do not start on the same frame.  Group g
-        # begins its (endless) replay at the g-th safe entry point of the clip -- a frame without
-        # references after which no frame refers to a pool slot written before it (a key frame) -- so
-        # that the key frames of one group (latency-bound intra wavefront) meet the inter frames of the
-        # others instead of each other.  Every stream still decodes every frame of the clip per pass.
-        self.entry = self.entry_points() if stagger else [0]
-        self.order = []
-        for gi in range(len(self.groups)):
-            k = self.entry[gi % len(self.entry)]
-            self.order.append(list(range(k, self.n_coded)) + list(range(k)))
         self.packs = [[vb.GpuRecon.make_multi([self.ctxs[ci] for ci in grp], [(self.dptr[ci][f], self.hdrs[f]) for ci in grp])
-                       for f in self.order[gi]] for gi, grp in enumerate(self.groups)]
+                       for f in range(self.n_coded)] for grp in self.groups]
         self.bytes_tot, self.bytes_frame = stage_bytes(np, self.packed, self.hdrs)
-
-    def entry_points(self):
-        pts = [0]
-        for k in range(1, self.n_coded):
-            if not self.hdrs[k].intra_only:
-                continue
-            written, ok = set(), True
-            for j in range(k, self.n_coded):
-                h = self.hdrs[j]
-                if not h.intra_only and any(r.slot >= 0 and r.width and r.slot not in written for r in h.ref):
-                    ok = False
-                    break
-                written.add(h.dst_slot)
-            if ok:
-                pts.append(k)
-        return pts
 
     def submit_pass(self, gi):
         for pk in self.packs[gi]:
@@ -520,7 +494,7 @@ def run_ours(args, rank, world, local):
                        "frame into pinned host memory, %d host threads / streams per rank, %d clip passes each" % (E, e2e_passes)}
 
     # ---- recon-only replay
-    rp = Replay(vb, torch, local, args.clip, S, args.batch, args.stop_stage, parsed=parsed, stagger=not args.no_stagger)
+    rp = Replay(vb, torch, local, args.clip, S, args.batch, args.stop_stage, parsed=parsed)
     args.batch = rp.K
     sampler = ClockSampler(local)
     ms, host_submit_ms, launches = rp.timed(args.steps, args.warmup, P, barrier, sampler)
@@ -581,7 +555,6 @@ def run_ours(args, rank, world, local):
                 "parallelism": "independent streams, %d per GPU, %d per kernel launch, no collective" % (S, K),
                 "l2": ("working set %d MB per GPU (> 126 MB L2): %d streams x (frame pool + packed buffers)" %
                        (S * (12 * frame_bytes + sum(len(p) for p in rp.packed)) >> 20, S)),
-                "group_first_frame": [o[0] for o in rp.order],   # launch groups enter the clip at different key frames
                 "host_parse_fps_1thread": rp.shown / rp.parse_s, "host_submit_ms_per_step": host_submit_ms,
                 "timed_region_s": ms * 1e-3}
     rp.close()
@@ -630,7 +603,6 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-others", action="store_true")
-    ap.add_argument("--no-stagger", action="store_true", help="every launch group starts its replay at frame 0 (A/B)")
     ap.add_argument("--stop-stage", type=int, default=0, help=argparse.SUPPRESS)
     args = ap.parse_args()
     from cuda_vp9_b200 import sharding

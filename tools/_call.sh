@@ -1,15 +1,4 @@
 mkdir -p gpurun_out
-nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm --format=csv > gpurun_out/gpu.txt 2>&1
-timeout 900 python -m pytest tests -m gpu -x -q --timeout 180 > gpurun_out/pytest_gpu_final.log 2>&1
-echo "pytest rc=$?" >> gpurun_out/pytest_gpu_final.log
-tail -3 gpurun_out/pytest_gpu_final.log
-timeout 300 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" > gpurun_out/smoke_final.log 2>&1; tail -1 gpurun_out/smoke_final.log
-( time timeout 900 python bench.py > gpurun_out/r02_bench_4k.json 2> gpurun_out/r02_bench_4k.err ) 2> gpurun_out/r02_bench_time.txt
-echo "bench rc=$?"; tail -c 300 gpurun_out/r02_bench_4k.json
-( time timeout 600 python bench.py --impl reference > gpurun_out/r02_ref_4k.json 2> gpurun_out/r02_ref_4k.err ) 2>> gpurun_out/r02_bench_time.txt
-echo "ref rc=$?"; tail -c 300 gpurun_out/r02_ref_4k.json
-for clip in bench_1440p bench_4k; do
-  timeout 300 python tools/replay.py $clip 1 --stages > gpurun_out/r02_stages_${clip#bench_}.txt 2>&1
-done
-bash tools/profile_r02.sh
-cp cuda-vp9_b200/libvp9b200.so gpurun_out/lib_for_prof_r02.so
+L=$PWD/build/libvp9b200
+VP9B_LIB=${L}_aw.so timeout 600 python -m pytest tests/test_gpu_parity.py tests/test_synthetic.py -m gpu -x -q --timeout 120 > gpurun_out/pytest_aw.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_aw.log; tail -2 gpurun_out/pytest_aw.log
+bash tools/ab.sh "cur|VP9B_LIB=${L}_cur.so|--steps 8" "aw|VP9B_LIB=${L}_aw.so|--steps 8" "cur2|VP9B_LIB=${L}_cur.so|--steps 8" "aw2|VP9B_LIB=${L}_aw.so|--steps 8" "aw-1440|VP9B_LIB=${L}_aw.so|--clip 1440p --streams 32" "aw-hbd|VP9B_LIB=${L}_aw.so|--clip hbd1080 --streams 32"
