@@ -1,4 +1,3 @@
 mkdir -p gpurun_out
-L=$PWD/build/libvp9b200
-VP9B_LIB=${L}_iq.so timeout 400 python -m pytest tests/test_gpu_parity.py tests/test_synthetic.py -m gpu -x -q --timeout 120 > gpurun_out/pytest_iq.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_iq.log; tail -4 gpurun_out/pytest_iq.log
-bash tools/ab.sh "iq|VP9B_LIB=${L}_iq.so|--steps 8" "head||--steps 8" "iq-hbd|VP9B_LIB=${L}_iq.so|--clip hbd1080 --streams 32"
+timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 10 --warmup 3 --no-cpu --no-others > gpurun_out/r02_bench_4k_2gpu.json 2> gpurun_out/r02_bench_4k_2gpu.err
+echo "rc=$?"; tail -c 400 gpurun_out/r02_bench_4k_2gpu.json
