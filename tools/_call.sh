@@ -1,3 +1,3 @@
 mkdir -p gpurun_out
-timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 10 --warmup 3 --no-cpu --no-others > gpurun_out/r02_bench_4k_2gpu.json 2> gpurun_out/r02_bench_4k_2gpu.err
-echo "rc=$?"; tail -c 400 gpurun_out/r02_bench_4k_2gpu.json
+timeout 400 python -m pytest tests/test_gpu_parity.py tests/test_synthetic.py tests/test_ref_binding.py -m gpu -x -q --timeout 120 > gpurun_out/pytest_last.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_last.log; tail -3 gpurun_out/pytest_last.log
+timeout 200 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" 2>&1 | tail -1
