@@ -38,6 +38,26 @@ def emu():
     return _LIB
 
 
+_LIB_MC = None
+
+
+def emu_multicall():
+    """The same emulator compiled with -DVP9B_LF_MULTICALL: the A/B variant of the edge walks (one
+    inlined copy of the filter per size instead of one per walk) stays bit-exact too."""
+    global _LIB_MC
+    if _LIB_MC is None:
+        src = os.path.join(ROOT, "tests", "emul", "lf_emul.cc")
+        hdr = os.path.join(ROOT, "cuda-vp9_b200", "csrc", "vp9_lf_sb.cuh")
+        out = os.path.join(ROOT, "tests", "emul", "_build_lfemu_mc.so")
+        if not os.path.exists(out) or os.path.getmtime(out) < max(os.path.getmtime(src), os.path.getmtime(hdr)):
+            subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-Wno-unknown-pragmas", "-DVP9B_LF_MULTICALL",
+                                   "-I" + os.path.join(ROOT, "include"), src, "-o", out])
+        L = C.CDLL(out)
+        L.lfemu_frame.argtypes = emu().lfemu_frame.argtypes
+        _LIB_MC = L
+    return _LIB_MC
+
+
 def raw_planes(rec, slot):
     L = ref_decoder.lib()
     L.vp9ref_plane.restype = C.POINTER(C.c_uint16)
@@ -166,3 +186,8 @@ def random_mask_case(bd, ss, w, h, density, emu_fn=None):
     assert changed > 1000            # the filters really did something
     if density > 1.0:
         assert max(chains) > 0      # all-4x4 masks: every superblock takes the serialised (chain) path
+
+
+@pytest.mark.parametrize("bd,ss,w,h,density", [(8, 1, 328, 200, 1.0), (10, 1, 200, 264, 0.5), (8, 0, 200, 136, 2.0)])
+def test_multicall_variant_equals_oracle(bd, ss, w, h, density):
+    random_mask_case(bd, ss, w, h, density, emu_fn=emu_multicall().lfemu_frame)
